@@ -1,0 +1,95 @@
+/* valida_b200 — C ABI of the B200-native STARK prover backend for Valida's Machine::prove().
+ *
+ * The reference (valida-xyz/valida @ 5058de85) has NO FFI boundary: its only seam
+ * is the Rust generic `StarkConfig::Pcs: UnivariatePcsWithLde<..>` (machine/src/config.rs:7-31) plus
+ * the free functions `generate_permutation_trace` (machine/src/chip.rs:121) and `quotient`
+ * (machine/src/quotient.rs:18) that `Machine::prove` (machine/src/machine.rs:22-24; body
+ * derive/src/lib.rs:275-446) calls directly.  Each entry point below names the reference interface
+ * it replaces; INTEGRATION.md shows the Rust `extern "C"` binding a maintainer would add.
+ *
+ * Conventions: every function returns int32_t status (0 = OK, <0 = error; text via
+ * vgpu_last_error).  No exceptions/panics cross the boundary.  A context is single-threaded: one
+ * context per device/stream.  BabyBear words cross as uint32_t in the representation named by a
+ * `repr` argument so that a Rust caller can pass `RowMajorMatrix<BabyBear>.values` zero-copy
+ * (p3-baby-bear stores Montgomery form, R = 2^32).  Host matrices are ROW-major
+ * (p3_matrix::dense::RowMajorMatrix); device matrices are column-major Montgomery words.
+ */
+#ifndef VALIDA_B200_H
+#define VALIDA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGPU_REPR_CANONICAL 0 /* 0 <= x < p */
+#define VGPU_REPR_MONTY_R32 1 /* x * 2^32 mod p  (p3_baby_bear::BabyBear { value }) */
+
+#define VGPU_NUM_CHIPS 14 /* basic/src/lib.rs:151-166: cpu, program, mem, add, sub, mul, div, shift, lt, com, bitwise, output, range, static_data */
+
+typedef struct vgpu_ctx vgpu_ctx;
+typedef struct vgpu_dmat vgpu_dmat;               /* device matrix (column-major, Montgomery) */
+typedef struct vgpu_prover_data vgpu_prover_data; /* <ValMmcs as Mmcs>::ProverData: LDEs + digest layers, device resident */
+typedef struct vgpu_traces vgpu_traces;           /* host witness of one machine run */
+
+/* RowMajorMatrix<Val> view (caller-owned host memory). */
+typedef struct vgpu_matrix {
+    const uint32_t* data;
+    uint64_t height;
+    uint64_t width;
+} vgpu_matrix;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* `cuda_stream` may be NULL (library-owned stream) or a cudaStream_t to enqueue on (e.g. torch's). */
+int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out);
+void vgpu_ctx_destroy(vgpu_ctx* ctx);
+const char* vgpu_last_error(const vgpu_ctx* ctx);
+int32_t vgpu_ctx_synchronize(vgpu_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t vgpu_ctx_launch_count(const vgpu_ctx* ctx);
+/* Poseidon instance of the DuplexChallenger, as the Rust side builds it
+ * (basic/src/bin/valida.rs:360-365,382,397): 480 round constants (canonical), 16x16 MDS matrix
+ * row-major or NULL for CosetMds<_,16>::default(). */
+int32_t vgpu_set_challenger(vgpu_ctx* ctx, const uint32_t round_constants[480], const uint32_t* mds_16x16_or_null);
+
+/* ---- device matrices (K12 staging: H2D + row-major -> column-major + repr conversion) ---------- */
+int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out);
+int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint32_t* host_row_major_out);
+int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width);
+void vgpu_dmat_free(vgpu_dmat* m);
+
+/* ---- p3-dft: TwoAdicSubgroupDft::dft_batch / idft_batch / coset_lde_batch ------------------------
+ * (reached via pcs.commit_batches, derive/src/lib.rs:309,330,355).  In place, natural order in and out. */
+int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse);
+/* out = evaluations over shift*K, |K| = height << log_blowup; bit_reversed != 0 stores row r at reverse_bits(r). */
+int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_blowup, uint32_t shift_canonical,
+                             int32_t bit_reversed, vgpu_dmat** out);
+/* Host-buffer variants (row-major, `repr` words; H2D/D2H inside): the e2e path of bench.py. */
+int32_t vgpu_ntt_batch_host(vgpu_ctx* ctx, uint32_t* row_major, uint64_t height, uint64_t width, int32_t repr, int32_t inverse);
+
+/* ---- Pcs::commit_batches / UnivariatePcsWithLde::commit_shifted_batches ---------------------------
+ * (derive/src/lib.rs:309,330,355,372).  coset_shifts_or_null: per-matrix shift (canonical), NULL = 1.
+ * Writes the [BabyBear;8] commitment (canonical words) and returns the prover data handle. */
+int32_t vgpu_commit_batches(vgpu_ctx* ctx, const vgpu_dmat* const* mats, uint32_t n, const uint32_t* coset_shifts_or_null,
+                            uint32_t digest_out[8], vgpu_prover_data** out);
+int32_t vgpu_commit_batches_host(vgpu_ctx* ctx, const vgpu_matrix* mats, uint32_t n, int32_t repr, const uint32_t* coset_shifts_or_null,
+                                 uint32_t digest_out[8], vgpu_prover_data** out);
+/* pcs.get_ldes (derive/src/lib.rs:311,332,358): borrowed view of committed LDE i (bit-reversed rows). */
+int32_t vgpu_prover_data_lde(const vgpu_prover_data* pd, uint32_t i, const vgpu_dmat** view);
+void vgpu_prover_data_free(vgpu_prover_data* pd);
+
+/* ---- host witness generation (Chip::generate_trace x14; machine/src/chip.rs:22) -------------------
+ * program_words: n_instr x 6 int32 (opcode, a, b, c, d, e) as ProgramROM<i32> (machine/src/program.rs:165-185). */
+int32_t vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                         vgpu_traces** out, char* err, uint64_t err_len);
+const vgpu_matrix* vgpu_traces_main(const vgpu_traces* t, uint32_t chip);           /* canonical words */
+const vgpu_matrix* vgpu_traces_preprocessed(const vgpu_traces* t, uint32_t which);  /* 0 = program (7 cols), 1 = range (1 col) */
+void vgpu_traces_stats(const vgpu_traces* t, uint32_t* clock, uint32_t* mem_ops, uint32_t* add_ops);
+int32_t vgpu_traces_mem_cell(const vgpu_traces* t, uint32_t addr, uint32_t* value);
+void vgpu_traces_free(vgpu_traces* t);
+/* fib_program of basic/tests/test_prover.rs:35-188 with `imm32 -8(fp)` = n; returns the instruction count (23). */
+uint64_t vgpu_fib_program(uint32_t n, int32_t* out_words /* >= 23*6 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALIDA_B200_H */

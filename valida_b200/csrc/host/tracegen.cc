@@ -1,0 +1,356 @@
+// Host witness generation for BasicMachine: a small Valida VM for the instruction subset the
+// reference's proving tests exercise (imm32, add32/sub32 with and without immediates, jal, jalv,
+// beq, bne, load32, store32, loadfp, stop) and the Chip::generate_trace of every chip.
+// This is the INPUT side of the proving path (SURVEY.md §8a "Chip::generate_trace x14 — kept on
+// host, input to the GPU path"); it follows
+//   run loop + STOP padding        basic/src/lib.rs:127-145, 1063-1188
+//   instruction semantics          cpu/src/lib.rs:437-923, alu_u32/src/add/mod.rs:138-169, sub/mod.rs:126-166
+//   CPU rows                       cpu/src/lib.rs:79-97, 163-373
+//   memory rows                    memory/src/lib.rs:85-136, 143-194, 237-263
+//   add/sub rows                   alu_u32/src/add/mod.rs:38-129, alu_u32/src/sub/mod.rs
+//   mul floor (2^10 counter rows)  alu_u32/src/mul/mod.rs:38-64
+//   range / program rows           range/src/lib.rs:32-72, program/src/lib.rs:38-81, program/src/stark.rs:22-40
+// Output: 14 row-major matrices of canonical BabyBear words in chip order
+// (cpu, program, mem, add, sub, mul, div, shift, lt, com, bitwise, output, range, static_data)
+// plus the two preprocessed traces.
+#include <cstdint>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+#include <string>
+#include "../../../include/valida_b200.h"
+
+namespace {
+
+constexpr uint32_t P = 2013265921u;
+inline uint32_t fmul(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) % P); }
+inline uint32_t fpow(uint32_t a, uint32_t e) { uint32_t r = 1; while (e) { if (e & 1) r = fmul(r, a); a = fmul(a, a); e >>= 1; } return r; }
+inline uint32_t from_i32(int32_t x) { return x < 0 ? (P - (uint32_t)(-(int64_t)x) % P) % P : (uint32_t)x % P; }
+inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+
+enum : uint32_t { OP_LOAD32 = 1, OP_STORE32 = 2, OP_JAL = 3, OP_JALV = 4, OP_BEQ = 5, OP_BNE = 6, OP_IMM32 = 7, OP_STOP = 8, OP_LOADFP = 10,
+                  OP_ADD32 = 100, OP_SUB32 = 101 };
+enum CpuOp : uint8_t { K_STORE32, K_LOAD32, K_JAL, K_JALV, K_BEQ, K_BNE, K_IMM32, K_BUS, K_STOP, K_LOADFP };
+
+struct MemOp { uint32_t clk, addr, value; uint8_t is_write; };
+struct CpuRec { uint32_t pc, fp; uint32_t instr; CpuOp kind; bool has_imm; uint32_t imm; };
+struct AluRec { uint32_t a, b, c; };
+
+struct Vm {
+    const int32_t* prog; size_t n_instr;
+    uint32_t pc = 0, fp = 0, clock = 0;
+    std::unordered_map<uint32_t, uint32_t> cells;
+    std::vector<MemOp> mem_ops;
+    std::vector<CpuRec> cpu;
+    std::vector<AluRec> adds, subs;
+    std::vector<uint32_t> prog_counts;
+    uint32_t range_count[256] = {0};
+    std::string err;
+
+    bool read(uint32_t addr, uint32_t& v) {
+        auto it = cells.find(addr);
+        if (it == cells.end()) { err = "memory chip: read before write at " + std::to_string(addr) + " (pc=" + std::to_string(pc) + ")"; return false; }
+        v = it->second;
+        mem_ops.push_back({clock, addr, v, 0});
+        return true;
+    }
+    void write(uint32_t addr, uint32_t v) { mem_ops.push_back({clock, addr, v, 1}); cells[addr] = v; }
+    void range_check(uint32_t w) { for (int i = 0; i < 4; i++) range_count[(w >> (8 * i)) & 0xff]++; }
+    void push(CpuOp kind, uint32_t instr_pc, uint32_t pc_before, uint32_t fp_before, bool has_imm = false, uint32_t imm = 0) {
+        cpu.push_back({pc_before, fp_before, instr_pc, kind, has_imm, imm});
+        clock++;
+    }
+    // returns 1 when STOP executed, 0 otherwise, -1 on error
+    int step() {
+        if (pc >= n_instr) { err = "pc out of range"; return -1; }
+        const int32_t* w = prog + 6 * (size_t)pc;
+        uint32_t opcode = (uint32_t)w[0];
+        int32_t a = w[1], b = w[2], c = w[3], d = w[4], e = w[5];
+        uint32_t pc0 = pc, fp0 = fp;
+        auto at = [&](int32_t off) { return (uint32_t)((int32_t)fp0 + off); };
+        switch (opcode) {
+            case OP_IMM32: {
+                uint32_t v = ((uint32_t)(uint8_t)b << 24) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 8) | (uint32_t)(uint8_t)e;
+                write(at(a), v); pc++; push(K_IMM32, pc0, pc0, fp0); break; }
+            case OP_ADD32: case OP_SUB32: {
+                uint32_t bv, cv; bool imm = (e == 1);
+                if (!read(at(b), bv)) return -1;
+                if (imm) cv = (uint32_t)c; else if (!read(at(c), cv)) return -1;
+                uint32_t av = opcode == OP_ADD32 ? bv + cv : bv - cv;
+                write(at(a), av);
+                (opcode == OP_ADD32 ? adds : subs).push_back({av, bv, cv});
+                pc++; push(K_BUS, pc0, pc0, fp0, imm, cv);
+                range_check(av); break; }
+            case OP_JAL: {
+                write(at(a), 24u * (pc0 + 1)); pc = (uint32_t)b / 24u; fp = at(c); push(K_JAL, pc0, pc0, fp0); break; }
+            case OP_JALV: {
+                write(at(a), 24u * (pc0 + 1));
+                uint32_t t, off;
+                if (!read(at(b), t)) return -1;
+                pc = t / 24u;
+                if (!read(at(c), off)) return -1;
+                fp = (uint32_t)((int32_t)fp0 + (int32_t)off);
+                push(K_JALV, pc0, pc0, fp0); break; }
+            case OP_BEQ: case OP_BNE: {
+                uint32_t v1, v2; bool imm = (e == 1);
+                if (!read(at(b), v1)) return -1;
+                if (imm) v2 = (uint32_t)c; else if (!read(at(c), v2)) return -1;
+                bool take = (opcode == OP_BEQ) ? (v1 == v2) : (v1 != v2);
+                pc = take ? (uint32_t)a / 24u : pc0 + 1;
+                push(opcode == OP_BEQ ? K_BEQ : K_BNE, pc0, pc0, fp0, imm, v2); break; }
+            case OP_LOADFP: { write(at(a), at(b)); pc++; push(K_LOADFP, pc0, pc0, fp0); break; }
+            case OP_LOAD32: {
+                uint32_t p, cell;
+                if (!read(at(c), p)) return -1;
+                if (!read(p, cell)) return -1;
+                write(at(a), cell); pc++; push(K_LOAD32, pc0, pc0, fp0); break; }
+            case OP_STORE32: {
+                uint32_t waddr, cell;
+                if (!read(at(b), waddr)) return -1;
+                if (!read(at(c), cell)) return -1;
+                write(waddr, cell); pc++; push(K_STORE32, pc0, pc0, fp0); break; }
+            case OP_STOP: { push(K_STOP, pc0, pc0, fp0); break; }
+            default: err = "unsupported opcode " + std::to_string(opcode) + " at pc " + std::to_string(pc0); return -1;
+        }
+        prog_counts[pc0]++;
+        return opcode == OP_STOP ? 1 : 0;
+    }
+};
+
+struct Traces {
+    vgpu_matrix main[14];
+    vgpu_matrix prep[2];
+    std::vector<uint32_t> store[16];
+    uint32_t clock = 0, n_mem_ops = 0, n_add_ops = 0, n_sub_ops = 0;
+    std::unordered_map<uint32_t, uint32_t> cells;
+};
+
+inline void word_be(uint32_t v, uint32_t* out) { out[0] = v >> 24; out[1] = (v >> 16) & 0xff; out[2] = (v >> 8) & 0xff; out[3] = v & 0xff; }
+
+void build_cpu(const Vm& vm, Traces& t) {
+    constexpr size_t W = 51;
+    size_t n = vm.cpu.size(), h = next_pow2(n);
+    std::vector<uint32_t>& v = t.store[0];
+    v.assign(h * W, 0);
+    // per-clk memory ops are contiguous in vm.mem_ops (clk non-decreasing)
+    std::vector<size_t> first(n + 1, 0);
+    { size_t k = 0; for (size_t clk = 0; clk <= n; clk++) { while (k < vm.mem_ops.size() && vm.mem_ops[k].clk < clk) k++; first[clk] = k; } }
+    std::vector<uint32_t> diff(n, 0);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        const CpuRec& r = vm.cpu[i];
+        uint32_t* row = &v[(size_t)i * W];
+        const int32_t* w = vm.prog + 6 * (size_t)r.instr;
+        row[0] = (uint32_t)i; row[1] = r.pc; row[2] = r.fp;
+        row[3] = (uint32_t)w[0];
+        for (int k = 0; k < 5; k++) row[4 + k] = from_i32(w[1 + k]);
+        bool left_imm = false;
+        switch (r.kind) {
+            case K_STORE32: row[16] = 1; break;
+            case K_LOAD32: row[13] = 1; break;
+            case K_JAL: row[20] = 1; break;
+            case K_JALV: row[21] = 1; break;
+            case K_BEQ: row[18] = 1; break;
+            case K_BNE: row[19] = 1; break;
+            case K_IMM32: row[22] = 1; break;
+            case K_BUS: row[9] = 1; break;
+            case K_STOP: row[24] = 1; break;
+            case K_LOADFP: row[25] = 1; break;
+        }
+        if (r.has_imm) {  // set_imm_value (cpu/src/lib.rs:355-362)
+            row[11] = 1;
+            word_be(r.imm, &row[36 + 3]);
+            row[6] = r.imm % P;
+        }
+        row[29 + 1] = 1; row[36 + 1] = 1; row[43 + 1] = 0;
+        bool first_read = true;
+        for (size_t k = first[i]; k < first[i + 1]; k++) {
+            const MemOp& m = vm.mem_ops[k];
+            uint32_t ch;
+            if (m.is_write) ch = 43;
+            else if (first_read && !left_imm) { ch = 29; first_read = false; }
+            else ch = 36;
+            row[ch] = 1; row[ch + 2] = m.addr; word_be(m.value, &row[ch + 3]);
+        }
+        uint64_t dsum = 0;
+        for (int k = 0; k < 4; k++) { int64_t dd = (int64_t)row[32 + k] - (int64_t)row[39 + k]; dsum += (uint64_t)(dd * dd); }
+        diff[i] = (uint32_t)(dsum % P);
+    }
+    // diff_inv via a small cache (diff <= 4*255^2)
+    {
+        std::unordered_map<uint32_t, uint32_t> invs;
+        for (size_t i = 0; i < n; i++) if (diff[i] && !invs.count(diff[i])) invs[diff[i]] = fpow(diff[i], P - 2);
+        for (size_t i = 0; i < n; i++) {
+            uint32_t* row = &v[i * W];
+            row[26] = diff[i];
+            if (diff[i]) { row[27] = invs[diff[i]]; row[28] = 1; }
+        }
+    }
+    // pad_to_power_of_two (cpu/src/lib.rs:318-353)
+    if (n) {
+        const uint32_t* last = &v[(n - 1) * W];
+        uint32_t pc = last[1], fp = last[2], clk = last[0];
+        for (size_t i = n; i < h; i++) {
+            uint32_t* row = &v[i * W];
+            row[1] = pc; row[2] = fp; row[0] = clk + (uint32_t)(i - n) + 1;
+            row[24] = 1; row[3] = OP_STOP;
+            row[29 + 1] = 1; row[36 + 1] = 1;
+        }
+    }
+    t.main[0] = {v.data(), h, W};
+}
+
+void build_mem(const Vm& vm, Traces& t) {
+    constexpr size_t W = 14;
+    std::vector<MemOp> ops = vm.mem_ops;
+    std::stable_sort(ops.begin(), ops.end(), [](const MemOp& x, const MemOp& y) { return x.addr != y.addr ? x.addr < y.addr : x.clk < y.clk; });
+    size_t n = ops.size(), h = next_pow2(n);
+    std::vector<uint32_t>& v = t.store[2];
+    v.assign(h * W, 0);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        uint32_t* row = &v[(size_t)i * W];
+        row[0] = ops[i].addr; word_be(ops[i].value, &row[1]);
+        row[5] = ops[i].clk; row[6] = 0;
+        if (ops[i].is_write) row[8] = 1; else row[7] = 1;
+        row[12] = (uint32_t)i;
+    }
+    t.main[2] = {v.data(), h, W};
+}
+
+void build_addsub(const std::vector<AluRec>& ops, bool is_add, std::vector<uint32_t>& v, vgpu_matrix& out) {
+    constexpr size_t W = 16;
+    size_t n = ops.size(), h = next_pow2(n);
+    v.assign(h * W, 0);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t* row = &v[i * W];
+        uint32_t a[4], b[4], c[4];
+        word_be(ops[i].a, a); word_be(ops[i].b, b); word_be(ops[i].c, c);
+        std::memcpy(row + 0, b, 16); std::memcpy(row + 4, c, 16); std::memcpy(row + 11, a, 16);
+        if (is_add) {
+            uint32_t c1 = (b[3] + c[3] > 255), c2 = (b[2] + c[2] + c1 > 255), c3 = (b[1] + c[1] + c2 > 255);
+            row[8] = c1; row[9] = c2; row[10] = c3;
+        } else {  // alu_u32/src/sub/mod.rs op_to_row
+            // exactly as the reference (no borrow propagation into the comparison): sub/mod.rs:103-111
+            uint32_t b1 = (b[3] < c[3]), b2 = (b[2] < c[2]), b3 = (b[1] < c[1]);
+            row[8] = b1; row[9] = b2; row[10] = b3;
+        }
+        row[15] = 1;
+    }
+    out = {v.data(), h, W};
+}
+
+void zero_chip(std::vector<uint32_t>& v, vgpu_matrix& out, size_t w) { v.assign(w, 0); out = {v.data(), 1, w}; }
+
+}  // namespace
+
+struct vgpu_traces { Traces t; };
+
+extern "C" {
+
+int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                   vgpu_traces** out, char* err, uint64_t err_len) {
+    Vm vm;
+    vm.prog = program_words; vm.n_instr = n_instr; vm.pc = initial_pc; vm.fp = initial_fp;
+    vm.prog_counts.assign(n_instr, 0);
+    int rc = 0;
+    while ((rc = vm.step()) == 0) {
+        if (vm.clock >= max_cycles) { vm.err = "cycle limit reached"; rc = -1; break; }
+    }
+    if (rc < 0) { if (err && err_len) { std::strncpy(err, vm.err.c_str(), err_len - 1); err[err_len - 1] = 0; } return -1; }
+    // STOP padding reads the program word at the final pc (basic/src/lib.rs:140-144)
+    size_t padded = next_pow2(vm.clock);
+    vm.prog_counts[vm.pc] += (uint32_t)(padded - vm.clock);
+
+    vgpu_traces* tr = new vgpu_traces();
+    Traces& t = tr->t;
+    t.clock = vm.clock; t.n_mem_ops = (uint32_t)vm.mem_ops.size(); t.n_add_ops = (uint32_t)vm.adds.size(); t.n_sub_ops = (uint32_t)vm.subs.size();
+    build_cpu(vm, t);
+    build_mem(vm, t);
+    {  // program: 1 main column (counts) + 7 preprocessed
+        size_t h = next_pow2(n_instr);
+        t.store[1].assign(h, 0);
+        for (size_t i = 0; i < n_instr; i++) t.store[1][i] = vm.prog_counts[i];
+        t.main[1] = {t.store[1].data(), h, 1};
+        t.store[14].assign(h * 7, 0);
+        for (size_t i = 0; i < h; i++) {
+            uint32_t* row = &t.store[14][i * 7];
+            row[0] = (uint32_t)i;
+            if (i < n_instr) { row[1] = (uint32_t)program_words[6 * i]; for (int k = 0; k < 5; k++) row[2 + k] = from_i32(program_words[6 * i + 1 + k]); }
+        }
+        t.prep[0] = {t.store[14].data(), h, 7};
+    }
+    build_addsub(vm.adds, true, t.store[3], t.main[3]);
+    build_addsub(vm.subs, false, t.store[4], t.main[4]);
+    {  // mul: 2^10 counter rows
+        t.store[5].assign(1024 * 18, 0);
+        for (size_t i = 0; i < 1024; i++) t.store[5][i * 18 + 17] = (uint32_t)i + 1;
+        t.main[5] = {t.store[5].data(), 1024, 18};
+    }
+    zero_chip(t.store[6], t.main[6], 14);   // div
+    zero_chip(t.store[7], t.main[7], 28);   // shift
+    zero_chip(t.store[8], t.main[8], 45);   // lt
+    zero_chip(t.store[9], t.main[9], 14);   // com
+    zero_chip(t.store[10], t.main[10], 79); // bitwise
+    zero_chip(t.store[11], t.main[11], 7);  // output
+    {  // range: (mult, counter) + preprocessed counter
+        t.store[12].assign(256 * 2, 0); t.store[15].assign(256, 0);
+        for (uint32_t i = 0; i < 256; i++) { t.store[12][i * 2] = vm.range_count[i]; t.store[12][i * 2 + 1] = i; t.store[15][i] = i; }
+        t.main[12] = {t.store[12].data(), 256, 2};
+        t.prep[1] = {t.store[15].data(), 256, 1};
+    }
+    zero_chip(t.store[13], t.main[13], 6);  // static_data (no static data loaded)
+    t.cells = std::move(vm.cells);
+    *out = tr;
+    return 0;
+}
+
+const vgpu_matrix* vgpu_traces_main(const vgpu_traces* t, uint32_t chip) { return chip < 14 ? &t->t.main[chip] : nullptr; }
+const vgpu_matrix* vgpu_traces_preprocessed(const vgpu_traces* t, uint32_t which) { return which < 2 ? &t->t.prep[which] : nullptr; }
+void vgpu_traces_stats(const vgpu_traces* t, uint32_t* clock, uint32_t* mem_ops, uint32_t* add_ops) {
+    *clock = t->t.clock; *mem_ops = t->t.n_mem_ops; *add_ops = t->t.n_add_ops;
+}
+int vgpu_traces_mem_cell(const vgpu_traces* t, uint32_t addr, uint32_t* value) {
+    auto it = t->t.cells.find(addr);
+    if (it == t->t.cells.end()) return -1;
+    *value = it->second; return 0;
+}
+void vgpu_traces_free(vgpu_traces* t) { delete t; }
+
+// fib_program of basic/tests/test_prover.rs:35-188 with `imm32 -8(fp)` carrying n (big-endian bytes).
+uint64_t vgpu_fib_program(uint32_t n, int32_t* out_words /* 25*6 */) {
+    const int32_t B = 24;
+    const int32_t bb0 = 8 * B, bb0_1 = 13 * B, bb0_2 = 15 * B, bb0_3 = 19 * B, bb0_4 = 21 * B;
+    const int32_t prog[25][6] = {
+        {OP_IMM32, -4, 0, 0, 0, 0},
+        {OP_IMM32, -8, (int32_t)(n >> 24), (int32_t)((n >> 16) & 0xff), (int32_t)((n >> 8) & 0xff), (int32_t)(n & 0xff)},
+        {OP_ADD32, -16, -8, 0, 0, 1},
+        {OP_IMM32, -20, 0, 0, 0, 28},
+        {OP_JAL, -28, bb0, -28, 0, 0},
+        {OP_ADD32, -12, -24, 0, 0, 1},
+        {OP_ADD32, 4, -12, 0, 0, 1},
+        {OP_STOP, 0, 0, 0, 0, 0},
+        {OP_ADD32, -4, 12, 0, 0, 1},
+        {OP_IMM32, -8, 0, 0, 0, 0},
+        {OP_IMM32, -12, 0, 0, 0, 1},
+        {OP_IMM32, -16, 0, 0, 0, 0},
+        {OP_BEQ, bb0_1, 0, 0, 0, 0},
+        {OP_BNE, bb0_2, -16, -4, 0, 0},
+        {OP_BEQ, bb0_4, 0, 0, 0, 0},
+        {OP_ADD32, -20, -8, -12, 0, 0},
+        {OP_ADD32, -8, -12, 0, 0, 1},
+        {OP_ADD32, -12, -20, 0, 0, 1},
+        {OP_BEQ, bb0_3, 0, 0, 0, 0},
+        {OP_ADD32, -16, -16, 1, 0, 1},
+        {OP_BEQ, bb0_1, 0, 0, 0, 0},
+        {OP_ADD32, 4, -8, 0, 0, 1},
+        {OP_JALV, -4, 0, 8, 0, 0},
+    };
+    (void)bb0_3;
+    std::memcpy(out_words, prog, sizeof(int32_t) * 23 * 6);
+    return 23;
+}
+
+}  // extern "C"
