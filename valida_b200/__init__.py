@@ -1,0 +1,20 @@
+"""valida_b200 — B200-native STARK prover backend for Valida's Machine::prove() hot path.
+
+Host-side mirror of the reference's prover-facing interface (StarkConfig / UnivariatePcsWithLde /
+Machine::prove) over the C ABI in include/valida_b200.h.  There is no CPU fallback: constructing a
+Context without a CUDA device raises.
+"""
+from .api import (  # noqa: F401
+    BABYBEAR_P,
+    Context,
+    DeviceMatrix,
+    ProverData,
+    Radix2Dft,
+    TwoAdicFriPcs,
+    MachineTraces,
+    VgpuError,
+    fib_program,
+    lib,
+    lib_path,
+    run_program,
+)

@@ -1,0 +1,195 @@
+// C ABI entry points (include/valida_b200.h): context, device matrices, NTT/LDE, commit.
+#include "ctx.h"
+#include "merkle.h"
+#include <cstring>
+#include <new>
+
+// ---- memory ------------------------------------------------------------------------------------
+int32_t vg_alloc(vgpu_ctx* ctx, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 4;
+    VG_CUDA(ctx, cudaMallocAsync(p, bytes, ctx->stream));
+    return 0;
+}
+void vg_free(vgpu_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+int32_t vg_dmat_alloc(vgpu_ctx* ctx, uint64_t h, uint64_t w, vgpu_dmat** out) {
+    vgpu_dmat* m = new (std::nothrow) vgpu_dmat();
+    if (!m) VG_FAIL(ctx, "out of host memory");
+    m->ctx = ctx; m->h = h; m->w = w; m->col_stride = h; m->owns = true;
+    int32_t rc = vg_alloc(ctx, (void**)&m->d, h * w * 4);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return 0;
+}
+
+static int32_t build_pow_table(vgpu_ctx* ctx, uint32_t base_monty, uint32_t scale_monty, uint64_t max_exp, PowTable* t) {
+    uint64_t hi_len = (max_exp >> VG_POW_LO_BITS) + 1;
+    std::vector<uint32_t> lo(VG_POW_LO), hi(hi_len);
+    uint32_t a = bb::R1;
+    for (uint32_t j = 0; j < VG_POW_LO; j++) { lo[j] = a; a = bb::mul(a, base_monty); }
+    uint32_t step = a;  // base^4096
+    a = scale_monty;
+    for (uint64_t j = 0; j < hi_len; j++) { hi[j] = a; a = bb::mul(a, step); }
+    VG_TRY(vg_alloc(ctx, (void**)&t->lo, lo.size() * 4));
+    VG_TRY(vg_alloc(ctx, (void**)&t->hi, hi.size() * 4));
+    VG_CUDA(ctx, cudaMemcpyAsync(t->lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    VG_CUDA(ctx, cudaMemcpyAsync(t->hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+    t->hi_len = (uint32_t)hi_len;
+    return 0;
+}
+
+int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t scale_canonical, uint64_t max_exp, const PowTable** out) {
+    auto key = std::make_pair(shift_canonical, scale_canonical);
+    auto it = ctx->shift_tables.find(key);
+    if (it == ctx->shift_tables.end() || (uint64_t)it->second.hi_len * VG_POW_LO <= max_exp) {
+        PowTable t;
+        VG_TRY(build_pow_table(ctx, bb::to_monty(shift_canonical), bb::to_monty(scale_canonical), max_exp, &t));
+        if (it != ctx->shift_tables.end()) { vg_free(ctx, it->second.lo); vg_free(ctx, it->second.hi); }
+        ctx->shift_tables[key] = t;
+        it = ctx->shift_tables.find(key);
+    }
+    *out = &it->second;
+    return 0;
+}
+
+extern "C" {
+
+int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    vgpu_ctx* ctx = new (std::nothrow) vgpu_ctx();
+    if (!ctx) return -1;
+    ctx->device = device;
+    *out = ctx;   // returned even on failure so the caller can read vgpu_last_error
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { ctx->err = "no CUDA device available: valida_b200 has no CPU fallback"; return -2; }
+    VG_CUDA(ctx, cudaSetDevice(device));
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { VG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    cudaDeviceProp prop;
+    VG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaMemPool_t pool;
+    VG_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    VG_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    VG_TRY(build_pow_table(ctx, bb::two_adic_generator_monty(VG_LOG_NMAX), bb::R1, (1ull << VG_LOG_NMAX) - 1, &ctx->root_table));
+    return 0;
+}
+
+void vgpu_ctx_destroy(vgpu_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        vg_free(ctx, ctx->root_table.lo); vg_free(ctx, ctx->root_table.hi);
+        for (auto& kv : ctx->shift_tables) { vg_free(ctx, kv.second.lo); vg_free(ctx, kv.second.hi); }
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char* vgpu_last_error(const vgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int32_t vgpu_ctx_synchronize(vgpu_ctx* ctx) { VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+uint64_t vgpu_ctx_launch_count(const vgpu_ctx* ctx) { return ctx->launches; }
+
+// ---- device matrices -----------------------------------------------------------------------------
+int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out) {
+    if (!host || !out) VG_FAIL(ctx, "dmat_upload: null argument");
+    vgpu_dmat* m = nullptr;
+    VG_TRY(vg_dmat_alloc(ctx, host->height, host->width, &m));
+    int32_t rc = vg_upload_rowmajor(ctx, host->data, host->height, host->width, repr, m);
+    if (rc) { vgpu_dmat_free(m); return rc; }
+    *out = m;
+    return 0;
+}
+int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint32_t* host_row_major_out) {
+    return vg_download_rowmajor(ctx, m, repr, host_row_major_out);
+}
+int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width) { *height = m->h; *width = m->w; return 0; }
+void vgpu_dmat_free(vgpu_dmat* m) {
+    if (!m) return;
+    if (m->owns) vg_free(m->ctx, m->d);
+    delete m;
+}
+
+// ---- NTT / LDE -------------------------------------------------------------------------------------
+int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
+    int log_n = 0;
+    while ((1ull << log_n) < m->h) log_n++;
+    if ((1ull << log_n) != m->h) VG_FAIL(ctx, "ntt_batch: height %llu is not a power of two", (unsigned long long)m->h);
+    if (log_n > VG_LOG_NMAX) VG_FAIL(ctx, "ntt_batch: height exceeds two-adicity");
+    if (log_n > 24) VG_FAIL(ctx, "ntt_batch: heights above 2^24 need a three-pass split (not built yet)");
+    uint32_t* tmp = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&tmp, m->h * m->w * 4));
+    int32_t rc = vg_ntt_nat2nat(ctx, m->d, m->col_stride, m->d, m->col_stride, log_n, m->w, inverse != 0, nullptr, tmp, m->h);
+    vg_free(ctx, tmp);
+    return rc;
+}
+
+int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_blowup, uint32_t shift_canonical, int32_t bit_reversed, vgpu_dmat** out) {
+    if (log_blowup != 1) VG_FAIL(ctx, "coset_lde: only log_blowup = 1 (FriConfig of basic/src/bin/valida.rs:385-390) is built");
+    vgpu_dmat* o = nullptr;
+    VG_TRY(vg_dmat_alloc(ctx, in->h * 2, in->w, &o));
+    int32_t rc = vg_coset_lde(ctx, in->d, in->col_stride, in->h, in->w, shift_canonical, o->d, o->col_stride, bit_reversed != 0);
+    if (rc) { vgpu_dmat_free(o); return rc; }
+    *out = o;
+    return 0;
+}
+
+int32_t vgpu_ntt_batch_host(vgpu_ctx* ctx, uint32_t* row_major, uint64_t height, uint64_t width, int32_t repr, int32_t inverse) {
+    vgpu_matrix hm{row_major, height, width};
+    vgpu_dmat* m = nullptr;
+    VG_TRY(vgpu_dmat_upload(ctx, &hm, repr, &m));
+    int32_t rc = vgpu_ntt_batch(ctx, m, inverse);
+    if (rc == 0) rc = vgpu_dmat_download(ctx, m, repr, row_major);
+    vgpu_dmat_free(m);
+    return rc;
+}
+
+// ---- commit ------------------------------------------------------------------------------------------
+int32_t vgpu_commit_batches(vgpu_ctx* ctx, const vgpu_dmat* const* mats, uint32_t n, const uint32_t* coset_shifts_or_null,
+                            uint32_t digest_out[8], vgpu_prover_data** out) {
+    vgpu_prover_data* pd = new (std::nothrow) vgpu_prover_data();
+    if (!pd) VG_FAIL(ctx, "out of host memory");
+    pd->ctx = ctx;
+    int32_t rc = 0;
+    for (uint32_t i = 0; i < n && rc == 0; i++) {
+        // TwoAdicFriPcs::commit_shifted_batches: shift = generator / coset_shift_i; LDE; bit-reverse rows
+        uint32_t cs = coset_shifts_or_null ? coset_shifts_or_null[i] : 1;
+        uint32_t shift = bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
+        vgpu_dmat* lde = nullptr;
+        rc = vgpu_coset_lde_batch(ctx, mats[i], 1, shift, 1, &lde);
+        if (rc == 0) pd->ldes.push_back(lde);
+    }
+    if (rc == 0) rc = vg_merkle_build(ctx, pd);
+    if (rc) { vgpu_prover_data_free(pd); return rc; }
+    if (digest_out) std::memcpy(digest_out, pd->root, 32);
+    *out = pd;
+    return 0;
+}
+
+int32_t vgpu_commit_batches_host(vgpu_ctx* ctx, const vgpu_matrix* mats, uint32_t n, int32_t repr, const uint32_t* coset_shifts_or_null,
+                                 uint32_t digest_out[8], vgpu_prover_data** out) {
+    std::vector<vgpu_dmat*> dm(n, nullptr);
+    int32_t rc = 0;
+    for (uint32_t i = 0; i < n && rc == 0; i++) rc = vgpu_dmat_upload(ctx, &mats[i], repr, &dm[i]);
+    if (rc == 0) rc = vgpu_commit_batches(ctx, dm.data(), n, coset_shifts_or_null, digest_out, out);
+    for (auto* m : dm) vgpu_dmat_free(m);
+    return rc;
+}
+
+int32_t vgpu_prover_data_lde(const vgpu_prover_data* pd, uint32_t i, const vgpu_dmat** view) {
+    if (i >= pd->ldes.size()) return -1;
+    *view = pd->ldes[i];
+    return 0;
+}
+void vgpu_prover_data_free(vgpu_prover_data* pd) {
+    if (!pd) return;
+    for (auto* m : pd->ldes) vgpu_dmat_free(m);
+    vg_free(pd->ctx, pd->digests);
+    delete pd;
+}
+
+}  // extern "C"

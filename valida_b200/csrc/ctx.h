@@ -1,0 +1,63 @@
+// Internal context / device-matrix definitions shared by the kernels' host wrappers.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <map>
+#include <cuda_runtime.h>
+#include "../../include/valida_b200.h"
+#include "bb.cuh"
+
+constexpr int VG_LOG_NMAX = 27;                    // BabyBear two-adicity: largest transform/LDE size
+constexpr int VG_POW_LO_BITS = 12;                 // two-level power tables: base^e = lo[e & 4095] * hi[e >> 12]
+constexpr uint32_t VG_POW_LO = 1u << VG_POW_LO_BITS;
+
+struct PowTable {            // device tables of Montgomery words
+    uint32_t* lo = nullptr;  // base^j, j < 4096
+    uint32_t* hi = nullptr;  // scale * base^(4096 j), j < hi_len
+    uint32_t hi_len = 0;
+};
+
+struct vgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    PowTable root_table;                                        // base = two_adic_generator(27)
+    std::map<std::pair<uint32_t, uint32_t>, PowTable> shift_tables;  // (shift, scale) canonical -> table
+    std::vector<void*> owned;                                   // freed at destroy
+    // Poseidon challenger instance (host side; the transcript is sequential and tiny)
+    uint32_t poseidon_rc[480];
+    uint32_t poseidon_mds[256];
+    bool challenger_set = false;
+    bool poseidon_has_mds = false;
+};
+
+struct vgpu_dmat {
+    vgpu_ctx* ctx = nullptr;
+    uint32_t* d = nullptr;       // column-major: element (r, c) at d[c * col_stride + r], Montgomery form
+    uint64_t h = 0, w = 0, col_stride = 0;
+    bool owns = true;
+};
+
+#define VG_FAIL(ctx, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (ctx)->err = _b; return -1; } while (0)
+#define VG_CUDA(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { VG_FAIL(ctx, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
+#define VG_TRY(expr) do { int32_t _r = (expr); if (_r != 0) return _r; } while (0)
+#define VG_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { VG_FAIL(ctx, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
+
+int32_t vg_alloc(vgpu_ctx* ctx, void** p, size_t bytes);
+void vg_free(vgpu_ctx* ctx, void* p);
+int32_t vg_dmat_alloc(vgpu_ctx* ctx, uint64_t h, uint64_t w, vgpu_dmat** out);
+int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t scale_canonical, uint64_t max_exp, const PowTable** out);
+
+// ntt.cu
+int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, int log_n, uint64_t w,
+                       bool inverse, const PowTable* coset_or_null, uint32_t* tmp, uint64_t tmp_cs);
+int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64_t h, uint64_t w, uint32_t shift_canonical,
+                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed);
+// staging.cu
+int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);
+int32_t vg_download_rowmajor(vgpu_ctx* ctx, const vgpu_dmat* src, int32_t repr, uint32_t* host);

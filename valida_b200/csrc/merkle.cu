@@ -1,0 +1,149 @@
+// K3/K4 — Keccak-256 Merkle commitment over mixed-height column-major LDE matrices (sm_100a).
+// Replaces FieldMerkleTreeMmcs<BabyBear, SerializingHasher32<Keccak256Hash>,
+// CompressionFunctionFromHasher<_,_,2,8>, 8>::commit (basic/src/bin/valida.rs:367-374) as reached
+// from TwoAdicFriPcs::commit_shifted_batches (derive/src/lib.rs:309,330,355,372).
+//  * leaf kernel: one thread per LDE row; the row of every matrix of that height is streamed from
+//    the column-major store (coalesced across the warp), converted Montgomery -> canonical, absorbed
+//    little-endian into a register-resident 1600-bit state; digest words are reduced mod p;
+//  * node kernel: one thread per parent, 64-byte compression (one permutation), with the
+//    "inject shorter matrices" rule: node = compress(compress(l, r), hash(rows at that height)).
+// Digests are stored canonical, 8 words (32 B) per node, all layers kept for the opening phase.
+#include "ctx.h"
+#include "keccak.cuh"
+#include "merkle.h"
+#include <algorithm>
+#include <numeric>
+
+namespace {
+
+constexpr int RATE_WORDS = 34;   // 136-byte rate
+
+// Sponge over `nwords` canonical words fetched by `fetch(i)`; Keccak pad 0x01 .. 0x80.
+template <class Fetch>
+__device__ __forceinline__ void keccak256_words(uint32_t nwords, Fetch fetch, uint32_t out[8]) {
+    uint2 A[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) A[i] = make_uint2(0, 0);
+    uint32_t nblocks = nwords / RATE_WORDS + 1;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        uint32_t base = b * RATE_WORDS;
+#pragma unroll
+        for (int i = 0; i < RATE_WORDS / 2; i++) {
+            uint32_t g0 = base + 2 * i, g1 = g0 + 1;
+            uint32_t w0 = g0 < nwords ? fetch(g0) : (g0 == nwords ? 1u : 0u);
+            uint32_t w1 = g1 < nwords ? fetch(g1) : (g1 == nwords ? 1u : 0u);
+            if (i == RATE_WORDS / 2 - 1 && b == nblocks - 1) w1 ^= 0x80000000u;
+            A[i].x ^= w0; A[i].y ^= w1;
+        }
+        kk::keccak_f(A);
+    }
+    out[0] = A[0].x; out[1] = A[0].y; out[2] = A[1].x; out[3] = A[1].y;
+    out[4] = A[2].x; out[5] = A[2].y; out[6] = A[3].x; out[7] = A[3].y;
+}
+
+__device__ __forceinline__ uint32_t wrap_mod_p(uint32_t w) {   // F::from_wrapped_u32
+    w = bb::umin32(w, w - bb::P);
+    return bb::umin32(w, w - bb::P);
+}
+
+// colptr[i] = device pointer to column i of the concatenated row (all matrices of this height).
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const uint32_t* const* __restrict__ colptr, uint32_t nwords, uint64_t nrows, uint32_t* __restrict__ digests) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    uint32_t d[8];
+    keccak256_words(nwords, [&](uint32_t i) { return bb::from_monty(__ldg(colptr[i] + r)); }, d);
+    uint4* o = reinterpret_cast<uint4*>(digests + r * 8);
+    o[0] = make_uint4(wrap_mod_p(d[0]), wrap_mod_p(d[1]), wrap_mod_p(d[2]), wrap_mod_p(d[3]));
+    o[1] = make_uint4(wrap_mod_p(d[4]), wrap_mod_p(d[5]), wrap_mod_p(d[6]), wrap_mod_p(d[7]));
+}
+
+__device__ __forceinline__ void compress_pair(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
+    uint32_t d[8];
+    keccak256_words(16, [&](uint32_t i) { return i < 8 ? l[i] : r[i - 8]; }, d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = wrap_mod_p(d[i]);
+}
+
+// next[i] = compress(prev[2i], prev[2i+1]) ; if inject != null: next[i] = compress(next[i], inject[i])
+__global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ inject, uint64_t n_next, uint32_t* __restrict__ next) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_next) return;
+    uint32_t l[8], r[8], o[8];
+    const uint4* p = reinterpret_cast<const uint4*>(prev + i * 16);
+    uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    l[0] = a.x; l[1] = a.y; l[2] = a.z; l[3] = a.w; l[4] = b.x; l[5] = b.y; l[6] = b.z; l[7] = b.w;
+    r[0] = c.x; r[1] = c.y; r[2] = c.z; r[3] = c.w; r[4] = d.x; r[5] = d.y; r[6] = d.z; r[7] = d.w;
+    compress_pair(l, r, o);
+    if (inject) {
+        const uint4* q = reinterpret_cast<const uint4*>(inject + i * 8);
+        uint4 e = __ldg(q), f = __ldg(q + 1);
+        uint32_t t[8] = {e.x, e.y, e.z, e.w, f.x, f.y, f.z, f.w};
+        uint32_t o2[8];
+        compress_pair(o, t, o2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = o2[k];
+    }
+    uint4* w = reinterpret_cast<uint4*>(next + i * 8);
+    w[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    w[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint64_t nrows, uint32_t* digests) {
+    std::vector<const uint32_t*> cols;
+    for (auto* m : mats) for (uint64_t c = 0; c < m->w; c++) cols.push_back(m->d + c * m->col_stride);
+    const uint32_t** dcols = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&dcols, cols.size() * sizeof(void*)));
+    VG_CUDA(ctx, cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    // the host vector must outlive the async copy from pageable memory: cudaMemcpyAsync from pageable memory
+    // stages synchronously, so it is safe to let `cols` go once the call returns.
+    leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), nrows, digests);
+    VG_LAUNCH_CHECK(ctx);
+    vg_free(ctx, dcols);
+    return 0;
+}
+
+}  // namespace
+
+// Build the mixed-height tree over the (already bit-reversed) LDE matrices in `pd->ldes`.
+int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd) {
+    size_t n = pd->ldes.size();
+    if (!n) VG_FAIL(ctx, "commit: no matrices");
+    std::vector<size_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pd->ldes[a]->h > pd->ldes[b]->h; });
+    uint64_t max_h = pd->ldes[order[0]]->h;
+    if (max_h & (max_h - 1)) VG_FAIL(ctx, "commit: heights must be powers of two");
+    pd->max_height = max_h;
+    // all layers in one allocation: max_h + max_h/2 + ... + 1 = 2*max_h - 1 digests
+    VG_TRY(vg_alloc(ctx, (void**)&pd->digests, (2 * max_h) * 32));
+    size_t pos = 0;
+    std::vector<const vgpu_dmat*> group;
+    while (pos < n && pd->ldes[order[pos]]->h == max_h) group.push_back(pd->ldes[order[pos++]]);
+    uint32_t* layer = pd->digests;
+    pd->layer_ptr.clear(); pd->layer_len.clear();
+    pd->layer_ptr.push_back(layer); pd->layer_len.push_back(max_h);
+    VG_TRY(hash_rows(ctx, group, max_h, layer));
+    uint32_t* inject_buf = nullptr;
+    uint64_t len = max_h;
+    while (len > 1) {
+        uint64_t next_len = len / 2;
+        group.clear();
+        while (pos < n && pd->ldes[order[pos]]->h == next_len) group.push_back(pd->ldes[order[pos++]]);
+        const uint32_t* inj = nullptr;
+        if (!group.empty()) {
+            if (!inject_buf) VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (max_h / 2) * 32));
+            VG_TRY(hash_rows(ctx, group, next_len, inject_buf));
+            inj = inject_buf;
+        }
+        uint32_t* next = layer + len * 8;
+        compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, inj, next_len, next);
+        VG_LAUNCH_CHECK(ctx);
+        pd->layer_ptr.push_back(next); pd->layer_len.push_back(next_len);
+        layer = next; len = next_len;
+    }
+    if (inject_buf) vg_free(ctx, inject_buf);
+    if (pos != n) VG_FAIL(ctx, "commit: a matrix height does not match any tree layer");
+    VG_CUDA(ctx, cudaMemcpyAsync(pd->root, layer, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -1,0 +1,16 @@
+// <ValMmcs as Mmcs>::ProverData, device resident: committed (bit-reversed) LDE matrices in the
+// caller's order + every digest layer (canonical words, 8 per node).
+#pragma once
+#include "ctx.h"
+
+struct vgpu_prover_data {
+    vgpu_ctx* ctx = nullptr;
+    std::vector<vgpu_dmat*> ldes;          // owned
+    uint32_t* digests = nullptr;           // all layers, leaf layer first
+    std::vector<uint32_t*> layer_ptr;      // layer_ptr[i] -> layer i (len layer_len[i] digests)
+    std::vector<uint64_t> layer_len;
+    uint64_t max_height = 0;
+    uint32_t root[8] = {0};
+};
+
+int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd);
