@@ -77,6 +77,69 @@ int32_t vgpu_commit_batches_host(vgpu_ctx* ctx, const vgpu_matrix* mats, uint32_
 int32_t vgpu_prover_data_lde(const vgpu_prover_data* pd, uint32_t i, const vgpu_dmat** view);
 void vgpu_prover_data_free(vgpu_prover_data* pd);
 
+
+/* ---- chip description: Chip::all_interactions (machine/src/chip.rs:40-63) ---------------------------
+ * The data-driven half of a chip: its bus interactions as affine combinations of trace columns
+ * (p3_air::VirtualPairCol; machine/src/chip.rs:76-80).  The AIR half (Air::eval) is compiled into the
+ * library per chip id (BasicMachine order, basic/src/lib.rs:151-166). */
+#define VGPU_MAX_TERMS 4
+#define VGPU_MAX_FIELDS 14
+#define VGPU_MAX_INTERACTIONS 5
+typedef struct vgpu_pair_col {      /* VirtualPairCol: constant + sum_k weight_k * column_k */
+    uint32_t constant;              /* canonical */
+    uint32_t n_terms;
+    struct { uint32_t is_preprocessed, column, weight; } terms[VGPU_MAX_TERMS];
+} vgpu_pair_col;
+typedef struct vgpu_interaction {
+    uint32_t n_fields;
+    vgpu_pair_col fields[VGPU_MAX_FIELDS];
+    vgpu_pair_col count;
+    uint32_t bus;                   /* BusArgument::Global(bus) */
+    uint32_t is_send;               /* InteractionType::{GlobalSend, GlobalReceive} */
+} vgpu_interaction;
+typedef struct vgpu_chip_desc {
+    uint32_t chip_id;               /* selects the compiled Air::eval */
+    uint32_t width, preprocessed_width;
+    uint32_t n_interactions;
+    vgpu_interaction interactions[VGPU_MAX_INTERACTIONS];
+} vgpu_chip_desc;
+/* Built-in BasicMachine chips (0..13). */
+const vgpu_chip_desc* vgpu_basic_machine_chip(uint32_t chip_id);
+
+/* ---- generate_permutation_trace (machine/src/chip.rs:121-208) ---------------------------------------
+ * main (h x width), prep (h x preprocessed_width or NULL); challenges = 3 ext elements (15 canonical
+ * words: local alpha base, global alpha base, beta).  Returns the flattened perm trace
+ * (h x 5*(k+1), RowMajorMatrix<Challenge>::flatten_to_base) and the cumulative sum (last row, last column). */
+int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const vgpu_dmat* main, const vgpu_dmat* prep_or_null,
+                        const uint32_t challenges[15], vgpu_dmat** out_perm, uint32_t cumulative_sum_out[5]);
+
+/* ---- quotient (machine/src/quotient.rs:18-68) -------------------------------------------------------
+ * LDE arguments are committed LDEs (bit-reversed rows, 2h x w) as returned by vgpu_prover_data_lde.
+ * Output: the h x 10 quotient-chunk matrix (decompose_and_flatten with log_quotient_degree = 1). */
+int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint32_t log_degree, const vgpu_dmat* prep_lde_or_null,
+                      const vgpu_dmat* main_lde, const vgpu_dmat* perm_lde, const uint32_t cumulative_sum[5],
+                      const uint32_t perm_challenges[15], const uint32_t alpha[5], vgpu_dmat** out_chunks);
+
+/* ---- Fiat-Shamir transcript owned by the context (DuplexChallenger; config.challenger() clone) ------
+ * reset() restores the initial sponge of vgpu_set_challenger; values are canonical words. */
+int32_t vgpu_challenger_reset(vgpu_ctx* ctx);
+int32_t vgpu_challenger_observe(vgpu_ctx* ctx, const uint32_t* values, uint32_t n);
+int32_t vgpu_challenger_sample_ext(vgpu_ctx* ctx, uint32_t out[5]);
+
+/* ---- Machine::prove (machine/src/machine.rs:22-24; body derive/src/lib.rs:275-446) -------------------
+ * main: the 14 chip traces in BasicMachine order; prep: preprocessed traces (program 7 cols, range 1 col).
+ * Runs steps 3-23 of the reference's prove() on the device (transcript on the host) and returns the
+ * CBOR image of MachineProof (ciborium::into_writer, basic/src/bin/valida.rs:425-426) in a buffer
+ * released with vgpu_free_bytes.  vgpu_set_challenger must have been called. */
+int32_t vgpu_prove(vgpu_ctx* ctx, const vgpu_matrix main[VGPU_NUM_CHIPS], const vgpu_matrix prep[2], int32_t repr,
+                   uint8_t** proof_out, uint64_t* proof_len);
+/* Same with the traces already resident in HBM (bench.py's device-resident timing). */
+int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CHIPS], const vgpu_dmat* const prep[2],
+                          uint8_t** proof_out, uint64_t* proof_len);
+void vgpu_free_bytes(uint8_t* p);
+/* Per-phase device time of the last vgpu_prove* call: names[i] (static strings) / ms[i]; returns the count. */
+uint32_t vgpu_last_prove_phases(const vgpu_ctx* ctx, const char** names, float* ms, uint32_t cap);
+
 /* ---- host witness generation (Chip::generate_trace x14; machine/src/chip.rs:22) -------------------
  * program_words: n_instr x 6 int32 (opcode, a, b, c, d, e) as ProgramROM<i32> (machine/src/program.rs:165-185). */
 int32_t vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,

@@ -13,7 +13,12 @@ from .api import (  # noqa: F401
     TwoAdicFriPcs,
     MachineTraces,
     VgpuError,
+    StarkConfig,
+    prove_machine,
+    last_prove_phases,
     fib_program,
+    generate_permutation_trace,
+    quotient,
     lib,
     lib_path,
     run_program,

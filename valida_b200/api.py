@@ -53,6 +53,17 @@ def _load():
         "vgpu_commit_batches_host": (C.c_int32, [vp, C.POINTER(_Matrix), C.c_uint32, C.c_int32, u32p, u32p, C.POINTER(vp)]),
         "vgpu_prover_data_lde": (C.c_int32, [vp, C.c_uint32, C.POINTER(vp)]),
         "vgpu_prover_data_free": (None, [vp]),
+        "vgpu_basic_machine_chip": (vp, [C.c_uint32]),
+        "vgpu_perm_trace": (C.c_int32, [vp, vp, vp, vp, u32p, C.POINTER(vp), u32p]),
+        "vgpu_quotient": (C.c_int32, [vp, vp, C.c_uint32, vp, vp, vp, u32p, u32p, u32p, C.POINTER(vp)]),
+        "vgpu_set_challenger": (C.c_int32, [vp, u32p, u32p]),
+        "vgpu_challenger_reset": (C.c_int32, [vp]),
+        "vgpu_challenger_observe": (C.c_int32, [vp, u32p, C.c_uint32]),
+        "vgpu_challenger_sample_ext": (C.c_int32, [vp, u32p]),
+        "vgpu_prove": (C.c_int32, [vp, C.POINTER(_Matrix), C.POINTER(_Matrix), C.c_int32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
+        "vgpu_prove_device": (C.c_int32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
+        "vgpu_free_bytes": (None, [C.POINTER(C.c_uint8)]),
+        "vgpu_last_prove_phases": (C.c_uint32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_uint32]),
         "vgpu_machine_run": (C.c_int32, [C.POINTER(C.c_int32), u64, C.c_uint32, C.c_uint32, u64, C.POINTER(vp), C.c_char_p, u64]),
         "vgpu_traces_main": (C.POINTER(_Matrix), [vp, C.c_uint32]),
         "vgpu_traces_preprocessed": (C.POINTER(_Matrix), [vp, C.c_uint32]),
@@ -240,6 +251,78 @@ class TwoAdicFriPcs:
             self.ctx.check(lib().vgpu_prover_data_lde(prover_data._h, i, C.byref(v)))
             out.append(DeviceMatrix(self.ctx, v, owned=False))
         return out
+
+
+def _u32arr(a, n):
+    a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1)
+    assert a.size == n
+    return (C.c_uint32 * n)(*[int(x) for x in a])
+
+
+def generate_permutation_trace(ctx, chip_id, main, prep, random_elements):
+    """machine/src/chip.rs:121 — returns (flattened perm trace DeviceMatrix, cumulative_sum[5])."""
+    chip = lib().vgpu_basic_machine_chip(chip_id)
+    out = C.c_void_p()
+    cs = (C.c_uint32 * 5)()
+    ctx.check(lib().vgpu_perm_trace(ctx._h, chip, main._h, prep._h if prep is not None else None, _u32arr(random_elements, 15), C.byref(out), cs))
+    return DeviceMatrix(ctx, out), np.array(list(cs), dtype=np.uint32)
+
+
+def quotient(ctx, chip_id, log_degree, prep_lde, main_lde, perm_lde, cumulative_sum, perm_challenges, alpha):
+    """machine/src/quotient.rs:18 — returns the h x 10 quotient-chunk DeviceMatrix."""
+    chip = lib().vgpu_basic_machine_chip(chip_id)
+    out = C.c_void_p()
+    ctx.check(lib().vgpu_quotient(ctx._h, chip, log_degree, prep_lde._h if prep_lde is not None else None, main_lde._h, perm_lde._h,
+                                  _u32arr(cumulative_sum, 5), _u32arr(perm_challenges, 15), _u32arr(alpha, 5), C.byref(out)))
+    return DeviceMatrix(ctx, out)
+
+
+class StarkConfig:
+    """StarkConfigImpl (machine/src/config.rs:33-76): the PCS plus the initial challenger.
+
+    round_constants: the 480 Poseidon round constants the caller's RNG produced
+    (Poseidon::new_from_rng(4, 22, mds, rng), basic/src/bin/valida.rs:364-365), canonical words.
+    """
+
+    def __init__(self, ctx, round_constants, mds=None):
+        self.ctx = ctx
+        self.pcs_ = TwoAdicFriPcs(ctx)
+        rc = _u32arr(round_constants, 480)
+        m = _u32arr(mds, 256) if mds is not None else None
+        ctx.check(lib().vgpu_set_challenger(ctx._h, rc, m))
+
+    def pcs(self):
+        return self.pcs_
+
+
+def prove_machine(config, traces, device_resident=None):
+    """Machine::prove (machine/src/machine.rs:22-24): returns the CBOR bytes of MachineProof.
+
+    traces: MachineTraces (host, row-major canonical).  device_resident: optional pair
+    ([14 DeviceMatrix], [2 DeviceMatrix]) already uploaded (bench's HBM-resident timing)."""
+    ctx = config.ctx
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_uint64()
+    if device_resident is not None:
+        dm, dp = device_resident
+        a = (C.c_void_p * NUM_CHIPS)(*[m._h for m in dm])
+        b = (C.c_void_p * 2)(*[m._h for m in dp])
+        ctx.check(lib().vgpu_prove_device(ctx._h, a, b, C.byref(out), C.byref(n)))
+    else:
+        keep = [_as_u32(m) for m in traces.main] + [_as_u32(m) for m in traces.preprocessed]
+        a = (_Matrix * NUM_CHIPS)(*[_mat(m) for m in keep[:NUM_CHIPS]])
+        b = (_Matrix * 2)(*[_mat(m) for m in keep[NUM_CHIPS:]])
+        ctx.check(lib().vgpu_prove(ctx._h, a, b, REPR_CANONICAL, C.byref(out), C.byref(n)))
+    proof = bytes(bytearray(out[: n.value])) if n.value < (1 << 22) else C.string_at(out, n.value)
+    lib().vgpu_free_bytes(out)
+    return proof
+
+
+def last_prove_phases(ctx):
+    names = (C.c_char_p * 32)()
+    ms = (C.c_float * 32)()
+    n = lib().vgpu_last_prove_phases(ctx._h, names, ms, 32)
+    return [(names[i].decode(), float(ms[i])) for i in range(min(n, 32))]
 
 
 class MachineTraces:

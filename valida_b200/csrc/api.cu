@@ -53,6 +53,8 @@ int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t sca
     return 0;
 }
 
+void vg_host_state_free(vgpu_ctx* ctx);
+
 extern "C" {
 
 int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
@@ -80,6 +82,7 @@ int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
 
 void vgpu_ctx_destroy(vgpu_ctx* ctx) {
     if (!ctx) return;
+    vg_host_state_free(ctx);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         vg_free(ctx, ctx->root_table.lo); vg_free(ctx, ctx->root_table.hi);

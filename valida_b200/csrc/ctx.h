@@ -34,6 +34,9 @@ struct vgpu_ctx {
     uint32_t poseidon_mds[256];
     bool challenger_set = false;
     bool poseidon_has_mds = false;
+    void* challenger = nullptr;                                  // vgh::Challenger* (host/challenger.h)
+    void* poseidon = nullptr;                                    // vgh::Poseidon16*
+    std::vector<std::pair<const char*, float>> phases;          // last prove: per-phase milliseconds
 };
 
 struct vgpu_dmat {

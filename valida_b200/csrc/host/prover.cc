@@ -1,0 +1,432 @@
+// Machine::prove on the device — orchestration, transcript and proof assembly.
+// Mirrors, step for step, the reference's prove() (derive/src/lib.rs:275-446; hand copy
+// basic/src/lib.rs:147-675) and TwoAdicFriPcs::open_multi_batches / p3-fri prove
+// [P3-UNVERIFIED; SURVEY App. A items 14, 15]; every observe/sample occurs in the reference's order.
+// Heavy steps are the CUDA kernels of ntt.cu / merkle.cu / perm.cu / quotient.cu / open.cu; this file
+// holds no field loops over trace-sized data.
+#include "../ctx.h"
+#include "../merkle.h"
+#include "../open.h"
+#include "../devchip.h"
+#include "challenger.h"
+#include <array>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <memory>
+
+using bb::E5;
+
+namespace {
+
+constexpr int LOG_BLOWUP = 1, NUM_QUERIES = 40, POW_BITS = 8;   // basic/src/bin/valida.rs:385-390
+
+using Digest = std::array<uint32_t, 8>;   // canonical words
+struct ExtC { uint32_t c[5]; };           // canonical
+ExtC canon(const E5& e) { ExtC r; for (int i = 0; i < 5; i++) r.c[i] = bb::from_monty(e.c[i]); return r; }
+
+struct BatchOpeningH { std::vector<std::vector<uint32_t>> opened_values; std::vector<Digest> opening_proof; };
+struct CommitPhaseStepH { ExtC sibling_value; std::vector<Digest> opening_proof; };
+struct QueryProofH { std::vector<CommitPhaseStepH> steps; };
+struct FriProofH { std::vector<Digest> commit_phase_commits; std::vector<QueryProofH> query_proofs; ExtC final_poly; uint32_t pow_witness; };
+struct OpeningH {
+    std::vector<std::vector<std::vector<std::vector<ExtC>>>> values;   // [round][matrix][point][column]
+    FriProofH fri;
+    std::vector<std::vector<BatchOpeningH>> query_openings;             // [query][round]
+};
+struct OpenRound { const vgpu_prover_data* pd; std::vector<std::vector<E5>> points; };
+
+struct FriLayer {
+    uint32_t* values = nullptr;   // limb-major ext5 vector of length n
+    uint64_t n = 0;
+    uint32_t* digests = nullptr;
+    std::vector<uint32_t*> layer_ptr; std::vector<uint64_t> layer_len;
+};
+
+struct PointKey {
+    uint32_t log_H; uint32_t c[5];
+    bool operator<(const PointKey& o) const { if (log_H != o.log_H) return log_H < o.log_H; return std::memcmp(c, o.c, 20) < 0; }
+};
+
+int log2u(uint64_t n) { int l = 0; while ((1ull << l) < n) l++; return l; }
+
+int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, vgh::Challenger& ch, OpeningH* out) {
+    const E5 alpha = ch.sample_ext();
+    // alpha^c table
+    uint32_t max_w = 1;
+    for (auto& r : rounds) for (auto* m : r.pd->ldes) max_w = std::max<uint32_t>(max_w, (uint32_t)m->w);
+    std::vector<E5> apow(max_w);
+    { E5 a = bb::e5_one(); for (uint32_t c = 0; c < max_w; c++) { apow[c] = a; a = bb::e5_mul(a, alpha); } }
+    E5* d_apow = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&d_apow, max_w * sizeof(E5)));
+    VG_CUDA(ctx, cudaMemcpyAsync(d_apow, apow.data(), max_w * sizeof(E5), cudaMemcpyHostToDevice, ctx->stream));
+
+    std::map<PointKey, uint32_t*> invden;       // (height, point) -> 1/(x - z) over the whole coset
+    uint32_t* ro[32] = {nullptr};
+    uint64_t num_reduced[32] = {0};
+    auto cleanup = [&]() {
+        for (auto& kv : invden) vg_free(ctx, kv.second);
+        invden.clear();
+        vg_free(ctx, d_apow);
+    };
+    out->values.clear();
+    for (const OpenRound& rd : rounds) {
+        out->values.emplace_back();
+        for (size_t mi = 0; mi < rd.pd->ldes.size(); mi++) {
+            const vgpu_dmat* lde = rd.pd->ldes[mi];
+            const uint32_t log_H = (uint32_t)log2u(lde->h), w = (uint32_t)lde->w;
+            const std::vector<E5>& pts = rd.points[mi];
+            if (pts.empty() || pts.size() > 2) { cleanup(); VG_FAIL(ctx, "open: 1 or 2 points per matrix are supported"); }
+            if (!ro[log_H]) {
+                VG_TRY(vg_alloc(ctx, (void**)&ro[log_H], 5 * lde->h * 4));
+                VG_CUDA(ctx, cudaMemsetAsync(ro[log_H], 0, 5 * lde->h * 4, ctx->stream));
+            }
+            const uint32_t* dens[2] = {nullptr, nullptr};
+            for (size_t q = 0; q < pts.size(); q++) {
+                PointKey key; key.log_H = log_H; std::memcpy(key.c, pts[q].c, 20);
+                auto it = invden.find(key);
+                if (it == invden.end()) {
+                    uint32_t* buf = nullptr;
+                    VG_TRY(vg_alloc(ctx, (void**)&buf, 5 * lde->h * 4));
+                    VG_TRY(vg_inverse_denominators(ctx, log_H, pts[q], buf));
+                    it = invden.emplace(key, buf).first;
+                }
+                dens[q] = it->second;
+            }
+            std::vector<E5> ys;
+            VG_TRY(vg_eval_columns(ctx, lde, (uint32_t)pts.size(), pts.data(), dens, &ys));
+            E5 sum_y[2], alpha_off[2];
+            out->values.back().emplace_back();
+            for (size_t q = 0; q < pts.size(); q++) {
+                E5 s = bb::e5_zero();
+                std::vector<ExtC> yc(w);
+                for (uint32_t c = 0; c < w; c++) { s = bb::e5_add(s, bb::e5_mul(apow[c], ys[q * w + c])); yc[c] = canon(ys[q * w + c]); }
+                sum_y[q] = s;
+                alpha_off[q] = bb::e5_pow(alpha, num_reduced[log_H]);
+                num_reduced[log_H] += w;
+                out->values.back().back().push_back(std::move(yc));
+            }
+            VG_TRY(vg_reduced_opening_accumulate(ctx, lde, d_apow, (uint32_t)pts.size(), dens, sum_y, alpha_off, ro[log_H]));
+        }
+    }
+    cleanup();
+
+    // ---- p3-fri prove: commit phase --------------------------------------------------------------
+    int log_max = 31;
+    while (log_max >= 0 && !ro[log_max]) log_max--;
+    if (log_max < LOG_BLOWUP) VG_FAIL(ctx, "open: nothing to open");
+    std::vector<FriLayer> layers;
+    uint32_t* current = ro[log_max];
+    uint64_t cur_n = 1ull << log_max;
+    ro[log_max] = nullptr;
+    for (int lfh = log_max - 1; lfh >= LOG_BLOWUP; lfh--) {
+        FriLayer L;
+        L.values = current; L.n = cur_n;
+        uint64_t npairs = cur_n / 2;
+        VG_TRY(vg_alloc(ctx, (void**)&L.digests, 2 * npairs * 32));
+        Digest root;
+        VG_TRY(vg_fri_layer_commit(ctx, current, cur_n, npairs, L.digests, &L.layer_ptr, &L.layer_len, root.data()));
+        ch.observe_digest_canonical(root.data());
+        out->fri.commit_phase_commits.push_back(root);
+        E5 beta = ch.sample_ext();
+        uint32_t* next = nullptr;
+        VG_TRY(vg_alloc(ctx, (void**)&next, 5 * npairs * 4));
+        VG_TRY(vg_fri_fold(ctx, current, cur_n, beta, ro[lfh], next));
+        if (ro[lfh]) { vg_free(ctx, ro[lfh]); ro[lfh] = nullptr; }
+        layers.push_back(std::move(L));
+        current = next; cur_n = npairs;
+    }
+    for (int i = 0; i < 32; i++) if (ro[i]) { vg_free(ctx, ro[i]); ro[i] = nullptr; }
+    {
+        std::vector<uint32_t> fin(5 * cur_n);
+        VG_CUDA(ctx, cudaMemcpyAsync(fin.data(), current, fin.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        vg_free(ctx, current);
+        E5 f0;
+        for (int l = 0; l < 5; l++) f0.c[l] = fin[l * cur_n];
+        for (uint64_t i = 1; i < cur_n; i++)
+            for (int l = 0; l < 5; l++)
+                if (fin[l * cur_n + i] != f0.c[l]) VG_FAIL(ctx, "FRI: final layer is not constant (the committed functions are not low degree)");
+        out->fri.final_poly = canon(f0);
+    }
+    out->fri.pow_witness = bb::from_monty(ch.grind(POW_BITS));
+    std::vector<uint64_t> indices;
+    for (int q = 0; q < NUM_QUERIES; q++) indices.push_back(ch.sample_bits(log_max));
+
+    // ---- query phase: one gather for every word the proof needs -----------------------------------
+    std::vector<const uint32_t*> ptrs;
+    auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) ptrs.push_back(d + k); };
+    for (uint64_t index : indices) {
+        for (size_t i = 0; i < layers.size(); i++) {
+            const FriLayer& L = layers[i];
+            uint64_t index_i = index >> i, sib = index_i ^ 1, pair = index_i >> 1;
+            for (int l = 0; l < 5; l++) ptrs.push_back(L.values + (uint64_t)l * L.n + sib);
+            for (size_t lvl = 0; lvl + 1 < L.layer_ptr.size(); lvl++) push_digest(L.layer_ptr[lvl] + ((pair >> lvl) ^ 1) * 8);
+        }
+        for (const OpenRound& rd : rounds) {
+            int lg = log2u(rd.pd->max_height);
+            uint64_t bidx = index >> (log_max - lg);
+            for (auto* m : rd.pd->ldes) {
+                uint64_t row = bidx >> (lg - log2u(m->h));
+                for (uint64_t c = 0; c < m->w; c++) ptrs.push_back(m->d + c * m->col_stride + row);
+            }
+            for (int lvl = 0; lvl < lg; lvl++) push_digest(rd.pd->layer_ptr[lvl] + ((bidx >> lvl) ^ 1) * 8);
+        }
+    }
+    std::vector<uint32_t> words;
+    VG_TRY(vg_gather_words(ctx, ptrs, &words));
+    size_t pos = 0;
+    auto take_digest = [&]() { Digest d; for (int k = 0; k < 8; k++) d[k] = words[pos++]; return d; };
+    for (size_t qi = 0; qi < indices.size(); qi++) {
+        QueryProofH qp;
+        for (size_t i = 0; i < layers.size(); i++) {
+            CommitPhaseStepH st;
+            for (int l = 0; l < 5; l++) st.sibling_value.c[l] = bb::from_monty(words[pos++]);
+            for (size_t lvl = 0; lvl + 1 < layers[i].layer_ptr.size(); lvl++) st.opening_proof.push_back(take_digest());
+            qp.steps.push_back(std::move(st));
+        }
+        out->fri.query_proofs.push_back(std::move(qp));
+        out->query_openings.emplace_back();
+        for (const OpenRound& rd : rounds) {
+            BatchOpeningH bo;
+            int lg = log2u(rd.pd->max_height);
+            for (auto* m : rd.pd->ldes) {
+                std::vector<uint32_t> row(m->w);
+                for (uint64_t c = 0; c < m->w; c++) row[c] = bb::from_monty(words[pos++]);
+                bo.opened_values.push_back(std::move(row));
+            }
+            for (int lvl = 0; lvl < lg; lvl++) bo.opening_proof.push_back(take_digest());
+            out->query_openings.back().push_back(std::move(bo));
+        }
+    }
+    for (auto& L : layers) { vg_free(ctx, L.values); vg_free(ctx, L.digests); }
+    return 0;
+}
+
+// ---- CBOR (serde/ciborium image of MachineProof; machine/src/proof.rs:13-44) -------------------------
+struct Cbor {
+    std::vector<uint8_t> b;
+    void head(uint8_t major, uint64_t v) {
+        uint8_t m = (uint8_t)(major << 5);
+        if (v < 24) b.push_back(m | (uint8_t)v);
+        else if (v <= 0xff) { b.push_back(m | 24); b.push_back((uint8_t)v); }
+        else if (v <= 0xffff) { b.push_back(m | 25); b.push_back((uint8_t)(v >> 8)); b.push_back((uint8_t)v); }
+        else if (v <= 0xffffffffull) { b.push_back(m | 26); for (int s = 24; s >= 0; s -= 8) b.push_back((uint8_t)(v >> s)); }
+        else { b.push_back(m | 27); for (int s = 56; s >= 0; s -= 8) b.push_back((uint8_t)(v >> s)); }
+    }
+    void key(const char* s) { size_t n = std::strlen(s); head(3, n); b.insert(b.end(), s, s + n); }
+    void map(uint64_t n) { head(5, n); }
+    void arr(uint64_t n) { head(4, n); }
+    void felt(uint32_t canonical) { map(1); key("value"); head(0, bb::to_monty(canonical)); }   // BabyBear { value } holds the Montgomery word
+    void ext(const ExtC& e) { map(1); key("value"); arr(5); for (int i = 0; i < 5; i++) felt(e.c[i]); }
+    void digest(const Digest& d) { arr(8); for (int i = 0; i < 8; i++) felt(d[i]); }
+    void digests(const std::vector<Digest>& v) { arr(v.size()); for (auto& d : v) digest(d); }
+    void exts(const std::vector<ExtC>& v) { arr(v.size()); for (auto& e : v) ext(e); }
+};
+
+struct Phase {
+    vgpu_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
+    Phase(vgpu_ctx* c, const char* n) : ctx(c), name(n) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
+    ~Phase() { cudaStreamSynchronize(ctx->stream); ctx->phases.push_back({name, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count()}); }
+};
+
+vgh::Poseidon16* poseidon_of(vgpu_ctx* ctx) {
+    if (!ctx->poseidon) {
+        auto* p = new vgh::Poseidon16();
+        p->set(ctx->poseidon_rc, ctx->poseidon_has_mds ? ctx->poseidon_mds : nullptr);
+        ctx->poseidon = p;
+    }
+    return (vgh::Poseidon16*)ctx->poseidon;
+}
+
+struct PdGuard { vgpu_prover_data* p = nullptr; ~PdGuard() { if (p) vgpu_prover_data_free(p); } };
+struct MatGuard { std::vector<vgpu_dmat*> v; ~MatGuard() { for (auto* m : v) vgpu_dmat_free(m); } };
+
+}  // namespace
+
+void vg_host_state_free(vgpu_ctx* ctx) {
+    delete (vgh::Challenger*)ctx->challenger; ctx->challenger = nullptr;
+    delete (vgh::Poseidon16*)ctx->poseidon; ctx->poseidon = nullptr;
+}
+
+extern "C" {
+
+int32_t vgpu_challenger_reset(vgpu_ctx* ctx) {
+    if (!ctx->challenger_set) VG_FAIL(ctx, "challenger: vgpu_set_challenger has not been called");
+    delete (vgh::Poseidon16*)ctx->poseidon; ctx->poseidon = nullptr;
+    delete (vgh::Challenger*)ctx->challenger;
+    auto* c = new vgh::Challenger();
+    c->perm = poseidon_of(ctx);
+    ctx->challenger = c;
+    return 0;
+}
+int32_t vgpu_challenger_observe(vgpu_ctx* ctx, const uint32_t* values, uint32_t n) {
+    if (!ctx->challenger) VG_TRY(vgpu_challenger_reset(ctx));
+    for (uint32_t i = 0; i < n; i++) ((vgh::Challenger*)ctx->challenger)->observe(bb::to_monty(values[i] % bb::P));
+    return 0;
+}
+int32_t vgpu_challenger_sample_ext(vgpu_ctx* ctx, uint32_t out[5]) {
+    if (!ctx->challenger) VG_TRY(vgpu_challenger_reset(ctx));
+    E5 e = ((vgh::Challenger*)ctx->challenger)->sample_ext();
+    for (int i = 0; i < 5; i++) out[i] = bb::from_monty(e.c[i]);
+    return 0;
+}
+
+int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CHIPS], const vgpu_dmat* const prep[2],
+                          uint8_t** proof_out, uint64_t* proof_len) {
+    if (!ctx->challenger_set) VG_FAIL(ctx, "prove: vgpu_set_challenger has not been called");
+    if (!proof_out || !proof_len) VG_FAIL(ctx, "prove: null output");
+    ctx->phases.clear();
+    const vgpu_chip_desc* chips[VGPU_NUM_CHIPS];
+    int log_degrees[VGPU_NUM_CHIPS];
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
+        chips[i] = vgpu_basic_machine_chip(i);
+        if (!main[i] || main[i]->w != chips[i]->width) VG_FAIL(ctx, "prove: chip %d trace has width %llu, expected %u", i, main[i] ? (unsigned long long)main[i]->w : 0ull, chips[i]->width);
+        log_degrees[i] = log2u(main[i]->h);
+        if ((1ull << log_degrees[i]) != main[i]->h) VG_FAIL(ctx, "prove: chip %d trace height is not a power of two", i);
+    }
+    vgh::Challenger ch;
+    { delete (vgh::Poseidon16*)ctx->poseidon; ctx->poseidon = nullptr; }
+    ch.perm = poseidon_of(ctx);
+
+    PdGuard prep_pd, main_pd, perm_pd, quot_pd;
+    uint32_t digest[8];
+    {   // preprocessed commit (derive:299-311)
+        Phase ph(ctx, "commit preprocessed");
+        VG_TRY(vgpu_commit_batches(ctx, prep, 2, nullptr, digest, &prep_pd.p));
+        ch.observe_digest_canonical(digest);
+    }
+    Digest main_commit, perm_commit, quot_commit;
+    {   // main commit (313-332)
+        Phase ph(ctx, "commit main");
+        VG_TRY(vgpu_commit_batches(ctx, main, VGPU_NUM_CHIPS, nullptr, main_commit.data(), &main_pd.p));
+        ch.observe_digest_canonical(main_commit.data());
+    }
+    uint32_t perm_challenges[15];
+    for (int i = 0; i < 3; i++) { E5 e = ch.sample_ext(); for (int l = 0; l < 5; l++) perm_challenges[5 * i + l] = bb::from_monty(e.c[l]); }
+    uint32_t cumsum[VGPU_NUM_CHIPS][5];
+    {   // permutation traces (339-358)
+        MatGuard perms;
+        {
+            Phase ph(ctx, "permutation traces");
+            for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
+                const vgpu_dmat* p = i == 1 ? prep[0] : i == 12 ? prep[1] : nullptr;
+                vgpu_dmat* pm = nullptr;
+                VG_TRY(vgpu_perm_trace(ctx, chips[i], main[i], p, perm_challenges, &pm, cumsum[i]));
+                perms.v.push_back(pm);
+            }
+        }
+        Phase ph(ctx, "commit permutation");
+        VG_TRY(vgpu_commit_batches(ctx, perms.v.data(), VGPU_NUM_CHIPS, nullptr, perm_commit.data(), &perm_pd.p));
+        ch.observe_digest_canonical(perm_commit.data());
+    }
+    E5 alpha = ch.sample_ext();
+    uint32_t alpha_c[5];
+    for (int l = 0; l < 5; l++) alpha_c[l] = bb::from_monty(alpha.c[l]);
+    {   // quotients (246-270, 362-374)
+        MatGuard quots;
+        {
+            Phase ph(ctx, "quotient");
+            int prep_idx = 0;
+            for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
+                const vgpu_dmat* plde = chips[i]->preprocessed_width ? prep_pd.p->ldes[prep_idx++] : nullptr;
+                vgpu_dmat* q = nullptr;
+                VG_TRY(vgpu_quotient(ctx, chips[i], (uint32_t)log_degrees[i], plde, main_pd.p->ldes[i], perm_pd.p->ldes[i], cumsum[i], perm_challenges, alpha_c, &q));
+                quots.v.push_back(q);
+            }
+        }
+        Phase ph(ctx, "commit quotient");
+        uint32_t shifts[VGPU_NUM_CHIPS];
+        for (int i = 0; i < VGPU_NUM_CHIPS; i++) shifts[i] = (uint32_t)(((uint64_t)bb::GEN_CANON * bb::GEN_CANON) % bb::P);   // coset_shift^(2^log_quotient_degree)
+        VG_TRY(vgpu_commit_batches(ctx, quots.v.data(), VGPU_NUM_CHIPS, shifts, quot_commit.data(), &quot_pd.p));
+        ch.observe_digest_canonical(quot_commit.data());
+    }
+    E5 zeta = ch.sample_ext();
+    // openings (379-392): main & perm at [zeta, zeta*g_i], quotient at [zeta^2]; preprocessed is NOT opened
+    std::vector<OpenRound> rounds(3);
+    rounds[0].pd = main_pd.p; rounds[1].pd = perm_pd.p; rounds[2].pd = quot_pd.p;
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
+        E5 zg = bb::e5_mul_base(zeta, bb::two_adic_generator_monty(log_degrees[i]));
+        rounds[0].points.push_back({zeta, zg});
+        rounds[1].points.push_back({zeta, zg});
+        rounds[2].points.push_back({bb::e5_sqr(zeta)});
+    }
+    OpeningH op;
+    {
+        Phase ph(ctx, "open (evaluate + FRI)");
+        VG_TRY(open_multi_batches(ctx, rounds, ch, &op));
+    }
+    // MachineProof -> CBOR
+    Cbor w;
+    w.map(3);
+    w.key("commitments"); w.map(3);
+    w.key("main_trace"); w.digest(main_commit);
+    w.key("perm_trace"); w.digest(perm_commit);
+    w.key("quotient_chunks"); w.digest(quot_commit);
+    w.key("opening_proof"); w.map(2);
+    w.key("fri_proof"); w.map(4);
+    w.key("commit_phase_commits"); w.digests(op.fri.commit_phase_commits);
+    w.key("query_proofs"); w.arr(op.fri.query_proofs.size());
+    for (auto& q : op.fri.query_proofs) {
+        w.map(1); w.key("commit_phase_openings"); w.arr(q.steps.size());
+        for (auto& s : q.steps) { w.map(2); w.key("sibling_value"); w.ext(s.sibling_value); w.key("opening_proof"); w.digests(s.opening_proof); }
+    }
+    w.key("final_poly"); w.ext(op.fri.final_poly);
+    w.key("pow_witness"); w.felt(op.fri.pow_witness);
+    w.key("query_openings"); w.arr(op.query_openings.size());
+    for (auto& q : op.query_openings) {
+        w.arr(q.size());
+        for (auto& bo : q) {
+            w.map(2);
+            w.key("opened_values"); w.arr(bo.opened_values.size());
+            for (auto& row : bo.opened_values) { w.arr(row.size()); for (uint32_t x : row) w.felt(x); }
+            w.key("opening_proof"); w.digests(bo.opening_proof);
+        }
+    }
+    w.key("chip_proofs"); w.arr(VGPU_NUM_CHIPS);
+    const std::vector<ExtC> none;
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
+        w.map(3);
+        w.key("log_degree"); w.head(0, (uint64_t)log_degrees[i]);
+        w.key("opened_values"); w.map(7);
+        w.key("preprocessed_local"); w.exts(none);
+        w.key("preprocessed_next"); w.exts(none);
+        w.key("trace_local"); w.exts(op.values[0][i][0]);
+        w.key("trace_next"); w.exts(op.values[0][i][1]);
+        w.key("permutation_local"); w.exts(op.values[1][i][0]);
+        w.key("permutation_next"); w.exts(op.values[1][i][1]);
+        w.key("quotient_chunks"); w.exts(op.values[2][i][0]);
+        w.key("cumulative_sum");
+        ExtC cs; for (int l = 0; l < 5; l++) cs.c[l] = cumsum[i][l];
+        w.ext(cs);
+    }
+    uint8_t* buf = (uint8_t*)std::malloc(w.b.size());
+    if (!buf) VG_FAIL(ctx, "out of host memory");
+    std::memcpy(buf, w.b.data(), w.b.size());
+    *proof_out = buf; *proof_len = w.b.size();
+    return 0;
+}
+
+int32_t vgpu_prove(vgpu_ctx* ctx, const vgpu_matrix main[VGPU_NUM_CHIPS], const vgpu_matrix prep[2], int32_t repr,
+                   uint8_t** proof_out, uint64_t* proof_len) {
+    MatGuard dm, dp;
+    ctx->phases.clear();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) { vgpu_dmat* m = nullptr; VG_TRY(vgpu_dmat_upload(ctx, &main[i], repr, &m)); dm.v.push_back(m); }
+    for (int i = 0; i < 2; i++) { vgpu_dmat* m = nullptr; VG_TRY(vgpu_dmat_upload(ctx, &prep[i], repr, &m)); dp.v.push_back(m); }
+    cudaStreamSynchronize(ctx->stream);
+    float up = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    int32_t rc = vgpu_prove_device(ctx, dm.v.data(), dp.v.data(), proof_out, proof_len);
+    ctx->phases.insert(ctx->phases.begin(), {"upload traces (H2D + transpose)", up});
+    return rc;
+}
+
+void vgpu_free_bytes(uint8_t* p) { std::free(p); }
+
+uint32_t vgpu_last_prove_phases(const vgpu_ctx* ctx, const char** names, float* ms, uint32_t cap) {
+    uint32_t n = (uint32_t)ctx->phases.size();
+    for (uint32_t i = 0; i < n && i < cap; i++) { names[i] = ctx->phases[i].first; ms[i] = ctx->phases[i].second; }
+    return n;
+}
+
+}  // extern "C"

@@ -102,7 +102,47 @@ int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint
     return 0;
 }
 
+// FRI commit-phase leaf: the pair (v[2i], v[2i+1]) of ext5 values flattened to 10 base words
+// (ExtensionMmcs over a width-2 matrix); v is limb-major: limb l of element e at v[l * cs + e].
+__global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __restrict__ v, uint64_t cs, uint64_t npairs, uint32_t* __restrict__ digests) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    uint32_t w[10];
+#pragma unroll
+    for (int l = 0; l < 5; l++) {
+        uint2 t = __ldg(reinterpret_cast<const uint2*>(v + (uint64_t)l * cs + 2 * i));
+        w[l] = bb::from_monty(t.x); w[5 + l] = bb::from_monty(t.y);
+    }
+    uint32_t d[8];
+    keccak256_words(10, [&](uint32_t k) { return w[k]; }, d);
+    uint4* o = reinterpret_cast<uint4*>(digests + i * 8);
+    o[0] = make_uint4(wrap_mod_p(d[0]), wrap_mod_p(d[1]), wrap_mod_p(d[2]), wrap_mod_p(d[3]));
+    o[1] = make_uint4(wrap_mod_p(d[4]), wrap_mod_p(d[5]), wrap_mod_p(d[6]), wrap_mod_p(d[7]));
+}
+
 }  // namespace
+
+// Single-matrix tree over ext5 pairs (p3-fri commit phase): digests = [leaf layer | ... | root].
+int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint64_t npairs, uint32_t* digests,
+                            std::vector<uint32_t*>* layer_ptr, std::vector<uint64_t>* layer_len, uint32_t root_out[8]) {
+    fri_leaf_hash_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(v, cs, npairs, digests);
+    VG_LAUNCH_CHECK(ctx);
+    uint32_t* layer = digests;
+    uint64_t len = npairs;
+    layer_ptr->clear(); layer_len->clear();
+    layer_ptr->push_back(layer); layer_len->push_back(len);
+    while (len > 1) {
+        uint64_t next_len = len / 2;
+        uint32_t* next = layer + len * 8;
+        compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, nullptr, next_len, next);
+        VG_LAUNCH_CHECK(ctx);
+        layer_ptr->push_back(next); layer_len->push_back(next_len);
+        layer = next; len = next_len;
+    }
+    VG_CUDA(ctx, cudaMemcpyAsync(root_out, layer, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 // Build the mixed-height tree over the (already bit-reversed) LDE matrices in `pd->ldes`.
 int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd) {

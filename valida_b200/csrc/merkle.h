@@ -14,3 +14,5 @@ struct vgpu_prover_data {
 };
 
 int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd);
+int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint64_t npairs, uint32_t* digests,
+                            std::vector<uint32_t*>* layer_ptr, std::vector<uint64_t>* layer_len, uint32_t root_out[8]);

@@ -1,0 +1,214 @@
+// K6 + K7 — fused constraint / quotient sweep with the chunk split, one kernel per chip.
+// Replaces quotient() / quotient_values() (machine/src/quotient.rs:18-238), ProverConstraintFolder
+// (machine/src/folding_builder.rs:32-125), eval_permutation_constraints (machine/src/chip.rs:210-289)
+// and p3-uni-stark's decompose_and_flatten / ZerofierOnCoset for log_quotient_degree = 1.
+//
+// The reference gathers LDE rows through a bit-reversed view element by element; here one thread owns
+// the STORAGE row pair (2r, 2r+1) of the committed (bit-reversed) LDEs, i.e. the natural rows
+// (j, j+h) with j = bitrev(r): x and -x.  That pair is exactly what the even/odd chunk split needs,
+// so the quotient values never touch HBM: the thread folds all constraints for both rows, divides by
+// Z_H, and writes row j of the h x 10 chunk matrix directly.  "next" rows (j+2) are another storage
+// pair, so every trace load is a coalesced 8-byte access.
+// alpha-folding: acc = sum_i c_i * alpha^(N-1-i) with precomputed powers — the same value as the
+// reference's Horner recurrence acc = acc*alpha + c_i, at 5 instead of 25 multiplications for the
+// base-field constraints.
+#include "ctx.h"
+#include "devchip.h"
+#include "airs.cuh"
+
+namespace {
+
+using bb::E5;
+using air::F;
+
+struct QParams {
+    const DevChip* chip;
+    const uint32_t* main; uint64_t mcs;
+    const uint32_t* prep; uint64_t pcs;
+    const uint32_t* perm; uint64_t qcs;
+    uint32_t* out; uint64_t ocs;            // h x 10 chunk matrix
+    const E5* apow;                         // apow[i] = alpha^(N-1-i)
+    uint32_t log_h;
+    uint32_t s;                             // coset shift (Montgomery)
+    uint32_t glast;                         // g_subgroup^-1
+    uint32_t zh[2], zinv[2];                // Z_H on even / odd natural rows, and inverses
+    uint32_t odd_scale;                     // 1 / (2 s)
+    uint32_t half;                          // 1 / 2
+    E5 cumsum;
+    const uint32_t* root_lo; const uint32_t* root_hi;
+};
+
+struct DevBuilder {
+    const uint32_t* lrow; const uint32_t* nrow; uint64_t cs;   // pointers already offset to the row
+    F first, last, trans;
+    const E5* apow; uint32_t idx; E5 acc;
+    __device__ __forceinline__ F L(int c) const { return F{__ldg(lrow + (uint64_t)c * cs)}; }
+    __device__ __forceinline__ F N(int c) const { return F{__ldg(nrow + (uint64_t)c * cs)}; }
+    __device__ __forceinline__ void z(F x) { acc = bb::e5_add(acc, bb::e5_mul_base(apow[idx], x.v)); idx++; }
+    __device__ __forceinline__ void z_ext(const E5& x) { acc = bb::e5_add(acc, bb::e5_mul(apow[idx], x)); idx++; }
+};
+
+__device__ __forceinline__ uint32_t qroot_pow(const QParams& p, uint64_t e) {
+    e &= ((1ull << VG_LOG_NMAX) - 1);
+    return bb::mul(__ldg(p.root_lo + (e & (VG_POW_LO - 1))), __ldg(p.root_hi + (e >> VG_POW_LO_BITS)));
+}
+__device__ __forceinline__ uint32_t dev_pair_col(const DevPairCol& pc, const uint32_t* mrow, uint64_t mcs, const uint32_t* prow, uint64_t pcs) {
+    uint32_t v = pc.constant;
+    for (uint32_t t = 0; t < pc.n_terms; t++) {
+        uint32_t x = pc.is_prep[t] ? __ldg(prow + (uint64_t)pc.column[t] * pcs) : __ldg(mrow + (uint64_t)pc.column[t] * mcs);
+        v = bb::add(v, bb::mul(x, pc.weight[t]));
+    }
+    return v;
+}
+__device__ __forceinline__ E5 load_e5(const uint32_t* row, uint64_t cs, uint32_t m) {
+    E5 r;
+#pragma unroll
+    for (int l = 0; l < 5; l++) r.c[l] = __ldg(row + (uint64_t)(5 * m + l) * cs);
+    return r;
+}
+
+template <int CHIP>
+__global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
+    const uint64_t h = 1ull << p.log_h;
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= h) return;
+    const uint32_t j = bb::reverse_bits((uint32_t)r, (int)p.log_h);
+    // next rows: natural (j+2) mod 2h for row j, and the partner of that for row j+h
+    const uint64_t t = (uint64_t)j + 2;
+    const uint32_t a = (uint32_t)(t & (h - 1));
+    const uint32_t swap = (uint32_t)((t >> p.log_h) & 1);
+    const uint64_t rn = bb::reverse_bits(a, (int)p.log_h);
+    const uint32_t x0 = bb::mul(p.s, qroot_pow(p, (uint64_t)j << (VG_LOG_NMAX - p.log_h - 1)));
+    // selectors: 1/(x-1), 1/(x-glast) for x = +-x0, one shared inversion
+    uint32_t den[4] = {bb::sub(x0, bb::R1), bb::sub(x0, p.glast), bb::sub(bb::neg(x0), bb::R1), bb::sub(bb::neg(x0), p.glast)};
+    uint32_t inv[4];
+    {
+        uint32_t p01 = bb::mul(den[0], den[1]), p23 = bb::mul(den[2], den[3]);
+        uint32_t all = bb::inv(bb::mul(p01, p23));
+        uint32_t i01 = bb::mul(all, p23), i23 = bb::mul(all, p01);
+        inv[0] = bb::mul(i01, den[1]); inv[1] = bb::mul(i01, den[0]);
+        inv[2] = bb::mul(i23, den[3]); inv[3] = bb::mul(i23, den[2]);
+    }
+    const DevChip& chip = *p.chip;
+    const uint32_t k = chip.n_interactions;
+    E5 q[2];
+#pragma unroll 1
+    for (int e = 0; e < 2; e++) {
+        const uint64_t srow = 2 * r + e, nrow = 2 * rn + (e ^ swap);
+        const uint32_t parity = (e == 0) ? (j & 1) : (uint32_t)((j + h) & 1);
+        const uint32_t x = e ? bb::neg(x0) : x0;
+        const uint32_t zh = p.zh[parity];
+        DevBuilder b;
+        b.lrow = p.main + srow; b.nrow = p.main + nrow; b.cs = p.mcs;
+        b.first = F{bb::mul(zh, inv[2 * e])};
+        b.last = F{bb::mul(zh, inv[2 * e + 1])};
+        b.trans = F{bb::sub(x, p.glast)};
+        b.apow = p.apow; b.idx = 0; b.acc = bb::e5_zero();
+        air::eval_chip<CHIP>(b);
+        // eval_permutation_constraints
+        const uint32_t* ql = p.perm + srow; const uint32_t* qn = p.perm + nrow;
+        const uint32_t* pl = p.prep ? p.prep + srow : nullptr; const uint32_t* pn = p.prep ? p.prep + nrow : nullptr;
+        const E5 phi_local = load_e5(ql, p.qcs, k), phi_next = load_e5(qn, p.qcs, k);
+        E5 rhs = bb::e5_zero(), phi0 = bb::e5_zero();
+        for (uint32_t m = 0; m < k; m++) {
+            const DevInteraction& it = chip.interactions[m];
+            E5 rlc = it.alpha;
+            for (uint32_t f = 0; f < it.n_fields; f++) rlc = bb::e5_add(rlc, bb::e5_mul_base(chip.betas[f], dev_pair_col(it.fields[f], b.lrow, p.mcs, pl, p.pcs)));
+            const E5 pm_l = load_e5(ql, p.qcs, m), pm_n = load_e5(qn, p.qcs, m);
+            b.z_ext(bb::e5_sub_base(bb::e5_mul(rlc, pm_l), bb::R1));
+            const uint32_t mult_l = dev_pair_col(it.count, b.lrow, p.mcs, pl, p.pcs), mult_n = dev_pair_col(it.count, b.nrow, p.mcs, pn, p.pcs);
+            const E5 tl = bb::e5_mul_base(pm_l, mult_l), tn = bb::e5_mul_base(pm_n, mult_n);
+            if (it.is_send) { phi0 = bb::e5_add(phi0, tl); rhs = bb::e5_add(rhs, tn); }
+            else { phi0 = bb::e5_sub(phi0, tl); rhs = bb::e5_sub(rhs, tn); }
+        }
+        b.z_ext(bb::e5_mul_base(bb::e5_sub(bb::e5_sub(phi_next, phi_local), rhs), b.trans.v));
+        b.z_ext(bb::e5_mul_base(bb::e5_sub(phi_local, phi0), b.first.v));
+        b.z_ext(bb::e5_mul_base(bb::e5_sub(phi_local, p.cumsum), b.last.v));
+        q[e] = bb::e5_mul_base(b.acc, p.zinv[parity]);
+    }
+    // decompose_and_flatten: even = (q(x) + q(-x))/2, odd = (q(x) - q(-x)) / (2 s g^j)
+    const uint32_t ginv_j = qroot_pow(p, (1ull << VG_LOG_NMAX) - ((uint64_t)j << (VG_LOG_NMAX - p.log_h - 1)));
+    const E5 even = bb::e5_mul_base(bb::e5_add(q[0], q[1]), p.half);
+    const E5 odd = bb::e5_mul_base(bb::e5_sub(q[0], q[1]), bb::mul(p.odd_scale, ginv_j));
+#pragma unroll
+    for (int l = 0; l < 5; l++) { p.out[(uint64_t)l * p.ocs + j] = even.c[l]; p.out[(uint64_t)(5 + l) * p.ocs + j] = odd.c[l]; }
+}
+
+struct CountBuilder {
+    F first{0}, last{0}, trans{0};
+    uint32_t n = 0;
+    BB_HD F L(int) const { return F{0}; }
+    BB_HD F N(int) const { return F{0}; }
+    BB_HD void z(F) { n++; }
+};
+template <int CHIP> uint32_t count_base() { CountBuilder c; air::eval_chip<CHIP>(c); return c.n; }
+
+template <int CHIP> void launch(const QParams& p, uint64_t h, cudaStream_t st) {
+    quotient_kernel<CHIP><<<(unsigned)((h + 127) / 128), 128, 0, st>>>(p);
+}
+
+}  // namespace
+
+uint32_t vg_chip_base_constraints(uint32_t chip_id) {
+    switch (chip_id) {
+        case 0: return count_base<0>(); case 3: return count_base<3>(); case 4: return count_base<4>(); case 5: return count_base<5>();
+        case 7: return count_base<7>(); case 8: return count_base<8>(); case 9: return count_base<9>(); case 10: return count_base<10>();
+        case 11: return count_base<11>(); case 13: return count_base<13>(); default: return 0;
+    }
+}
+
+extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint32_t log_degree, const vgpu_dmat* prep_lde,
+                                 const vgpu_dmat* main_lde, const vgpu_dmat* perm_lde, const uint32_t cumulative_sum[5],
+                                 const uint32_t perm_challenges[15], const uint32_t alpha[5], vgpu_dmat** out_chunks) {
+    if (!chip || !main_lde || !perm_lde || !out_chunks) VG_FAIL(ctx, "quotient: null argument");
+    const uint64_t h = 1ull << log_degree;
+    if (main_lde->h != 2 * h || perm_lde->h != 2 * h) VG_FAIL(ctx, "quotient: LDE height must be 2 * 2^log_degree");
+    if (main_lde->w != chip->width || perm_lde->w != 5 * (chip->n_interactions + 1)) VG_FAIL(ctx, "quotient: LDE width does not match the chip");
+    if (chip->chip_id >= VGPU_NUM_CHIPS) VG_FAIL(ctx, "quotient: unknown chip id %u", chip->chip_id);
+    DevChip* dchip = nullptr;
+    VG_TRY(vg_upload_devchip(ctx, chip, perm_challenges, &dchip));
+    // alpha powers for N = base + k + 3 constraints
+    const uint32_t N = vg_chip_base_constraints(chip->chip_id) + chip->n_interactions + 3;
+    std::vector<E5> apow(N);
+    E5 al; for (int i = 0; i < 5; i++) al.c[i] = bb::to_monty(alpha[i] % bb::P);
+    { E5 a = bb::e5_one(); for (uint32_t i = 0; i < N; i++) { apow[N - 1 - i] = a; a = bb::e5_mul(a, al); } }
+    E5* d_apow = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&d_apow, N * sizeof(E5)));
+    VG_CUDA(ctx, cudaMemcpyAsync(d_apow, apow.data(), N * sizeof(E5), cudaMemcpyHostToDevice, ctx->stream));
+    vgpu_dmat* out = nullptr;
+    VG_TRY(vg_dmat_alloc(ctx, h, 10, &out));
+    QParams p{};
+    p.chip = dchip;
+    p.main = main_lde->d; p.mcs = main_lde->col_stride;
+    p.prep = prep_lde ? prep_lde->d : nullptr; p.pcs = prep_lde ? prep_lde->col_stride : 0;
+    p.perm = perm_lde->d; p.qcs = perm_lde->col_stride;
+    p.out = out->d; p.ocs = out->col_stride;
+    p.apow = d_apow;
+    p.log_h = log_degree;
+    p.s = bb::to_monty(bb::GEN_CANON);
+    uint32_t g_sub = bb::two_adic_generator_monty((int)log_degree);
+    p.glast = bb::inv(g_sub);
+    uint32_t s_pow_n = p.s;
+    for (uint32_t i = 0; i < log_degree; i++) s_pow_n = bb::sqr(s_pow_n);
+    p.zh[0] = bb::sub(s_pow_n, bb::R1);
+    p.zh[1] = bb::sub(bb::neg(s_pow_n), bb::R1);
+    p.zinv[0] = bb::inv(p.zh[0]); p.zinv[1] = bb::inv(p.zh[1]);
+    p.half = bb::inv(bb::to_monty(2));
+    p.odd_scale = bb::mul(p.half, bb::inv(p.s));
+    for (int i = 0; i < 5; i++) p.cumsum.c[i] = bb::to_monty(cumulative_sum[i] % bb::P);
+    p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi;
+    switch (chip->chip_id) {
+        case 0: launch<0>(p, h, ctx->stream); break;   case 1: launch<1>(p, h, ctx->stream); break;
+        case 2: launch<2>(p, h, ctx->stream); break;   case 3: launch<3>(p, h, ctx->stream); break;
+        case 4: launch<4>(p, h, ctx->stream); break;   case 5: launch<5>(p, h, ctx->stream); break;
+        case 6: launch<6>(p, h, ctx->stream); break;   case 7: launch<7>(p, h, ctx->stream); break;
+        case 8: launch<8>(p, h, ctx->stream); break;   case 9: launch<9>(p, h, ctx->stream); break;
+        case 10: launch<10>(p, h, ctx->stream); break; case 11: launch<11>(p, h, ctx->stream); break;
+        case 12: launch<12>(p, h, ctx->stream); break; case 13: launch<13>(p, h, ctx->stream); break;
+    }
+    VG_LAUNCH_CHECK(ctx);
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // apow host vector / device temporaries
+    vg_free(ctx, d_apow); vg_free(ctx, dchip);
+    *out_chunks = out;
+    return 0;
+}
