@@ -46,6 +46,11 @@ const char* vgpu_last_error(const vgpu_ctx* ctx);
 int32_t vgpu_ctx_synchronize(vgpu_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t vgpu_ctx_launch_count(const vgpu_ctx* ctx);
+/* Optional per-kernel-class CUDA-event timing (event pairs on the context's stream around every launch).
+ * vgpu_ctx_kernel_stats synchronises, drains the records and returns the number of classes written:
+ * names[i] (static strings), launches, summed milliseconds and summed algorithmic bytes. */
+int32_t vgpu_ctx_set_kernel_timing(vgpu_ctx* ctx, int32_t on);
+uint32_t vgpu_ctx_kernel_stats(vgpu_ctx* ctx, const char** names, uint32_t* launches, float* ms, double* bytes, uint32_t cap);
 /* Poseidon instance of the DuplexChallenger, as the Rust side builds it
  * (basic/src/bin/valida.rs:360-365,382,397): 480 round constants (canonical), 16x16 MDS matrix
  * row-major or NULL for CosetMds<_,16>::default(). */

@@ -15,6 +15,7 @@
 #include <vector>
 #include <array>
 #include <cassert>
+#include <algorithm>
 
 namespace orc {
 
@@ -124,15 +125,37 @@ static inline std::vector<T> batch_inverse_generic(const std::vector<T>& v, Inv 
 struct MulU32 { uint32_t v; };
 static inline std::vector<uint32_t> batch_inverse(const std::vector<uint32_t>& v) {
     size_t n = v.size();
-    std::vector<uint32_t> out(n), pref(n);
-    uint32_t acc = 1;
-    for (size_t i = 0; i < n; i++) { pref[i] = acc; acc = mul(acc, v[i]); }
-    uint32_t ia = inv(acc);
-    for (size_t i = n; i-- > 0;) { out[i] = mul(ia, pref[i]); ia = mul(ia, v[i]); }
+    std::vector<uint32_t> out(n);
+    const size_t CH = 8192;
+    long nch = (long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static) if (n > 4 * CH)
+    for (long c = 0; c < nch; c++) {
+        size_t a = (size_t)c * CH, b = std::min(n, a + CH);
+        std::vector<uint32_t> pref(b - a);
+        uint32_t acc = 1;
+        for (size_t i = a; i < b; i++) { pref[i - a] = acc; acc = mul(acc, v[i]); }
+        uint32_t ia = inv(acc);
+        for (size_t i = b; i-- > a;) { out[i] = mul(ia, pref[i - a]); ia = mul(ia, v[i]); }
+    }
     return out;
 }
+// chunked so that the Montgomery trick runs on all cores (the reference's p3_field version is serial;
+// results are identical — inversion is exact)
 static inline std::vector<Ext5> batch_inverse(const std::vector<Ext5>& v) {
-    return batch_inverse_generic<Ext5>(v, [](const Ext5& x) { return ext_inv(x); }, Ext5::one());
+    size_t n = v.size();
+    std::vector<Ext5> out(n);
+    const size_t CH = 4096;
+    long nch = (long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static) if (n > 4 * CH)
+    for (long c = 0; c < nch; c++) {
+        size_t a = (size_t)c * CH, b = std::min(n, a + CH);
+        std::vector<Ext5> pref(b - a);
+        Ext5 acc = Ext5::one();
+        for (size_t i = a; i < b; i++) { pref[i - a] = acc; acc = acc * v[i]; }
+        Ext5 ia = ext_inv(acc);
+        for (size_t i = b; i-- > a;) { out[i] = ia * pref[i - a]; ia = ia * v[i]; }
+    }
+    return out;
 }
 // valida util::batch_multiplicative_inverse_allowing_zero (util/src/lib.rs:21-43): zeros stay zero.
 static inline std::vector<Ext5> batch_inverse_allowing_zero(const std::vector<Ext5>& v) {

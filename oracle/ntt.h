@@ -14,9 +14,10 @@ static inline void bit_reverse_rows(Matrix& m) {
     size_t h = m.height(), w = m.width;
     if (h <= 1) return;
     int lg = log2_strict(h);
-    for (size_t i = 0; i < h; i++) {
+#pragma omp parallel for schedule(static) if (h * w > (1u << 16))
+    for (long i = 0; i < (long)h; i++) {
         size_t j = reverse_bits_len((uint32_t)i, lg);
-        if (i < j) for (size_t c = 0; c < w; c++) std::swap(m.v[i * w + c], m.v[j * w + c]);
+        if ((size_t)i < j) for (size_t c = 0; c < w; c++) std::swap(m.v[i * w + c], m.v[j * w + c]);
     }
 }
 
@@ -63,11 +64,11 @@ static inline Matrix coset_lde_batch(const Matrix& in, int added_bits, uint32_t 
     Matrix coeffs = idft_batch(in);
     size_t h = in.height(), w = in.width, H = h << added_bits;
     Matrix out(H, w);
-    uint32_t s = 1;
-    for (size_t i = 0; i < h; i++) {
-        for (size_t c = 0; c < w; c++) out.v[i * w + c] = mul(coeffs.v[i * w + c], s);
-        s = mul(s, shift);
-    }
+    std::vector<uint32_t> sp(h);
+    { uint32_t s = 1; for (size_t i = 0; i < h; i++) { sp[i] = s; s = mul(s, shift); } }
+#pragma omp parallel for schedule(static) if (h * w > (1u << 16))
+    for (long i = 0; i < (long)h; i++)
+        for (size_t c = 0; c < w; c++) out.v[i * w + c] = mul(coeffs.v[i * w + c], sp[i]);
     dft_rows(out, false);
     return out;
 }

@@ -99,13 +99,21 @@ struct Pcs {
         std::vector<uint32_t> xs(h);
         { uint32_t x = s; for (size_t i = 0; i < h; i++) { xs[i] = x; x = mul(x, om); } }
         std::vector<Ext5> den(h);
-        for (size_t i = 0; i < h; i++) den[i] = z - xs[i];
+#pragma omp parallel for schedule(static) if (h > 4096)
+        for (long i = 0; i < (long)h; i++) den[i] = z - xs[i];
         std::vector<Ext5> dinv = batch_inverse(den);
         std::vector<Ext5> acc(w, Ext5::zero());
-        for (size_t i = 0; i < h; i++) {
-            Ext5 wgt = dinv[i] * xs[i];
-            const uint32_t* row = lde.row(reverse_bits_len((uint32_t)i, lg));
-            for (size_t c = 0; c < w; c++) acc[c] += wgt * row[c];
+#pragma omp parallel if (h > 4096)
+        {
+            std::vector<Ext5> loc(w, Ext5::zero());
+#pragma omp for schedule(static) nowait
+            for (long i = 0; i < (long)h; i++) {
+                Ext5 wgt = dinv[i] * xs[i];
+                const uint32_t* row = lde.row(reverse_bits_len((uint32_t)i, lg));
+                for (size_t c = 0; c < w; c++) loc[c] += wgt * row[c];
+            }
+#pragma omp critical
+            for (size_t c = 0; c < w; c++) acc[c] += loc[c];
         }
         uint32_t sn = exp_pow2(s, lg);
         Ext5 scale = (ext_exp_pow2(z, lg) - sn) * inv(mul((uint32_t)(h % P), sn));
@@ -141,7 +149,8 @@ struct Pcs {
                     Ext5 sum_y = Ext5::zero();
                     for (size_t c = 0; c < w; c++) sum_y += apow[c] * ys[c];
                     std::vector<Ext5> den(H);
-                    for (size_t i = 0; i < H; i++) den[i] = -z + xs[i];
+#pragma omp parallel for schedule(static) if (H > 4096)
+                    for (long i = 0; i < (long)H; i++) den[i] = -z + xs[i];
                     std::vector<Ext5> dinv = batch_inverse(den);
                     std::vector<Ext5>& r = ro[lh];
 #pragma omp parallel for schedule(static) if (H * w > (1u << 14))

@@ -42,6 +42,8 @@ def _load():
         "vgpu_last_error": (C.c_char_p, [vp]),
         "vgpu_ctx_synchronize": (C.c_int32, [vp]),
         "vgpu_ctx_launch_count": (u64, [vp]),
+        "vgpu_ctx_set_kernel_timing": (C.c_int32, [vp, C.c_int32]),
+        "vgpu_ctx_kernel_stats": (C.c_uint32, [vp, C.POINTER(C.c_char_p), u32p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_uint32]),
         "vgpu_dmat_upload": (C.c_int32, [vp, C.POINTER(_Matrix), C.c_int32, C.POINTER(vp)]),
         "vgpu_dmat_download": (C.c_int32, [vp, vp, C.c_int32, u32p]),
         "vgpu_dmat_dims": (C.c_int32, [vp, C.POINTER(u64), C.POINTER(u64)]),
@@ -120,6 +122,15 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().vgpu_ctx_launch_count(self._h))
+
+    def set_kernel_timing(self, on):
+        lib().vgpu_ctx_set_kernel_timing(self._h, 1 if on else 0)
+
+    def kernel_stats(self):
+        """[(kernel class, launches, total ms, algorithmic bytes)] since the last call (synchronises)."""
+        names = (C.c_char_p * 16)(); ln = (C.c_uint32 * 16)(); ms = (C.c_float * 16)(); by = (C.c_double * 16)()
+        n = lib().vgpu_ctx_kernel_stats(self._h, names, ln, ms, by, 16)
+        return [(names[i].decode(), int(ln[i]), float(ms[i]), float(by[i])) for i in range(n)]
 
     def upload(self, row_major, repr=REPR_CANONICAL):
         """RowMajorMatrix<Val> (numpy h x w uint32) -> DeviceMatrix."""
@@ -313,7 +324,7 @@ def prove_machine(config, traces, device_resident=None):
         a = (_Matrix * NUM_CHIPS)(*[_mat(m) for m in keep[:NUM_CHIPS]])
         b = (_Matrix * 2)(*[_mat(m) for m in keep[NUM_CHIPS:]])
         ctx.check(lib().vgpu_prove(ctx._h, a, b, REPR_CANONICAL, C.byref(out), C.byref(n)))
-    proof = bytes(bytearray(out[: n.value])) if n.value < (1 << 22) else C.string_at(out, n.value)
+    proof = C.string_at(out, n.value)
     lib().vgpu_free_bytes(out)
     return proof
 

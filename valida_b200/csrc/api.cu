@@ -97,6 +97,23 @@ const char* vgpu_last_error(const vgpu_ctx* ctx) { return ctx ? ctx->err.c_str()
 int32_t vgpu_ctx_synchronize(vgpu_ctx* ctx) { VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t vgpu_ctx_launch_count(const vgpu_ctx* ctx) { return ctx->launches; }
 
+int32_t vgpu_ctx_set_kernel_timing(vgpu_ctx* ctx, int32_t on) { ctx->ktiming = on != 0; return 0; }
+static const char* KCLASS_NAMES[KC_COUNT] = {"ntt_pass_kernel", "leaf_hash_kernel", "compress_layer_kernel", "fri_leaf_hash_kernel", "transpose (rm<->cm)",
+                                             "perm trace kernels", "quotient_kernel", "inverse denominators", "bary_kernel", "reduced_opening_kernel", "fri_fold_kernel", "other"};
+uint32_t vgpu_ctx_kernel_stats(vgpu_ctx* ctx, const char** names, uint32_t* launches, float* ms, double* bytes, uint32_t cap) {
+    cudaStreamSynchronize(ctx->stream);
+    uint32_t n[KC_COUNT] = {0}; float t[KC_COUNT] = {0}; double b[KC_COUNT] = {0};
+    for (auto& k : ctx->ktimers) {
+        float e = 0;
+        if (cudaEventElapsedTime(&e, k.a, k.b) == cudaSuccess) { n[k.cls]++; t[k.cls] += e; b[k.cls] += k.bytes; }
+        ctx->event_pool.push_back(k.a); ctx->event_pool.push_back(k.b);
+    }
+    ctx->ktimers.clear();
+    uint32_t out = 0;
+    for (int c = 0; c < KC_COUNT && out < cap; c++) if (n[c]) { names[out] = KCLASS_NAMES[c]; launches[out] = n[c]; ms[out] = t[c]; bytes[out] = b[c]; out++; }
+    return out;
+}
+
 // ---- device matrices -----------------------------------------------------------------------------
 int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out) {
     if (!host || !out) VG_FAIL(ctx, "dmat_upload: null argument");

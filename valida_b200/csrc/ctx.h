@@ -19,6 +19,10 @@ struct PowTable {            // device tables of Montgomery words
     uint32_t hi_len = 0;
 };
 
+// kernel classes for the optional per-launch CUDA-event timing (bench.py's roofline line)
+enum KClass { KC_NTT = 0, KC_LEAF_HASH, KC_COMPRESS, KC_FRI_LEAF, KC_TRANSPOSE, KC_PERM, KC_QUOTIENT, KC_INVDEN, KC_BARY, KC_REDUCED_OPENING, KC_FRI_FOLD, KC_OTHER, KC_COUNT };
+struct KTimer { cudaEvent_t a, b; int cls; double bytes; };
+
 struct vgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -37,6 +41,9 @@ struct vgpu_ctx {
     void* challenger = nullptr;                                  // vgh::Challenger* (host/challenger.h)
     void* poseidon = nullptr;                                    // vgh::Poseidon16*
     std::vector<std::pair<const char*, float>> phases;          // last prove: per-phase milliseconds
+    bool ktiming = false;
+    std::vector<KTimer> ktimers;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 struct vgpu_dmat {
@@ -50,6 +57,22 @@ struct vgpu_dmat {
 #define VG_CUDA(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { VG_FAIL(ctx, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
 #define VG_TRY(expr) do { int32_t _r = (expr); if (_r != 0) return _r; } while (0)
 #define VG_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { VG_FAIL(ctx, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
+
+// RAII scope: when ctx->ktiming is on, brackets the launches inside it with a CUDA event pair on ctx->stream.
+struct KScope {
+    vgpu_ctx* ctx; bool on;
+    KScope(vgpu_ctx* c, int cls, double bytes) : ctx(c), on(c->ktiming) {
+        if (!on) return;
+        KTimer t; t.cls = cls; t.bytes = bytes;
+        for (cudaEvent_t* e : {&t.a, &t.b}) {
+            if (!c->event_pool.empty()) { *e = c->event_pool.back(); c->event_pool.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(t.a, c->stream);
+        c->ktimers.push_back(t);
+    }
+    ~KScope() { if (on) cudaEventRecord(ctx->ktimers.back().b, ctx->stream); }
+};
 
 int32_t vg_alloc(vgpu_ctx* ctx, void** p, size_t bytes);
 void vg_free(vgpu_ctx* ctx, void* p);

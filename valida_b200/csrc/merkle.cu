@@ -96,7 +96,10 @@ int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint
     VG_CUDA(ctx, cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     // the host vector must outlive the async copy from pageable memory: cudaMemcpyAsync from pageable memory
     // stages synchronously, so it is safe to let `cols` go once the call returns.
-    leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), nrows, digests);
+    {
+        KScope ks(ctx, KC_LEAF_HASH, (double)nrows * (4.0 * cols.size() + 32.0));
+        leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), nrows, digests);
+    }
     VG_LAUNCH_CHECK(ctx);
     vg_free(ctx, dcols);
     return 0;
@@ -125,7 +128,10 @@ __global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __re
 // Single-matrix tree over ext5 pairs (p3-fri commit phase): digests = [leaf layer | ... | root].
 int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint64_t npairs, uint32_t* digests,
                             std::vector<uint32_t*>* layer_ptr, std::vector<uint64_t>* layer_len, uint32_t root_out[8]) {
-    fri_leaf_hash_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(v, cs, npairs, digests);
+    {
+        KScope ks(ctx, KC_FRI_LEAF, (double)npairs * 72.0);
+        fri_leaf_hash_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(v, cs, npairs, digests);
+    }
     VG_LAUNCH_CHECK(ctx);
     uint32_t* layer = digests;
     uint64_t len = npairs;
@@ -134,7 +140,10 @@ int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint6
     while (len > 1) {
         uint64_t next_len = len / 2;
         uint32_t* next = layer + len * 8;
-        compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, nullptr, next_len, next);
+        {
+            KScope ks(ctx, KC_COMPRESS, (double)next_len * 96.0);
+            compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, nullptr, next_len, next);
+        }
         VG_LAUNCH_CHECK(ctx);
         layer_ptr->push_back(next); layer_len->push_back(next_len);
         layer = next; len = next_len;
@@ -176,7 +185,10 @@ int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd) {
             inj = inject_buf;
         }
         uint32_t* next = layer + len * 8;
-        compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, inj, next_len, next);
+        {
+            KScope ks(ctx, KC_COMPRESS, (double)next_len * (inj ? 128.0 : 96.0));
+            compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, inj, next_len, next);
+        }
         VG_LAUNCH_CHECK(ctx);
         pd->layer_ptr.push_back(next); pd->layer_len.push_back(next_len);
         layer = next; len = next_len;

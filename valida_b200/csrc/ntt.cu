@@ -165,6 +165,7 @@ int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
         PassParams q = p;
         q.src = p.src + c0 * p.src_cs; q.dst = p.dst + c0 * p.dst_cs;
         dim3 grid((unsigned)tiles, (unsigned)wc);
+        KScope ks(ctx, KC_NTT, 8.0 * (double)(p.groups << p.log_len) * (double)wc);
         ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(q);
         VG_LAUNCH_CHECK(ctx);
     }

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256) gather_words_kernel(const uint32_t* const
 
 int32_t vg_inverse_denominators(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint32_t* out) {
     uint64_t H = 1ull << log_H;
+    KScope ks(ctx, KC_INVDEN, 20.0 * (double)H);
     coset_minus_point_kernel<<<(unsigned)((H + 255) / 256), 256, 0, ctx->stream>>>(out, H, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
     VG_LAUNCH_CHECK(ctx);
     return vg_ext_batch_inverse(ctx, out, H, H, 1);
@@ -159,7 +160,10 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
     p.mat = lde->d; p.mcs = lde->col_stride; p.h = h; p.log_H = log_H; p.w = w;
     p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = H; p.npoints = npoints;
     p.s = bb::to_monty(bb::GEN_CANON); p.lo = ctx->root_table.lo; p.hi = ctx->root_table.hi; p.partial = partial;
-    bary_kernel<<<dim3(bx, by), BARY_THREADS, 0, ctx->stream>>>(p);
+    {
+        KScope ks(ctx, KC_BARY, 4.0 * (double)h * w);
+        bary_kernel<<<dim3(bx, by), BARY_THREADS, 0, ctx->stream>>>(p);
+    }
     VG_LAUNCH_CHECK(ctx);
     std::vector<uint32_t> hp(pn);
     VG_CUDA(ctx, cudaMemcpyAsync(hp.data(), partial, pn * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -193,7 +197,10 @@ int32_t vg_reduced_opening_accumulate(vgpu_ctx* ctx, const vgpu_dmat* lde, const
     p.npoints = npoints; p.ics = lde->h;
     for (uint32_t q = 0; q < npoints; q++) { p.invden[q] = invden[q]; p.sum_y[q] = sum_y[q]; p.alpha_off[q] = alpha_off[q]; }
     p.ro = ro; p.rcs = lde->h;
-    reduced_opening_kernel<<<(unsigned)((lde->h + 255) / 256), 256, 0, ctx->stream>>>(p);
+    {
+        KScope ks(ctx, KC_REDUCED_OPENING, (double)lde->h * (4.0 * lde->w + 40.0));
+        reduced_opening_kernel<<<(unsigned)((lde->h + 255) / 256), 256, 0, ctx->stream>>>(p);
+    }
     VG_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -203,6 +210,7 @@ int32_t vg_fri_fold(vgpu_ctx* ctx, const uint32_t* cur, uint64_t n, const E5& be
     uint32_t log_half = 0; while ((1ull << log_half) < half) log_half++;
     uint32_t one_half = bb::inv(bb::to_monty(2));
     E5 half_beta = bb::e5_mul_base(beta, one_half);
+    KScope ks(ctx, KC_FRI_FOLD, 60.0 * (double)half);
     fri_fold_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(cur, n, half, log_half, half_beta, one_half, add_or_null, half, out, half, ctx->root_table.lo, ctx->root_table.hi);
     VG_LAUNCH_CHECK(ctx);
     return 0;

@@ -221,6 +221,7 @@ extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, co
     const uint32_t* pd = prep_or_null ? prep_or_null->d : nullptr;
     uint64_t pcs = prep_or_null ? prep_or_null->col_stride : 0;
     unsigned blocks = (unsigned)((h + 255) / 256);
+    KScope ks(ctx, KC_PERM, 4.0 * (double)h * (chip->width + 5.0 * (k + 1)));
     if (k) {
         perm_denominators_kernel<<<blocks, 256, 0, ctx->stream>>>(dchip, main->d, main->col_stride, pd, pcs, h, perm->d, perm->col_stride);
         VG_LAUNCH_CHECK(ctx);

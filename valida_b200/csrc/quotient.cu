@@ -197,6 +197,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     p.odd_scale = bb::mul(p.half, bb::inv(p.s));
     for (int i = 0; i < 5; i++) p.cumsum.c[i] = bb::to_monty(cumulative_sum[i] % bb::P);
     p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi;
+    KScope* ks = new KScope(ctx, KC_QUOTIENT, 8.0 * (double)h * (main_lde->w + perm_lde->w + (prep_lde ? prep_lde->w : 0)) + 40.0 * (double)h);
     switch (chip->chip_id) {
         case 0: launch<0>(p, h, ctx->stream); break;   case 1: launch<1>(p, h, ctx->stream); break;
         case 2: launch<2>(p, h, ctx->stream); break;   case 3: launch<3>(p, h, ctx->stream); break;
@@ -206,6 +207,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
         case 10: launch<10>(p, h, ctx->stream); break; case 11: launch<11>(p, h, ctx->stream); break;
         case 12: launch<12>(p, h, ctx->stream); break; case 13: launch<13>(p, h, ctx->stream); break;
     }
+    delete ks;
     VG_LAUNCH_CHECK(ctx);
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // apow host vector / device temporaries
     vg_free(ctx, d_apow); vg_free(ctx, dchip);

@@ -47,6 +47,7 @@ int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint
     VG_CUDA(ctx, cudaMemcpyAsync(stage, host, h * w * 4, cudaMemcpyHostToDevice, ctx->stream));
     for (uint64_t c0 = 0; c0 < w; c0 += TW) {
         uint32_t wc = (uint32_t)(w - c0 < TW ? w - c0 : TW);
+        KScope ks(ctx, KC_TRANSPOSE, 8.0 * (double)h * wc);
         rm_to_cm_kernel<<<(unsigned)((h + TR - 1) / TR), 256, 0, ctx->stream>>>(stage, h, w, dst->d, dst->col_stride, repr == VGPU_REPR_CANONICAL, c0, wc);
         VG_LAUNCH_CHECK(ctx);
     }
@@ -61,6 +62,7 @@ int32_t vg_download_rowmajor(vgpu_ctx* ctx, const vgpu_dmat* src, int32_t repr, 
     VG_TRY(vg_alloc(ctx, (void**)&stage, h * w * 4));
     for (uint64_t c0 = 0; c0 < w; c0 += TW) {
         uint32_t wc = (uint32_t)(w - c0 < TW ? w - c0 : TW);
+        KScope ks(ctx, KC_TRANSPOSE, 8.0 * (double)h * wc);
         cm_to_rm_kernel<<<(unsigned)((h + TR - 1) / TR), 256, 0, ctx->stream>>>(src->d, src->col_stride, h, w, stage, repr == VGPU_REPR_CANONICAL, c0, wc);
         VG_LAUNCH_CHECK(ctx);
     }
