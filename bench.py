@@ -40,6 +40,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def aggregate_throughput(dist, rows_local, ms_local, device=None):
+    """Whole-job rows/s over all ranks: sum of rows / max-over-ranks time (each rank proves its own trace)."""
+    import torch
+
+    t = torch.tensor([float(ms_local)], dtype=torch.float64, device=device)
+    r = torch.tensor([float(rows_local)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    return float(r.item()) / (float(t.item()) / 1000.0), float(t.item())
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region."""
 
@@ -199,12 +211,12 @@ def main():
         torch.cuda.synchronize()
 
     proof_len = 0
+    ctx.set_kernel_timing(True)   # on during warm-up too, so the event pool is populated before the timed region
     for _ in range(args.warmup):
         proof_len = len(vb.prove_machine(cfg, traces, device_resident=(dm, dp)))
 
     # ---- timed: device-resident ----
     sampler = ClockSampler(local_rank)
-    ctx.set_kernel_timing(True)
     ctx.kernel_stats()
     launches0 = ctx.launch_count
     barrier()
@@ -221,11 +233,7 @@ def main():
     kstats = ctx.kernel_stats()
     ctx.set_kernel_timing(False)
     phases = vb.last_prove_phases(ctx)
-    tmax = torch.tensor([ms_total], device="cuda")
-    if dist is not None:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total_max = float(tmax.item())
-    value = rows * world * args.steps / (ms_total_max / 1000.0)
+    value, ms_total_max = aggregate_throughput(dist, rows * args.steps, ms_total, device="cuda")
 
     # ---- timed: end to end through the host-buffer C-ABI call ----
     vb.prove_machine(cfg, PinnedTraces)
@@ -237,10 +245,7 @@ def main():
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    tm2 = torch.tensor([ms_e2e], device="cuda")
-    if dist is not None:
-        dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
-    e2e_value = rows * world * args.steps / (float(tm2.item()) / 1000.0)
+    e2e_value, _ = aggregate_throughput(dist, rows * args.steps, ms_e2e, device="cuda")
     assert proof_e2e == proof
 
     if rank != 0:

@@ -4,17 +4,21 @@
 // DFT selected at basic/src/bin/valida.rs:379).
 //
 // Design (B200-first, not the reference's row-major butterfly network):
-//  * a length-n column transform is split n = n1*n2 ("four-step"); each pass stages a tile of
-//    T sub-transforms of length L <= 2^12 in shared memory, runs all log2(L) radix-2 DIF stages
-//    there, and applies the inter-pass twiddle / coset scaling on the way out, so a column crosses
-//    HBM twice per transform regardless of n (<= 2^24 per coset);
-//  * tiles are addressed as element(r, g) = base + r*rs + g*gs, with the thread->element map chosen
-//    so that the unit-stride index is the fastest one in both the load and the store (T-wide
-//    segments in the strided passes, whole rows in the contiguous pass);
-//  * the coset LDE = iNTT (natural->natural, two tile passes with a transposed store) followed by
-//    two forward coset transforms natural->bit-reversed (shift and shift*w_2n) written into the two
-//    halves of the bit-reversed output — the committed row order needs no separate permutation;
-//  * twiddles come from a two-level power table of w_(2^27) (lo[e&4095]*hi[e>>12]) kept L2-resident.
+//  * a length-n column transform is split n = n1*n2 ("four-step"); each pass stages a tile of T
+//    sub-transforms of length L in shared memory and runs ALL log2(L) DIF stages there, four stages
+//    at a time in registers (radix-16 units: 16 loads, 32 butterflies, 16 stores per thread-unit, one
+//    __syncthreads per four stages), so a column crosses HBM twice per transform for n <= 2^24;
+//  * element(r, g) = base + r*rs + g*gs; the thread->element map makes the unit-stride index the
+//    fastest one in both the load and the store.  Strided ("column") passes keep L <= 2^10 so that
+//    T >= 16 adjacent groups give >= 64-byte segments; contiguous ("row") passes take up to 2^14;
+//  * bit reversal is never a separate pass: loads/stores may permute within the tile (free in smem),
+//    and a column pass may store its tile transposed (T contiguous runs of L);
+//  * coset LDE = iNTT natural->bit-reversed coefficients (column pass + row pass, in place) with
+//    shift^k/n folded into the store, then two forward coset transforms bit-reversed coefficients ->
+//    bit-reversed evaluations (row pass + column pass with transposed store) written straight into
+//    the two halves of the committed (bit-reversed) LDE;
+//  * twiddles: a two-level power table of w_(2^27) in global memory (L2-resident) feeds a per-CTA
+//    shared table of w_L^j.
 #include "ctx.h"
 
 namespace {
@@ -25,15 +29,17 @@ struct PassParams {
     const uint32_t* src; uint32_t* dst;
     uint64_t src_cs, dst_cs;          // column strides
     uint64_t src_rs, src_gs;          // element(r, g) = col + r*src_rs + g*src_gs
-    uint64_t dst_rs, dst_gs;          // output k of group g -> col + pos*dst_rs + g*dst_gs
-    uint32_t log_len;                 // L = 2^log_len (sub-transform length, staged in smem)
+    uint64_t dst_rs, dst_gs;          // output slot pos of group g -> col + pos*dst_rs + g*dst_gs
+    uint32_t log_len;                 // L = 2^log_len
     uint32_t tile;                    // T groups per CTA
     uint64_t groups;                  // groups per column (n / L)
     uint32_t inverse;                 // twiddle direction
-    uint32_t dst_natural;             // 1: output k stored at pos = k ; 0: raw DIF order pos = bitrev(k)
-    // pre-multiplier (odd coset): x *= w_NMAX^((r*pre_r + g*pre_g) * pre_unit)
+    uint32_t src_bitrev;              // 1: memory element r holds natural index bitrev(r) (load into slot bitrev(r))
+    uint32_t dst_natural;             // 1: natural output k stored at pos = k ; 0: raw DIF order pos = bitrev(k)
+    uint32_t g_bits;                  // if nonzero, multipliers see gval = bitrev(g, g_bits) instead of g
+    // pre-multiplier: x *= w_NMAX^((rnat*pre_r + gval*pre_g) * pre_unit), rnat = natural index of the element in its group
     uint32_t pre_mode; uint64_t pre_r, pre_g, pre_unit;
-    // post-multiplier: mode 1: w_NMAX^(+-(g*k) * post_unit) ; mode 2: table(g*post_g + k*post_k) ; mode 3: constant scale
+    // post-multiplier on natural output k: mode 1: w_NMAX^(+-(gval*k) * post_unit) ; mode 2: table[gval*post_g + k*post_k] ; mode 3: constant
     uint32_t post_mode; uint64_t post_unit, post_g, post_k; uint32_t post_scale;
     const uint32_t* root_lo; const uint32_t* root_hi;   // w_NMAX tables
     const uint32_t* tab_lo; const uint32_t* tab_hi;     // shift tables (mode 2)
@@ -46,11 +52,52 @@ __device__ __forceinline__ uint32_t root_pow(const PassParams& p, uint64_t e) {
     return mul(lo, hi);
 }
 
+__device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 4); }   // one spare word per 16: conflict-free radix-16 access
+
+// RHO DIF stages (s .. s+RHO-1) of one register unit: the 2^RHO elements base + m*q, q = L >> (s+RHO).
+template <int RHO>
+__device__ __forceinline__ void radix_unit(uint32_t* __restrict__ grp, const uint32_t* __restrict__ tw, uint32_t u, uint32_t log_len, uint32_t s) {
+    constexpr int R = 1 << RHO;
+    const uint32_t lq = log_len - s - RHO;
+    const uint32_t j = u & ((1u << lq) - 1), blk = u >> lq;
+    const uint32_t base = (blk << (lq + RHO)) + j;
+    uint32_t x[R];
+#pragma unroll
+    for (int m = 0; m < R; m++) x[m] = grp[pad(base + ((uint32_t)m << lq))];
+#pragma unroll
+    for (int a = 0; a < RHO; a++) {
+        const int half = R >> (a + 1);
+#pragma unroll
+        for (int m0 = 0; m0 < R; m0++) {
+            if ((m0 & half) == 0) {
+                const int m1 = m0 + half, mm = m0 & (half - 1);
+                const uint32_t A = x[m0], B = x[m1];
+                x[m0] = add(A, B);
+                const uint32_t d = sub(A, B);
+                if (a == RHO - 1 && lq == 0) x[m1] = d;                       // last stage of the transform: twiddle 1
+                else x[m1] = mul(d, tw[(j + ((uint32_t)mm << lq)) << (s + a)]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < R; m++) grp[pad(base + ((uint32_t)m << lq))] = x[m];
+}
+
+template <int RHO>
+__device__ __forceinline__ void radix_step(uint32_t* data, const uint32_t* tw, uint32_t T, uint32_t LS, uint32_t log_len, uint32_t s, uint32_t tid, uint32_t nt) {
+    const uint32_t lu = log_len - RHO;                 // log2(units per group)
+    const uint32_t total_units = T << lu;
+    for (uint32_t w = tid; w < total_units; w += nt) {
+        const uint32_t t = w >> lu, u = w & ((1u << lu) - 1);
+        radix_unit<RHO>(data + t * LS, tw, u, log_len, s);
+    }
+}
+
 // One CTA = one tile of `tile` sub-transforms of one column.  grid.x = tiles_per_col, grid.y = column.
-__global__ void __launch_bounds__(1024) ntt_pass_kernel(PassParams p) {
+__global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint32_t smem[];
     const uint32_t L = 1u << p.log_len, T = p.tile;
-    const uint32_t LS = L + 1;                       // padded row pitch (bank spread for t-fastest access)
+    const uint32_t LS = (L + (L >> 4)) | 1;          // padded, odd group pitch
     uint32_t* tw = smem;                             // L/2 twiddles w_L^(+-j)
     uint32_t* data = smem + (L >= 2 ? L / 2 : 1);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -59,8 +106,7 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(PassParams p) {
     const uint32_t* src = p.src + col * p.src_cs;
     uint32_t* dst = p.dst + col * p.dst_cs;
 
-    // twiddles for the in-smem transform: w_L^j = w_NMAX^(j * NMAX/L); NMAX/L >= 2^15 so only the hi table is touched
-    {
+    {   // w_L^j = w_NMAX^(j * NMAX/L); NMAX/L >= 2^13 so only the hi table is touched
         const uint64_t unit = (1ull << VG_LOG_NMAX) >> p.log_len;
         for (uint32_t j = tid; j < L / 2; j += nt) {
             uint64_t e = (uint64_t)j * unit;
@@ -70,98 +116,87 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(PassParams p) {
     }
     // ---- load ----
     const uint32_t total = L * T;
-    if (p.src_gs == 1) {           // groups are adjacent in memory: t fastest
+    {
+        const bool tfast = (p.src_gs == 1);
         for (uint32_t idx = tid; idx < total; idx += nt) {
-            uint32_t t = idx % T, r = idx / T;
-            uint32_t v = src[(uint64_t)r * p.src_rs + (g0 + t)];
-            if (p.pre_mode) v = mul(v, root_pow(p, ((uint64_t)r * p.pre_r + (g0 + t) * p.pre_g) * p.pre_unit));
-            data[t * LS + r] = v;
-        }
-    } else {                       // each group is contiguous: r fastest
-        for (uint32_t idx = tid; idx < total; idx += nt) {
-            uint32_t r = idx & (L - 1), t = idx >> p.log_len;
+            uint32_t t, r;
+            if (tfast) { t = idx % T; r = idx / T; } else { r = idx & (L - 1); t = idx >> p.log_len; }
             uint32_t v = src[(uint64_t)r * p.src_rs + (g0 + t) * p.src_gs];
-            if (p.pre_mode) v = mul(v, root_pow(p, ((uint64_t)r * p.pre_r + (g0 + t) * p.pre_g) * p.pre_unit));
-            data[t * LS + r] = v;
+            const uint32_t rnat = p.src_bitrev ? bb::reverse_bits(r, (int)p.log_len) : r;
+            if (p.pre_mode) {
+                const uint64_t g = g0 + t;
+                const uint64_t gval = p.g_bits ? bb::reverse_bits((uint32_t)g, (int)p.g_bits) : g;
+                v = mul(v, root_pow(p, ((uint64_t)rnat * p.pre_r + gval * p.pre_g) * p.pre_unit));
+            }
+            data[t * LS + pad(rnat)] = v;
         }
     }
     __syncthreads();
-    // ---- log2(L) DIF stages, natural in -> bit-reversed positions out ----
-    const uint32_t nbf = total >> 1;   // butterflies per stage
-    for (uint32_t s = 0; s < p.log_len; s++) {
-        const uint32_t lh = p.log_len - 1 - s;      // log2(half)
-        const uint32_t half = 1u << lh;
-        for (uint32_t b = tid; b < nbf; b += nt) {
-            uint32_t t = b >> (p.log_len - 1), bi = b & ((L >> 1) - 1);
-            uint32_t j = bi & (half - 1), blk = bi >> lh;
-            uint32_t i0 = t * LS + (blk << (lh + 1)) + j, i1 = i0 + half;
-            uint32_t a = data[i0], c = data[i1];
-            data[i0] = add(a, c);
-            uint32_t d = sub(a, c);
-            data[i1] = lh == 0 ? d : mul(d, tw[j << s]);   // j == 0 in the last stage: twiddle 1
-        }
-        __syncthreads();
+    // ---- all DIF stages, 4 at a time in registers ----
+    {
+        uint32_t s = 0;
+        while (p.log_len - s >= 4) { radix_step<4>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); s += 4; }
+        const uint32_t rem = p.log_len - s;
+        if (rem == 3) { radix_step<3>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); }
+        else if (rem == 2) { radix_step<2>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); }
+        else if (rem == 1) { radix_step<1>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); }
     }
     // ---- store (with optional post multiplier) ----
-    auto post = [&](uint32_t v, uint32_t k, uint64_t g) -> uint32_t {
-        if (p.post_mode == 1) {
-            uint64_t e = (g * k) * p.post_unit;
-            if (p.inverse && e) e = (1ull << VG_LOG_NMAX) - (e & ((1ull << VG_LOG_NMAX) - 1));
-            return mul(v, root_pow(p, e));
-        } else if (p.post_mode == 2) {
-            uint64_t e = g * p.post_g + (uint64_t)k * p.post_k;
-            return mul(v, mul(__ldg(p.tab_lo + (e & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e >> VG_POW_LO_BITS))));
-        } else if (p.post_mode == 3) {
-            return mul(v, p.post_scale);
-        }
-        return v;
-    };
-    if (p.dst_gs == 1) {           // t fastest
+    {
+        const bool tfast = (p.dst_gs == 1);
         for (uint32_t idx = tid; idx < total; idx += nt) {
-            uint32_t t = idx % T, pos = idx / T;
-            uint32_t q = p.dst_natural ? bb::reverse_bits(pos, p.log_len) : pos;   // smem slot holding the value for `pos`
-            uint32_t k = p.dst_natural ? pos : bb::reverse_bits(pos, p.log_len);   // its natural output index
-            dst[(uint64_t)pos * p.dst_rs + (g0 + t)] = post(data[t * LS + q], k, g0 + t);
-        }
-    } else {                       // pos fastest
-        for (uint32_t idx = tid; idx < total; idx += nt) {
-            uint32_t pos = idx & (L - 1), t = idx >> p.log_len;
-            uint32_t q = p.dst_natural ? bb::reverse_bits(pos, p.log_len) : pos;
-            uint32_t k = p.dst_natural ? pos : bb::reverse_bits(pos, p.log_len);
-            dst[(uint64_t)pos * p.dst_rs + (g0 + t) * p.dst_gs] = post(data[t * LS + q], k, g0 + t);
+            uint32_t t, pos;
+            if (tfast) { t = idx % T; pos = idx / T; } else { pos = idx & (L - 1); t = idx >> p.log_len; }
+            const uint32_t brp = bb::reverse_bits(pos, (int)p.log_len);
+            const uint32_t q = p.dst_natural ? brp : pos;      // smem slot holding the value stored at `pos`
+            const uint32_t k = p.dst_natural ? pos : brp;      // its natural output index
+            uint32_t v = data[t * LS + pad(q)];
+            if (p.post_mode) {
+                const uint64_t g = g0 + t;
+                const uint64_t gval = p.g_bits ? bb::reverse_bits((uint32_t)g, (int)p.g_bits) : g;
+                if (p.post_mode == 1) {
+                    uint64_t e = ((gval * k) * p.post_unit) & ((1ull << VG_LOG_NMAX) - 1);
+                    if (p.inverse && e) e = (1ull << VG_LOG_NMAX) - e;
+                    v = mul(v, root_pow(p, e));
+                } else if (p.post_mode == 2) {
+                    const uint64_t e = gval * p.post_g + (uint64_t)k * p.post_k;
+                    v = mul(v, mul(__ldg(p.tab_lo + (e & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e >> VG_POW_LO_BITS))));
+                } else {
+                    v = mul(v, p.post_scale);
+                }
+            }
+            dst[(uint64_t)pos * p.dst_rs + (g0 + t) * p.dst_gs] = v;
         }
     }
 }
 
-constexpr int LOG_LMAX = 12;   // largest sub-transform staged in shared memory
+constexpr int LOG_ROW_MAX = 14;   // longest contiguous sub-transform staged in shared memory (64 KB)
+constexpr int LOG_COL_MAX = 12;   // longest strided sub-transform (balanced nat->nat split)
+constexpr int LOG_TILE_ELEMS = 14;
 
-struct Split { int l1, l2; };
-Split choose_split(int log_n) {
-    if (log_n <= LOG_LMAX) return {log_n, 0};
-    int l1 = (log_n + 1) / 2;
-    return {l1, log_n - l1};
-}
 uint32_t choose_tile(int log_len, uint64_t groups) {
-    // L*T <= 2^14 elements (64 KB) so that 2-3 CTAs co-reside per SM; T <= 32 (128 B segments)
-    uint32_t t = 1u << (14 - log_len > 5 ? 5 : (14 - log_len < 0 ? 0 : 14 - log_len));
+    int lt = LOG_TILE_ELEMS - log_len;
+    if (lt < 0) lt = 0;
+    if (lt > 6) lt = 6;
+    uint32_t t = 1u << lt;
     while (t > groups) t >>= 1;
     return t ? t : 1;
 }
 
 int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
     p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi;
-    uint32_t L = 1u << p.log_len;
+    const uint32_t L = 1u << p.log_len;
     p.tile = choose_tile((int)p.log_len, p.groups);
-    uint64_t tiles = p.groups / p.tile;
-    size_t smem = ((L >= 2 ? L / 2 : 1) + (size_t)p.tile * (L + 1)) * sizeof(uint32_t);
-    uint32_t total = L * p.tile;
-    uint32_t threads = total / 2 >= 1024 ? 1024 : (total / 2 >= 32 ? total / 2 : 32);
-    if (threads > 512 && smem <= 70 * 1024) threads = 512;
+    const uint64_t tiles = p.groups / p.tile;
+    const uint32_t LS = (L + (L >> 4)) | 1;
+    const size_t smem = ((L >= 2 ? L / 2 : 1) + (size_t)p.tile * LS) * sizeof(uint32_t);
+    const uint32_t total = L * p.tile;
+    uint32_t threads = total / 16 >= 512 ? 512 : (total / 16 >= 32 ? total / 16 : 32);
+    if (total >= (1u << 14) && threads > 256) threads = 256 * 2;
     static bool attr_set = false;
     if (!attr_set) { VG_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
-    // grid.y limit 65535: chunk columns
-    for (uint64_t c0 = 0; c0 < w; c0 += 65535) {
-        uint64_t wc = w - c0 < 65535 ? w - c0 : 65535;
+    for (uint64_t c0 = 0; c0 < w; c0 += 65535) {     // grid.y limit
+        const uint64_t wc = w - c0 < 65535 ? w - c0 : 65535;
         PassParams q = p;
         q.src = p.src + c0 * p.src_cs; q.dst = p.dst + c0 * p.dst_cs;
         dim3 grid((unsigned)tiles, (unsigned)wc);
@@ -179,18 +214,24 @@ __global__ void zero_pad_kernel(const uint32_t* src, uint64_t src_cs, uint32_t* 
     dst[c * dst_cs + r] = r < h ? src[c * src_cs + r] : 0;
 }
 
+// split for the passes that have one strided and one contiguous sub-transform
+void split_col_row(int log_n, int* l_col, int* l_row) {
+    if (log_n <= LOG_ROW_MAX) { *l_col = 0; *l_row = log_n; return; }
+    int lc = log_n - LOG_ROW_MAX;
+    if (lc < 4) lc = 4;
+    *l_col = lc; *l_row = log_n - lc;
+}
+
 }  // namespace
 
 // natural -> natural transform of every column (forward: out[k] = sum_j in[j] w^(jk); inverse scales by 1/n).
-// coset != null (inverse only): coefficient k additionally multiplied by shift^k (table carries the 1/n).
 int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, int log_n, uint64_t w,
                        bool inverse, const PowTable* coset, uint32_t* tmp, uint64_t tmp_cs) {
     const uint64_t n = 1ull << log_n;
-    Split sp = choose_split(log_n);
     uint32_t ninv = inverse ? bb::inv(bb::to_monty((uint32_t)(n % bb::P))) : bb::R1;
     PassParams p{};
     p.inverse = inverse;
-    if (sp.l2 == 0) {
+    if (log_n <= LOG_ROW_MAX) {
         p.src = src; p.src_cs = src_cs; p.dst = dst; p.dst_cs = dst_cs;
         p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
         p.log_len = log_n; p.groups = 1; p.dst_natural = 1;
@@ -198,11 +239,13 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
         else if (inverse) { p.post_mode = 3; p.post_scale = ninv; }
         return launch_pass(ctx, p, w);
     }
-    const uint64_t n1 = 1ull << sp.l1, n2 = 1ull << sp.l2;
+    if (log_n > 2 * LOG_COL_MAX) VG_FAIL(ctx, "ntt: natural->natural transforms above 2^%d are not built", 2 * LOG_COL_MAX);
+    const int l1 = (log_n + 1) / 2, l2 = log_n - l1;
+    const uint64_t n1 = 1ull << l1, n2 = 1ull << l2;
     // pass 1: over i1 (stride n2) for each i2; times w_n^(+-i2*k1); transposed store tmp[i2][k1]
     p.src = src; p.src_cs = src_cs; p.dst = tmp; p.dst_cs = tmp_cs;
     p.src_rs = n2; p.src_gs = 1; p.dst_rs = 1; p.dst_gs = n1;
-    p.log_len = sp.l1; p.groups = n2; p.dst_natural = 1;
+    p.log_len = l1; p.groups = n2; p.dst_natural = 1;
     p.post_mode = 1; p.post_unit = (1ull << VG_LOG_NMAX) >> log_n;
     VG_TRY(launch_pass(ctx, p, w));
     // pass 2: tmp is [i2][k1]; over i2 (stride n1) for each k1; X[k1 + n1*k2] stored at that index
@@ -210,38 +253,78 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
     q.inverse = inverse;
     q.src = tmp; q.src_cs = tmp_cs; q.dst = dst; q.dst_cs = dst_cs;
     q.src_rs = n1; q.src_gs = 1; q.dst_rs = n1; q.dst_gs = 1;
-    q.log_len = sp.l2; q.groups = n1; q.dst_natural = 1;
+    q.log_len = l2; q.groups = n1; q.dst_natural = 1;
     if (coset) { q.post_mode = 2; q.post_g = 1; q.post_k = n1; q.tab_lo = coset->lo; q.tab_hi = coset->hi; }
     else if (inverse) { q.post_mode = 3; q.post_scale = ninv; }
     return launch_pass(ctx, q, w);
 }
 
-// forward coset transform, natural coefficients -> bit-reversed evaluations; odd != 0 multiplies
-// coefficient i by w_2n^i first (the second coset of the blow-up-2 LDE).
-static int32_t ntt_nat2bitrev(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, int log_n, uint64_t w, bool odd) {
+// iNTT natural evaluations -> coefficients in BIT-REVERSED order, coefficient K scaled by table[K]
+// (= shift^K / n).  buf (column stride bcs) receives c[K] at position bitrev_n(K).
+static int32_t intt_nat2bitrev_scaled(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* buf, uint64_t bcs, int log_n, uint64_t w, const PowTable* tab) {
     const uint64_t n = 1ull << log_n;
-    Split sp = choose_split(log_n);
+    int lc, lr;
+    split_col_row(log_n, &lc, &lr);
     PassParams p{};
-    p.inverse = 0;
-    if (odd) { p.pre_mode = 1; p.pre_unit = (1ull << VG_LOG_NMAX) >> (log_n + 1); }
-    if (sp.l2 == 0) {
-        p.src = src; p.src_cs = src_cs; p.dst = dst; p.dst_cs = dst_cs;
+    p.inverse = 1;
+    if (lc == 0) {
+        p.src = src; p.src_cs = src_cs; p.dst = buf; p.dst_cs = bcs;
         p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
         p.log_len = log_n; p.groups = 1; p.dst_natural = 0;
-        p.pre_r = 1; p.pre_g = 0;
+        p.post_mode = 2; p.post_g = 0; p.post_k = 1; p.tab_lo = tab->lo; p.tab_hi = tab->hi;
         return launch_pass(ctx, p, w);
     }
-    const uint64_t n1 = 1ull << sp.l1, n2 = 1ull << sp.l2;
-    p.src = src; p.src_cs = src_cs; p.dst = dst; p.dst_cs = dst_cs;
+    const uint64_t n1 = 1ull << lc, n2 = 1ull << lr;
+    // column pass over i1 (stride n2): A[k1][i2] * w_n^(-i2*k1) stored raw at row bitrev(k1)
+    p.src = src; p.src_cs = src_cs; p.dst = buf; p.dst_cs = bcs;
     p.src_rs = n2; p.src_gs = 1; p.dst_rs = n2; p.dst_gs = 1;
-    p.log_len = sp.l1; p.groups = n2; p.dst_natural = 0;
-    p.pre_r = n2; p.pre_g = 1;
+    p.log_len = lc; p.groups = n2; p.dst_natural = 0;
     p.post_mode = 1; p.post_unit = (1ull << VG_LOG_NMAX) >> log_n;
     VG_TRY(launch_pass(ctx, p, w));
+    // row pass on row q1 = bitrev(k1): over i2 -> k2 stored raw; K = k1 + n1*k2 = bitrev(q1) + n1*k
     PassParams q{};
-    q.src = dst; q.src_cs = dst_cs; q.dst = dst; q.dst_cs = dst_cs;
+    q.inverse = 1;
+    q.src = buf; q.src_cs = bcs; q.dst = buf; q.dst_cs = bcs;
     q.src_rs = 1; q.src_gs = n2; q.dst_rs = 1; q.dst_gs = n2;
-    q.log_len = sp.l2; q.groups = n1; q.dst_natural = 0;
+    q.log_len = lr; q.groups = n1; q.dst_natural = 0;
+    q.g_bits = lc;
+    q.post_mode = 2; q.post_g = 1; q.post_k = n1; q.tab_lo = tab->lo; q.tab_hi = tab->hi;
+    return launch_pass(ctx, q, w);
+}
+
+// forward coset transform: coefficients in bit-reversed order (c[K] at bitrev_n(K)) -> evaluations in
+// bit-reversed order (E[m] at bitrev_n(m)), out of place.  odd != 0 multiplies c[K] by w_2n^K first.
+static int32_t ntt_bitrev2bitrev(vgpu_ctx* ctx, const uint32_t* coef, uint64_t ccs, uint32_t* dst, uint64_t dst_cs, uint32_t* tmp, uint64_t tcs,
+                                 int log_n, uint64_t w, bool odd) {
+    const uint64_t n = 1ull << log_n;
+    int lc, lr;
+    split_col_row(log_n, &lc, &lr);
+    PassParams p{};
+    p.inverse = 0;
+    if (lc == 0) {
+        p.src = coef; p.src_cs = ccs; p.dst = dst; p.dst_cs = dst_cs;
+        p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
+        p.log_len = log_n; p.groups = 1; p.src_bitrev = 1; p.dst_natural = 0;
+        if (odd) { p.pre_mode = 1; p.pre_r = 1; p.pre_g = 0; p.pre_unit = (1ull << VG_LOG_NMAX) >> (log_n + 1); }
+        return launch_pass(ctx, p, w);
+    }
+    const uint64_t n1 = 1ull << lc, n2 = 1ull << lr;
+    // position (j1, j2) holds K = bitrev(j1) + n1*bitrev(j2) =: k1' + n1*k2'
+    // row pass on row j1: transform over k2' (slot = bitrev(j2)) -> m2 ; times w_n^(k1'*m2) ; stored raw (position q <-> m2 = bitrev(q))
+    p.src = coef; p.src_cs = ccs; p.dst = tmp; p.dst_cs = tcs;
+    p.src_rs = 1; p.src_gs = n2; p.dst_rs = 1; p.dst_gs = n2;
+    p.log_len = lr; p.groups = n1; p.src_bitrev = 1; p.dst_natural = 0;
+    p.g_bits = lc;
+    if (odd) { p.pre_mode = 1; p.pre_r = n1; p.pre_g = 1; p.pre_unit = (1ull << VG_LOG_NMAX) >> (log_n + 1); }
+    p.post_mode = 1; p.post_unit = (1ull << VG_LOG_NMAX) >> log_n;
+    VG_TRY(launch_pass(ctx, p, w));
+    // column pass over rows j1 (k1' = bitrev(j1)) for each column q: -> m1 ; E[m1*n2 + m2] goes to
+    // bitrev_n = bitrev(m2)*n1 + bitrev(m1) = q*n1 + raw slot: transposed store, raw order
+    PassParams q{};
+    q.inverse = 0;
+    q.src = tmp; q.src_cs = tcs; q.dst = dst; q.dst_cs = dst_cs;
+    q.src_rs = n2; q.src_gs = 1; q.dst_rs = 1; q.dst_gs = n1;
+    q.log_len = lc; q.groups = n2; q.src_bitrev = 1; q.dst_natural = 0;
     return launch_pass(ctx, q, w);
 }
 
@@ -252,11 +335,11 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
     while ((1ull << log_n) < h) log_n++;
     if ((1ull << log_n) != h) VG_FAIL(ctx, "coset_lde: height %llu is not a power of two", (unsigned long long)h);
     if (log_n + 1 > VG_LOG_NMAX) VG_FAIL(ctx, "coset_lde: LDE height 2^%d exceeds BabyBear two-adicity", log_n + 1);
+    if (log_n > LOG_ROW_MAX + 10) VG_FAIL(ctx, "coset_lde: heights above 2^%d are not built", LOG_ROW_MAX + 10);
     const PowTable* tab = nullptr;
     uint32_t ninv_canon = bb::from_monty(bb::inv(bb::to_monty((uint32_t)(h % bb::P))));
     VG_TRY(vg_get_shift_table(ctx, shift_canonical, ninv_canon, h, &tab));
-    // column batches: bound scratch (coefficients + transposed intermediate) to ~512 MB and keep
-    // mid-size batches L2-resident between passes
+    // column batches: bound the scratch and keep mid-size batches L2-resident between passes
     uint64_t batch = (uint64_t)(24u << 20) / (4 * h);
     if (batch < 1) batch = 1;
     if (batch > w) batch = w;
@@ -266,22 +349,24 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
     int32_t rc = 0;
     for (uint64_t c0 = 0; c0 < w && rc == 0; c0 += batch) {
         uint64_t wc = w - c0 < batch ? w - c0 : batch;
-        rc = vg_ntt_nat2nat(ctx, src + c0 * src_cs, src_cs, coef, h, log_n, wc, true, tab, tmp, h);
-        if (rc) break;
         if (bit_reversed) {
-            rc = ntt_nat2bitrev(ctx, coef, h, dst + c0 * dst_cs, dst_cs, log_n, wc, false);
+            rc = intt_nat2bitrev_scaled(ctx, src + c0 * src_cs, src_cs, coef, h, log_n, wc, tab);
             if (rc) break;
-            rc = ntt_nat2bitrev(ctx, coef, h, dst + c0 * dst_cs + h, dst_cs, log_n, wc, true);
+            rc = ntt_bitrev2bitrev(ctx, coef, h, dst + c0 * dst_cs, dst_cs, tmp, h, log_n, wc, false);
+            if (rc) break;
+            rc = ntt_bitrev2bitrev(ctx, coef, h, dst + c0 * dst_cs + h, dst_cs, tmp, h, log_n, wc, true);
         } else {
             // natural-order output (API completeness, not on the proving path): zero-pad and transform at size 2h
-            uint32_t* pad = nullptr; uint32_t* tmp2 = nullptr;
-            rc = vg_alloc(ctx, (void**)&pad, wc * 2 * h * 4); if (rc) break;
-            rc = vg_alloc(ctx, (void**)&tmp2, wc * 2 * h * 4); if (rc) { vg_free(ctx, pad); break; }
+            rc = vg_ntt_nat2nat(ctx, src + c0 * src_cs, src_cs, coef, h, log_n, wc, true, tab, tmp, h);
+            if (rc) break;
+            uint32_t* padb = nullptr; uint32_t* tmp2 = nullptr;
+            rc = vg_alloc(ctx, (void**)&padb, wc * 2 * h * 4); if (rc) break;
+            rc = vg_alloc(ctx, (void**)&tmp2, wc * 2 * h * 4); if (rc) { vg_free(ctx, padb); break; }
             uint64_t tot = 2 * h * wc;
-            zero_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(coef, h, pad, 2 * h, h, 2 * h, wc);
+            zero_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(coef, h, padb, 2 * h, h, 2 * h, wc);
             ctx->launches++;
-            rc = vg_ntt_nat2nat(ctx, pad, 2 * h, dst + c0 * dst_cs, dst_cs, log_n + 1, wc, false, nullptr, tmp2, 2 * h);
-            vg_free(ctx, pad); vg_free(ctx, tmp2);
+            rc = vg_ntt_nat2nat(ctx, padb, 2 * h, dst + c0 * dst_cs, dst_cs, log_n + 1, wc, false, nullptr, tmp2, 2 * h);
+            vg_free(ctx, padb); vg_free(ctx, tmp2);
         }
     }
     vg_free(ctx, coef); vg_free(ctx, tmp);
