@@ -6,11 +6,39 @@
 
 // ---- memory ------------------------------------------------------------------------------------
 int32_t vg_alloc(vgpu_ctx* ctx, void** p, size_t bytes) {
-    if (bytes == 0) bytes = 4;
-    VG_CUDA(ctx, cudaMallocAsync(p, bytes, ctx->stream));
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (bytes == 0) bytes = 512;
+    auto it = ctx->free_bufs.find(bytes);
+    if (it != ctx->free_bufs.end()) {
+        *p = it->second;
+        ctx->free_bufs.erase(it);
+        ctx->cached_bytes -= bytes;
+    } else {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess && !ctx->free_bufs.empty()) {   // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            cudaStreamSynchronize(ctx->stream);
+            for (auto& kv : ctx->free_bufs) cudaFree(kv.second);
+            ctx->free_bufs.clear(); ctx->cached_bytes = 0;
+            e = cudaMalloc(p, bytes);
+        }
+        if (e != cudaSuccess) VG_FAIL(ctx, "cudaMalloc(%zu bytes) failed: %s (live %zu MB)", bytes, cudaGetErrorString(e), ctx->live_bytes >> 20);
+    }
+    ctx->live_bufs[*p] = bytes;
+    ctx->live_bytes += bytes;
+    if (ctx->live_bytes > ctx->peak_bytes) ctx->peak_bytes = ctx->live_bytes;
     return 0;
 }
-void vg_free(vgpu_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+void vg_free(vgpu_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->live_bufs.find(p);
+    if (it == ctx->live_bufs.end()) return;
+    size_t bytes = it->second;
+    ctx->live_bufs.erase(it);
+    ctx->live_bytes -= bytes;
+    ctx->free_bufs.emplace(bytes, p);
+    ctx->cached_bytes += bytes;
+}
 
 int32_t vg_dmat_alloc(vgpu_ctx* ctx, uint64_t h, uint64_t w, vgpu_dmat** out) {
     vgpu_dmat* m = new (std::nothrow) vgpu_dmat();
@@ -72,10 +100,6 @@ int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
     cudaDeviceProp prop;
     VG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    cudaMemPool_t pool;
-    VG_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    VG_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     VG_TRY(build_pow_table(ctx, bb::two_adic_generator_monty(VG_LOG_NMAX), bb::R1, (1ull << VG_LOG_NMAX) - 1, &ctx->root_table));
     return 0;
 }
@@ -88,6 +112,9 @@ void vgpu_ctx_destroy(vgpu_ctx* ctx) {
         vg_free(ctx, ctx->root_table.lo); vg_free(ctx, ctx->root_table.hi);
         for (auto& kv : ctx->shift_tables) { vg_free(ctx, kv.second.lo); vg_free(ctx, kv.second.hi); }
         cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->free_bufs) cudaFree(kv.second);
+        for (auto& kv : ctx->live_bufs) cudaFree(kv.first);
+        for (auto e : ctx->event_pool) cudaEventDestroy(e);
         if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;

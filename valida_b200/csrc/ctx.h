@@ -41,6 +41,11 @@ struct vgpu_ctx {
     void* challenger = nullptr;                                  // vgh::Challenger* (host/challenger.h)
     void* poseidon = nullptr;                                    // vgh::Poseidon16*
     std::vector<std::pair<const char*, float>> phases;          // last prove: per-phase milliseconds
+    // size-keyed cache of device buffers: a proof repeats the same allocation sizes every step, so after the
+    // first step no driver allocator call is made (single stream => reuse in enqueue order is safe)
+    std::multimap<size_t, void*> free_bufs;
+    std::map<void*, size_t> live_bufs;
+    size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
     bool ktiming = false;
     std::vector<KTimer> ktimers;
     std::vector<cudaEvent_t> event_pool;

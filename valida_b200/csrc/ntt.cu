@@ -52,21 +52,26 @@ __device__ __forceinline__ uint32_t root_pow(const PassParams& p, uint64_t e) {
     return mul(lo, hi);
 }
 
-__device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 4); }   // one spare word per 16: conflict-free radix-16 access
+// one spare word per 16 (conflict-free stride-16 access of the last radix-16 step) plus one per 512
+// (spreads bit-reversed accesses, whose lanes differ only in the top five index bits, over all banks)
+__device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 4) + (i >> 9); }
 
-// RHO DIF stages (s .. s+RHO-1) of one register unit: the 2^RHO elements base + m*q, q = L >> (s+RHO).
-template <int RHO>
-__device__ __forceinline__ void radix_unit(uint32_t* __restrict__ grp, const uint32_t* __restrict__ tw, uint32_t u, uint32_t log_len, uint32_t s) {
+// RHO DIF stages (S .. S+RHO-1) of one register unit: the 2^RHO elements base + m*q, q = L >> (S+RHO).
+// LOG_LEN and S are compile-time so that every shift, pad() term and twiddle offset folds to an immediate.
+template <int RHO, int LOG_LEN, int S>
+__device__ __forceinline__ void radix_unit(uint32_t* __restrict__ grp, const uint32_t* __restrict__ tw, uint32_t u) {
     constexpr int R = 1 << RHO;
-    const uint32_t lq = log_len - s - RHO;
-    const uint32_t j = u & ((1u << lq) - 1), blk = u >> lq;
-    const uint32_t base = (blk << (lq + RHO)) + j;
+    constexpr int LQ = LOG_LEN - S - RHO;
+    const uint32_t j = u & ((1u << LQ) - 1), blk = u >> LQ;
+    const uint32_t base = (blk << (LQ + RHO)) + j;
     uint32_t x[R];
 #pragma unroll
-    for (int m = 0; m < R; m++) x[m] = grp[pad(base + ((uint32_t)m << lq))];
+    for (int m = 0; m < R; m++) x[m] = grp[pad(base + ((uint32_t)m << LQ))];
 #pragma unroll
     for (int a = 0; a < RHO; a++) {
+        constexpr int dummy = 0; (void)dummy;
         const int half = R >> (a + 1);
+        const uint32_t tj = j << (S + a);
 #pragma unroll
         for (int m0 = 0; m0 < R; m0++) {
             if ((m0 & half) == 0) {
@@ -74,30 +79,49 @@ __device__ __forceinline__ void radix_unit(uint32_t* __restrict__ grp, const uin
                 const uint32_t A = x[m0], B = x[m1];
                 x[m0] = add(A, B);
                 const uint32_t d = sub(A, B);
-                if (a == RHO - 1 && lq == 0) x[m1] = d;                       // last stage of the transform: twiddle 1
-                else x[m1] = mul(d, tw[(j + ((uint32_t)mm << lq)) << (s + a)]);
+                if (a == RHO - 1 && LQ == 0) x[m1] = d;                       // last stage of the transform: twiddle 1
+                else x[m1] = mul(d, tw[tj + ((uint32_t)mm << (LQ + S + a))]);
             }
         }
     }
 #pragma unroll
-    for (int m = 0; m < R; m++) grp[pad(base + ((uint32_t)m << lq))] = x[m];
+    for (int m = 0; m < R; m++) grp[pad(base + ((uint32_t)m << LQ))] = x[m];
 }
 
-template <int RHO>
-__device__ __forceinline__ void radix_step(uint32_t* data, const uint32_t* tw, uint32_t T, uint32_t LS, uint32_t log_len, uint32_t s, uint32_t tid, uint32_t nt) {
-    const uint32_t lu = log_len - RHO;                 // log2(units per group)
-    const uint32_t total_units = T << lu;
+template <int RHO, int LOG_LEN, int S>
+__device__ __forceinline__ void radix_step(uint32_t* data, const uint32_t* tw, uint32_t T, uint32_t LS, uint32_t tid, uint32_t nt) {
+    constexpr int LU = LOG_LEN - RHO;                  // log2(units per group)
+    const uint32_t total_units = T << LU;
     for (uint32_t w = tid; w < total_units; w += nt) {
-        const uint32_t t = w >> lu, u = w & ((1u << lu) - 1);
-        radix_unit<RHO>(data + t * LS, tw, u, log_len, s);
+        const uint32_t t = w >> LU, u = w & ((1u << LU) - 1);
+        radix_unit<RHO, LOG_LEN, S>(data + t * LS, tw, u);
+    }
+    __syncthreads();
+}
+
+// all stages of a length-2^LOG_LEN DIF, four at a time
+template <int LOG_LEN, int S>
+__device__ __forceinline__ void all_stages(uint32_t* data, const uint32_t* tw, uint32_t T, uint32_t LS, uint32_t tid, uint32_t nt) {
+    if constexpr (LOG_LEN - S >= 4) {
+        // prefer (4, 3, 3) over (4, 4, 2) style endings only when it saves a step: greedy 4s otherwise
+        radix_step<4, LOG_LEN, S>(data, tw, T, LS, tid, nt);
+        all_stages<LOG_LEN, S + 4>(data, tw, T, LS, tid, nt);
+    } else if constexpr (LOG_LEN - S == 3) {
+        radix_step<3, LOG_LEN, S>(data, tw, T, LS, tid, nt);
+    } else if constexpr (LOG_LEN - S == 2) {
+        radix_step<2, LOG_LEN, S>(data, tw, T, LS, tid, nt);
+    } else if constexpr (LOG_LEN - S == 1) {
+        radix_step<1, LOG_LEN, S>(data, tw, T, LS, tid, nt);
     }
 }
 
 // One CTA = one tile of `tile` sub-transforms of one column.  grid.x = tiles_per_col, grid.y = column.
+template <int LOG_LEN>
 __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint32_t smem[];
-    const uint32_t L = 1u << p.log_len, T = p.tile;
-    const uint32_t LS = (L + (L >> 4)) | 1;          // padded, odd group pitch
+    constexpr uint32_t L = 1u << LOG_LEN;
+    const uint32_t T = p.tile;
+    const uint32_t LS = (L + (L >> 4) + (L >> 9)) | 1;   // padded, odd group pitch
     uint32_t* tw = smem;                             // L/2 twiddles w_L^(+-j)
     uint32_t* data = smem + (L >= 2 ? L / 2 : 1);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -107,47 +131,54 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     uint32_t* dst = p.dst + col * p.dst_cs;
 
     {   // w_L^j = w_NMAX^(j * NMAX/L); NMAX/L >= 2^13 so only the hi table is touched
-        const uint64_t unit = (1ull << VG_LOG_NMAX) >> p.log_len;
+        const uint64_t unit = (1ull << VG_LOG_NMAX) >> LOG_LEN;
         for (uint32_t j = tid; j < L / 2; j += nt) {
             uint64_t e = (uint64_t)j * unit;
             if (p.inverse && e) e = (1ull << VG_LOG_NMAX) - e;
             tw[j] = __ldg(p.root_hi + (e >> VG_POW_LO_BITS));
         }
     }
-    // ---- load ----
+    // ---- load (4 independent global loads in flight per thread) ----
     const uint32_t total = L * T;
+    const uint32_t log_t = 31 - __clz(T);
     {
         const bool tfast = (p.src_gs == 1);
-        for (uint32_t idx = tid; idx < total; idx += nt) {
-            uint32_t t, r;
-            if (tfast) { t = idx % T; r = idx / T; } else { r = idx & (L - 1); t = idx >> p.log_len; }
-            uint32_t v = src[(uint64_t)r * p.src_rs + (g0 + t) * p.src_gs];
-            const uint32_t rnat = p.src_bitrev ? bb::reverse_bits(r, (int)p.log_len) : r;
-            if (p.pre_mode) {
-                const uint64_t g = g0 + t;
-                const uint64_t gval = p.g_bits ? bb::reverse_bits((uint32_t)g, (int)p.g_bits) : g;
-                v = mul(v, root_pow(p, ((uint64_t)rnat * p.pre_r + gval * p.pre_g) * p.pre_unit));
+        for (uint32_t idx0 = tid; idx0 < total; idx0 += 4 * nt) {
+            uint32_t v[4], tt[4], rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t idx = idx0 + u * nt;
+                if (idx < total) {
+                    if (tfast) { tt[u] = idx & (T - 1); rr[u] = idx >> log_t; } else { rr[u] = idx & (L - 1); tt[u] = idx >> LOG_LEN; }
+                    v[u] = src[(uint64_t)rr[u] * p.src_rs + (g0 + tt[u]) * p.src_gs];
+                }
             }
-            data[t * LS + pad(rnat)] = v;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t idx = idx0 + u * nt;
+                if (idx < total) {
+                    const uint32_t rnat = p.src_bitrev ? bb::reverse_bits(rr[u], (int)LOG_LEN) : rr[u];
+                    uint32_t x = v[u];
+                    if (p.pre_mode) {
+                        const uint64_t g = g0 + tt[u];
+                        const uint64_t gval = p.g_bits ? bb::reverse_bits((uint32_t)g, (int)p.g_bits) : g;
+                        x = mul(x, root_pow(p, ((uint64_t)rnat * p.pre_r + gval * p.pre_g) * p.pre_unit));
+                    }
+                    data[tt[u] * LS + pad(rnat)] = x;
+                }
+            }
         }
     }
     __syncthreads();
     // ---- all DIF stages, 4 at a time in registers ----
-    {
-        uint32_t s = 0;
-        while (p.log_len - s >= 4) { radix_step<4>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); s += 4; }
-        const uint32_t rem = p.log_len - s;
-        if (rem == 3) { radix_step<3>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); }
-        else if (rem == 2) { radix_step<2>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); }
-        else if (rem == 1) { radix_step<1>(data, tw, T, LS, p.log_len, s, tid, nt); __syncthreads(); }
-    }
+    all_stages<LOG_LEN, 0>(data, tw, T, LS, tid, nt);
     // ---- store (with optional post multiplier) ----
     {
         const bool tfast = (p.dst_gs == 1);
         for (uint32_t idx = tid; idx < total; idx += nt) {
             uint32_t t, pos;
-            if (tfast) { t = idx % T; pos = idx / T; } else { pos = idx & (L - 1); t = idx >> p.log_len; }
-            const uint32_t brp = bb::reverse_bits(pos, (int)p.log_len);
+            if (tfast) { t = idx & (T - 1); pos = idx >> log_t; } else { pos = idx & (L - 1); t = idx >> LOG_LEN; }
+            const uint32_t brp = bb::reverse_bits(pos, (int)LOG_LEN);
             const uint32_t q = p.dst_natural ? brp : pos;      // smem slot holding the value stored at `pos`
             const uint32_t k = p.dst_natural ? pos : brp;      // its natural output index
             uint32_t v = data[t * LS + pad(q)];
@@ -188,20 +219,25 @@ int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
     const uint32_t L = 1u << p.log_len;
     p.tile = choose_tile((int)p.log_len, p.groups);
     const uint64_t tiles = p.groups / p.tile;
-    const uint32_t LS = (L + (L >> 4)) | 1;
+    const uint32_t LS = (L + (L >> 4) + (L >> 9)) | 1;
     const size_t smem = ((L >= 2 ? L / 2 : 1) + (size_t)p.tile * LS) * sizeof(uint32_t);
     const uint32_t total = L * p.tile;
     uint32_t threads = total / 16 >= 512 ? 512 : (total / 16 >= 32 ? total / 16 : 32);
     if (total >= (1u << 14) && threads > 256) threads = 256 * 2;
+    using KernelFn = void (*)(PassParams);
+    static const KernelFn kernels[15] = {ntt_pass_kernel<0>, ntt_pass_kernel<1>, ntt_pass_kernel<2>, ntt_pass_kernel<3>, ntt_pass_kernel<4>, ntt_pass_kernel<5>,
+                                         ntt_pass_kernel<6>, ntt_pass_kernel<7>, ntt_pass_kernel<8>, ntt_pass_kernel<9>, ntt_pass_kernel<10>, ntt_pass_kernel<11>,
+                                         ntt_pass_kernel<12>, ntt_pass_kernel<13>, ntt_pass_kernel<14>};
+    if (p.log_len > 14) VG_FAIL(ctx, "ntt: sub-transform 2^%u exceeds the shared-memory tile", p.log_len);
     static bool attr_set = false;
-    if (!attr_set) { VG_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    if (!attr_set) { for (auto k : kernels) VG_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     for (uint64_t c0 = 0; c0 < w; c0 += 65535) {     // grid.y limit
         const uint64_t wc = w - c0 < 65535 ? w - c0 : 65535;
         PassParams q = p;
         q.src = p.src + c0 * p.src_cs; q.dst = p.dst + c0 * p.dst_cs;
         dim3 grid((unsigned)tiles, (unsigned)wc);
         KScope ks(ctx, KC_NTT, 8.0 * (double)(p.groups << p.log_len) * (double)wc);
-        ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(q);
+        kernels[p.log_len]<<<grid, threads, smem, ctx->stream>>>(q);
         VG_LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -339,8 +375,9 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
     const PowTable* tab = nullptr;
     uint32_t ninv_canon = bb::from_monty(bb::inv(bb::to_monty((uint32_t)(h % bb::P))));
     VG_TRY(vg_get_shift_table(ctx, shift_canonical, ninv_canon, h, &tab));
-    // column batches: bound the scratch and keep mid-size batches L2-resident between passes
-    uint64_t batch = (uint64_t)(24u << 20) / (4 * h);
+    // column batches bound the scratch; launches cover as many columns as possible (grid.y) so CTAs of
+    // different phases overlap on each SM
+    uint64_t batch = (2ull << 30) / (8 * h);   // coefficient + intermediate scratch <= 2 GB; whole matrices per launch
     if (batch < 1) batch = 1;
     if (batch > w) batch = w;
     uint32_t *coef = nullptr, *tmp = nullptr;
