@@ -101,6 +101,17 @@ int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
     VG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     VG_TRY(build_pow_table(ctx, bb::two_adic_generator_monty(VG_LOG_NMAX), bb::R1, (1ull << VG_LOG_NMAX) - 1, &ctx->root_table));
+    {   // three-level table (9 + 9 + 9 exponent bits)
+        std::vector<uint32_t> t(3 * 512);
+        uint32_t base = bb::two_adic_generator_monty(VG_LOG_NMAX);
+        for (int lvl = 0; lvl < 3; lvl++) {
+            uint32_t a = bb::R1;
+            for (int i = 0; i < 512; i++) { t[lvl * 512 + i] = a; a = bb::mul(a, base); }
+            base = a;   // base^512
+        }
+        VG_TRY(vg_alloc(ctx, (void**)&ctx->root3, t.size() * 4));
+        VG_CUDA(ctx, cudaMemcpy(ctx->root3, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 

@@ -37,19 +37,20 @@ struct PassParams {
     uint32_t src_bitrev;              // 1: memory element r holds natural index bitrev(r) (load into slot bitrev(r))
     uint32_t dst_natural;             // 1: natural output k stored at pos = k ; 0: raw DIF order pos = bitrev(k)
     uint32_t g_bits;                  // if nonzero, multipliers see gval = bitrev(g, g_bits) instead of g
-    // pre-multiplier: x *= w_NMAX^((rnat*pre_r + gval*pre_g) * pre_unit), rnat = natural index of the element in its group
-    uint32_t pre_mode; uint64_t pre_r, pre_g, pre_unit;
+    // pre-multiplier: x *= w_NMAX^((rnat*pre_r + gval*pre_g) << pre_shift), rnat = natural index of the element in its group
+    uint32_t pre_mode; uint32_t pre_r, pre_g, pre_shift;   // exponent = (rnat*pre_r + gval*pre_g) << pre_shift  (< 2^27)
     // post-multiplier on natural output k: mode 1: w_NMAX^(+-(gval*k) * post_unit) ; mode 2: table[gval*post_g + k*post_k] ; mode 3: constant
-    uint32_t post_mode; uint64_t post_unit, post_g, post_k; uint32_t post_scale;
-    const uint32_t* root_lo; const uint32_t* root_hi;   // w_NMAX tables
+    uint32_t post_mode; uint32_t post_shift, post_g, post_k; uint32_t post_scale;   // mode 1 exponent = (gval*k) << post_shift
+    const uint32_t* root_lo; const uint32_t* root_hi;   // w_NMAX tables (two-level: 4096 + 32768 entries)
+    const uint32_t* root3;                              // w_NMAX three-level table (3 x 512 entries, stays in L1)
     const uint32_t* tab_lo; const uint32_t* tab_hi;     // shift tables (mode 2)
 };
 
-__device__ __forceinline__ uint32_t root_pow(const PassParams& p, uint64_t e) {
-    e &= ((1ull << VG_LOG_NMAX) - 1);
-    uint32_t lo = __ldg(p.root_lo + (e & (VG_POW_LO - 1)));
-    uint32_t hi = __ldg(p.root_hi + (e >> VG_POW_LO_BITS));
-    return mul(lo, hi);
+__device__ __forceinline__ uint32_t root_pow(const PassParams& p, uint32_t e) {
+    // the shared-memory tiles leave ~24 KB of L1: the 144 KB two-level table misses to L2 on every element,
+    // the 6 KB three-level one hits (one more multiply, ~10x less latency)
+    const uint32_t a = __ldg(p.root3 + (e & 511)), b = __ldg(p.root3 + 512 + ((e >> 9) & 511)), c = __ldg(p.root3 + 1024 + ((e >> 18) & 511));
+    return mul(mul(a, b), c);
 }
 
 // one spare word per 16 (conflict-free stride-16 access of the last radix-16 step) plus one per 512
@@ -80,7 +81,7 @@ __device__ __forceinline__ void radix_unit(uint32_t* __restrict__ grp, const uin
                 x[m0] = add(A, B);
                 const uint32_t d = sub(A, B);
                 if (a == RHO - 1 && LQ == 0) x[m1] = d;                       // last stage of the transform: twiddle 1
-                else x[m1] = mul(d, tw[tj + ((uint32_t)mm << (LQ + S + a))]);
+                else { const uint32_t ti = tj + ((uint32_t)mm << (LQ + S + a)); x[m1] = mul(d, tw[ti + (ti >> 5)]); }
             }
         }
     }
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     const uint32_t T = p.tile;
     const uint32_t LS = (L + (L >> 4) + (L >> 9)) | 1;   // padded, odd group pitch
     uint32_t* tw = smem;                             // L/2 twiddles w_L^(+-j)
-    uint32_t* data = smem + (L >= 2 ? L / 2 : 1);
+    uint32_t* data = smem + (L >= 2 ? L / 2 + L / 64 + 1 : 1);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint64_t col = blockIdx.y;
     const uint64_t g0 = (uint64_t)blockIdx.x * T;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
         for (uint32_t j = tid; j < L / 2; j += nt) {
             uint64_t e = (uint64_t)j * unit;
             if (p.inverse && e) e = (1ull << VG_LOG_NMAX) - e;
-            tw[j] = __ldg(p.root_hi + (e >> VG_POW_LO_BITS));
+            tw[j + (j >> 5)] = __ldg(p.root_hi + (e >> VG_POW_LO_BITS));
         }
     }
     // ---- load (4 independent global loads in flight per thread) ----
@@ -160,9 +161,9 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
                     const uint32_t rnat = p.src_bitrev ? bb::reverse_bits(rr[u], (int)LOG_LEN) : rr[u];
                     uint32_t x = v[u];
                     if (p.pre_mode) {
-                        const uint64_t g = g0 + tt[u];
-                        const uint64_t gval = p.g_bits ? bb::reverse_bits((uint32_t)g, (int)p.g_bits) : g;
-                        x = mul(x, root_pow(p, ((uint64_t)rnat * p.pre_r + gval * p.pre_g) * p.pre_unit));
+                        const uint32_t g = (uint32_t)g0 + tt[u];
+                        const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+                        x = mul(x, root_pow(p, (rnat * p.pre_r + gval * p.pre_g) << p.pre_shift));
                     }
                     data[tt[u] * LS + pad(rnat)] = x;
                 }
@@ -183,14 +184,14 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
             const uint32_t k = p.dst_natural ? pos : brp;      // its natural output index
             uint32_t v = data[t * LS + pad(q)];
             if (p.post_mode) {
-                const uint64_t g = g0 + t;
-                const uint64_t gval = p.g_bits ? bb::reverse_bits((uint32_t)g, (int)p.g_bits) : g;
+                const uint32_t g = (uint32_t)g0 + t;
+                const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
                 if (p.post_mode == 1) {
-                    uint64_t e = ((gval * k) * p.post_unit) & ((1ull << VG_LOG_NMAX) - 1);
-                    if (p.inverse && e) e = (1ull << VG_LOG_NMAX) - e;
+                    uint32_t e = (gval * k) << p.post_shift;          // < 2^27: gval*k < n and shift = 27 - log2(n)
+                    if (p.inverse) e = (0u - e);                      // root_pow masks to 27 bits: w^(-e) = w^(2^27 - e)
                     v = mul(v, root_pow(p, e));
                 } else if (p.post_mode == 2) {
-                    const uint64_t e = gval * p.post_g + (uint64_t)k * p.post_k;
+                    const uint32_t e = gval * p.post_g + k * p.post_k;
                     v = mul(v, mul(__ldg(p.tab_lo + (e & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e >> VG_POW_LO_BITS))));
                 } else {
                     v = mul(v, p.post_scale);
@@ -215,12 +216,12 @@ uint32_t choose_tile(int log_len, uint64_t groups) {
 }
 
 int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
-    p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi;
+    p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi; p.root3 = ctx->root3;
     const uint32_t L = 1u << p.log_len;
     p.tile = choose_tile((int)p.log_len, p.groups);
     const uint64_t tiles = p.groups / p.tile;
     const uint32_t LS = (L + (L >> 4) + (L >> 9)) | 1;
-    const size_t smem = ((L >= 2 ? L / 2 : 1) + (size_t)p.tile * LS) * sizeof(uint32_t);
+    const size_t smem = ((L >= 2 ? L / 2 + L / 64 + 1 : 1) + (size_t)p.tile * LS) * sizeof(uint32_t);
     const uint32_t total = L * p.tile;
     uint32_t threads = total / 16 >= 512 ? 512 : (total / 16 >= 32 ? total / 16 : 32);
     if (total >= (1u << 14) && threads > 256) threads = 256 * 2;
@@ -282,7 +283,7 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
     p.src = src; p.src_cs = src_cs; p.dst = tmp; p.dst_cs = tmp_cs;
     p.src_rs = n2; p.src_gs = 1; p.dst_rs = 1; p.dst_gs = n1;
     p.log_len = l1; p.groups = n2; p.dst_natural = 1;
-    p.post_mode = 1; p.post_unit = (1ull << VG_LOG_NMAX) >> log_n;
+    p.post_mode = 1; p.post_shift = VG_LOG_NMAX - log_n;
     VG_TRY(launch_pass(ctx, p, w));
     // pass 2: tmp is [i2][k1]; over i2 (stride n1) for each k1; X[k1 + n1*k2] stored at that index
     PassParams q{};
@@ -290,7 +291,7 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
     q.src = tmp; q.src_cs = tmp_cs; q.dst = dst; q.dst_cs = dst_cs;
     q.src_rs = n1; q.src_gs = 1; q.dst_rs = n1; q.dst_gs = 1;
     q.log_len = l2; q.groups = n1; q.dst_natural = 1;
-    if (coset) { q.post_mode = 2; q.post_g = 1; q.post_k = n1; q.tab_lo = coset->lo; q.tab_hi = coset->hi; }
+    if (coset) { q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n1; q.tab_lo = coset->lo; q.tab_hi = coset->hi; }
     else if (inverse) { q.post_mode = 3; q.post_scale = ninv; }
     return launch_pass(ctx, q, w);
 }
@@ -315,7 +316,7 @@ static int32_t intt_nat2bitrev_scaled(vgpu_ctx* ctx, const uint32_t* src, uint64
     p.src = src; p.src_cs = src_cs; p.dst = buf; p.dst_cs = bcs;
     p.src_rs = n2; p.src_gs = 1; p.dst_rs = n2; p.dst_gs = 1;
     p.log_len = lc; p.groups = n2; p.dst_natural = 0;
-    p.post_mode = 1; p.post_unit = (1ull << VG_LOG_NMAX) >> log_n;
+    p.post_mode = 1; p.post_shift = VG_LOG_NMAX - log_n;
     VG_TRY(launch_pass(ctx, p, w));
     // row pass on row q1 = bitrev(k1): over i2 -> k2 stored raw; K = k1 + n1*k2 = bitrev(q1) + n1*k
     PassParams q{};
@@ -324,7 +325,7 @@ static int32_t intt_nat2bitrev_scaled(vgpu_ctx* ctx, const uint32_t* src, uint64
     q.src_rs = 1; q.src_gs = n2; q.dst_rs = 1; q.dst_gs = n2;
     q.log_len = lr; q.groups = n1; q.dst_natural = 0;
     q.g_bits = lc;
-    q.post_mode = 2; q.post_g = 1; q.post_k = n1; q.tab_lo = tab->lo; q.tab_hi = tab->hi;
+    q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n1; q.tab_lo = tab->lo; q.tab_hi = tab->hi;
     return launch_pass(ctx, q, w);
 }
 
@@ -341,7 +342,7 @@ static int32_t ntt_bitrev2bitrev(vgpu_ctx* ctx, const uint32_t* coef, uint64_t c
         p.src = coef; p.src_cs = ccs; p.dst = dst; p.dst_cs = dst_cs;
         p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
         p.log_len = log_n; p.groups = 1; p.src_bitrev = 1; p.dst_natural = 0;
-        if (odd) { p.pre_mode = 1; p.pre_r = 1; p.pre_g = 0; p.pre_unit = (1ull << VG_LOG_NMAX) >> (log_n + 1); }
+        if (odd) { p.pre_mode = 1; p.pre_r = 1; p.pre_g = 0; p.pre_shift = VG_LOG_NMAX - (log_n + 1); }
         return launch_pass(ctx, p, w);
     }
     const uint64_t n1 = 1ull << lc, n2 = 1ull << lr;
@@ -351,8 +352,8 @@ static int32_t ntt_bitrev2bitrev(vgpu_ctx* ctx, const uint32_t* coef, uint64_t c
     p.src_rs = 1; p.src_gs = n2; p.dst_rs = 1; p.dst_gs = n2;
     p.log_len = lr; p.groups = n1; p.src_bitrev = 1; p.dst_natural = 0;
     p.g_bits = lc;
-    if (odd) { p.pre_mode = 1; p.pre_r = n1; p.pre_g = 1; p.pre_unit = (1ull << VG_LOG_NMAX) >> (log_n + 1); }
-    p.post_mode = 1; p.post_unit = (1ull << VG_LOG_NMAX) >> log_n;
+    if (odd) { p.pre_mode = 1; p.pre_r = (uint32_t)n1; p.pre_g = 1; p.pre_shift = VG_LOG_NMAX - (log_n + 1); }
+    p.post_mode = 1; p.post_shift = VG_LOG_NMAX - log_n;
     VG_TRY(launch_pass(ctx, p, w));
     // column pass over rows j1 (k1' = bitrev(j1)) for each column q: -> m1 ; E[m1*n2 + m2] goes to
     // bitrev_n = bitrev(m2)*n1 + bitrev(m1) = q*n1 + raw slot: transposed store, raw order
