@@ -86,3 +86,58 @@ def test_prove_2_16_rows_verifies(ctx, oracle):
     t = vb.run_program(vb.fib_program(9360), initial_fp=0x1000)   # 65537 cycles -> 2^17 CPU rows
     proof = gpu_prove(ctx, oracle, t)
     assert oracle.verify(proof, t.preprocessed) == 0
+
+
+import json
+import os
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "programs.json")))
+
+
+@pytest.mark.parametrize("name", ["left_imm_ops_program", "signed_inequality_program", "loadfp_program"])
+def test_prove_reference_test_programs_bytes_equal(ctx, oracle, name):
+    """prove_left_imm_ops / prove_signed_inequality / prove_loadfp of basic/tests/test_prover.rs:490-625."""
+    import valida_b200 as vb
+
+    t = vb.run_program(np.array(GOLDEN[name]["program"], dtype=np.int32), initial_fp=0x1000)
+    for addr, value in GOLDEN[name]["expected_cells"]:
+        assert t.mem_cell(addr) == value
+    proof = gpu_prove(ctx, oracle, t)
+    assert proof == oracle.prove(t.main, t.preprocessed, debug_checks=False).cbor()
+    assert oracle.verify(proof, t.preprocessed) == 0
+
+
+def mixed_program(iters):
+    """Multi-chip synthetic loop (cpu + mem + add + lt + range + program): LCG-style value stream with
+    add / lt / lte / slt / sle (incl. left immediates) and a bne back-edge."""
+    B = 24
+    return np.array([
+        [7, -4, 0, 0, 0, 0],                                  # i = 0
+        [7, -8, 0x12, 0x34, 0x56, 0x78],                      # x = seed
+        [100, -8, -8, 1013904223, 0, 1],                      # x += c            (add32 imm)
+        [100, -12, -8, -4, 0, 0],                             # y = x + i         (add32)
+        [104, -16, -12, -8, 0, 0],                            # y < x             (lt32)
+        [117, -20, -8, -12, 0, 0],                            # x <s y            (slt32)
+        [115, -24, 77, -8, 1, 0],                             # 77 <= x           (lte32, left immediate)
+        [118, -28, -12, 1000, 0, 1],                          # y <=s 1000        (sle32, right immediate)
+        [100, -4, -4, 1, 0, 1],                               # i += 1
+        [6, 2 * B, -4, iters, 0, 1],                          # bne loop, i, iters
+        [8, 0, 0, 0, 0, 0],
+    ], dtype=np.int32)
+
+
+def test_prove_mixed_chip_program(ctx, oracle):
+    import valida_b200 as vb
+
+    t = vb.run_program(mixed_program(100), initial_fp=0x1000)
+    assert t.main[8].shape[0] == 512 and t.main[3].shape[0] == 512    # 400 lt ops, 300 add ops
+    ref = oracle.prove(t.main, t.preprocessed, debug_checks=True)
+    assert ref.constraint_failures() == [-1] * 14 and ref.cumulative_sum_zero()
+    proof = gpu_prove(ctx, oracle, t)
+    assert proof == ref.cbor()
+    assert oracle.verify(proof, t.preprocessed) == 0
+    # larger instance: verifier accepts (oracle prover not run)
+    t2 = vb.run_program(mixed_program(20000), initial_fp=0x1000)
+    assert t2.main[0].shape[0] == 1 << 18
+    p2 = gpu_prove(ctx, oracle, t2)
+    assert oracle.verify(p2, t2.preprocessed) == 0

@@ -104,3 +104,24 @@ def test_verifier_rejects_tampering(fib25, oracle):
     pr = oracle.prove(bad_main, fib25.preprocessed, debug_checks=True)
     assert pr.constraint_failures()[3] != -1
     assert oracle.verify(pr.cbor(), fib25.preprocessed) != 0
+
+
+# ---- the reference's other proving tests (basic/tests/test_prover.rs:490-625), via tests/golden/programs.json ----
+import json
+import os
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "programs.json")))
+
+
+@pytest.mark.parametrize("name", ["left_imm_ops_program", "signed_inequality_program", "loadfp_program"])
+def test_reference_test_programs_vm_state_and_oracle_proof(built, oracle, name):
+    import valida_b200 as vb
+
+    g = GOLDEN[name]
+    t = vb.run_program(np.array(g["program"], dtype=np.int32), initial_fp=0x1000)
+    for addr, value in g["expected_cells"]:          # the reference test's own assertions on machine.mem().cells
+        assert t.mem_cell(addr) == value, (name, hex(addr))
+    pr = oracle.prove(t.main, t.preprocessed, debug_checks=True)
+    assert pr.constraint_failures() == [-1] * 14     # check_constraints (debug builds of the reference)
+    assert pr.cumulative_sum_zero()                  # check_cumulative_sums
+    assert oracle.verify(pr.cbor(), t.preprocessed) == 0

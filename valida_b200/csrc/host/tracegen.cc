@@ -1,6 +1,6 @@
 // Host witness generation for BasicMachine: a small Valida VM for the instruction subset the
-// reference's proving tests exercise (imm32, add32/sub32 with and without immediates, jal, jalv,
-// beq, bne, load32, store32, loadfp, stop) and the Chip::generate_trace of every chip.
+// reference's proving tests exercise (imm32, add32/sub32 with and without immediates, lt32/lte32/
+// slt32/sle32 incl. left immediates, jal, jalv, beq, bne, load32, store32, loadfp, stop) and the Chip::generate_trace of every chip.
 // This is the INPUT side of the proving path (SURVEY.md §8a "Chip::generate_trace x14 — kept on
 // host, input to the GPU path"); it follows
 //   run loop + STOP padding        basic/src/lib.rs:127-145, 1063-1188
@@ -31,12 +31,13 @@ inline uint32_t from_i32(int32_t x) { return x < 0 ? (P - (uint32_t)(-(int64_t)x
 inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
 
 enum : uint32_t { OP_LOAD32 = 1, OP_STORE32 = 2, OP_JAL = 3, OP_JALV = 4, OP_BEQ = 5, OP_BNE = 6, OP_IMM32 = 7, OP_STOP = 8, OP_LOADFP = 10,
-                  OP_ADD32 = 100, OP_SUB32 = 101 };
-enum CpuOp : uint8_t { K_STORE32, K_LOAD32, K_JAL, K_JALV, K_BEQ, K_BNE, K_IMM32, K_BUS, K_STOP, K_LOADFP };
+                  OP_ADD32 = 100, OP_SUB32 = 101, OP_LT32 = 104, OP_LTE32 = 115, OP_SLT32 = 117, OP_SLE32 = 118 };
+enum CpuOp : uint8_t { K_STORE32, K_LOAD32, K_JAL, K_JALV, K_BEQ, K_BNE, K_IMM32, K_BUS, K_STOP, K_LOADFP, K_BUS_LEFT_IMM };
 
 struct MemOp { uint32_t clk, addr, value; uint8_t is_write; };
 struct CpuRec { uint32_t pc, fp; uint32_t instr; CpuOp kind; bool has_imm; uint32_t imm; };
 struct AluRec { uint32_t a, b, c; };
+struct LtRec { uint32_t a, b, c; uint32_t opcode; };
 
 struct Vm {
     const int32_t* prog; size_t n_instr;
@@ -45,6 +46,7 @@ struct Vm {
     std::vector<MemOp> mem_ops;
     std::vector<CpuRec> cpu;
     std::vector<AluRec> adds, subs;
+    std::vector<LtRec> lts;
     std::vector<uint32_t> prog_counts;
     uint32_t range_count[256] = {0};
     std::string err;
@@ -83,6 +85,19 @@ struct Vm {
                 (opcode == OP_ADD32 ? adds : subs).push_back({av, bv, cv});
                 pc++; push(K_BUS, pc0, pc0, fp0, imm, cv);
                 range_check(av); break; }
+            case OP_LT32: case OP_LTE32: case OP_SLT32: case OP_SLE32: {
+                // alu_u32/src/lt/mod.rs:162-205 (execute_with_closure): d == 1 -> left operand is the immediate b;
+                // e == 1 -> right operand is the immediate c (and `imm` then holds c, as in the reference)
+                uint32_t s1, s2; bool limm = (d == 1), rimm = (e == 1);
+                uint32_t immv = 0; bool has_imm = false;
+                if (limm) { s1 = (uint32_t)b; immv = s1; has_imm = true; } else if (!read(at(b), s1)) return -1;
+                if (rimm) { s2 = (uint32_t)c; immv = s2; has_imm = true; } else if (!read(at(c), s2)) return -1;
+                bool r;
+                if (opcode == OP_LT32) r = s1 < s2; else if (opcode == OP_LTE32) r = s1 <= s2;
+                else if (opcode == OP_SLT32) r = (int32_t)s1 < (int32_t)s2; else r = (int32_t)s1 <= (int32_t)s2;
+                write(at(a), r ? 1u : 0u);
+                lts.push_back({r ? 1u : 0u, s1, s2, opcode});
+                pc++; push(limm ? K_BUS_LEFT_IMM : K_BUS, pc0, pc0, fp0, has_imm, immv); break; }
             case OP_JAL: {
                 write(at(a), 24u * (pc0 + 1)); pc = (uint32_t)b / 24u; fp = at(c); push(K_JAL, pc0, pc0, fp0); break; }
             case OP_JALV: {
@@ -158,8 +173,13 @@ void build_cpu(const Vm& vm, Traces& t) {
             case K_BUS: row[9] = 1; break;
             case K_STOP: row[24] = 1; break;
             case K_LOADFP: row[25] = 1; break;
+            case K_BUS_LEFT_IMM: row[9] = 1; break;
         }
-        if (r.has_imm) {  // set_imm_value (cpu/src/lib.rs:355-362)
+        if (r.has_imm && r.kind == K_BUS_LEFT_IMM) {  // set_left_imm_value (cpu/src/lib.rs:364-371)
+            row[12] = 1; left_imm = true;
+            word_be(r.imm, &row[29 + 3]);
+            row[5] = r.imm % P;
+        } else if (r.has_imm) {  // set_imm_value (cpu/src/lib.rs:355-362)
             row[11] = 1;
             word_be(r.imm, &row[36 + 3]);
             row[6] = r.imm % P;
@@ -242,6 +262,36 @@ void build_addsub(const std::vector<AluRec>& ops, bool is_add, std::vector<uint3
     out = {v.data(), h, W};
 }
 
+// Lt32Chip::op_to_row / set_cols (alu_u32/src/lt/mod.rs:86-160)
+void build_lt(const std::vector<LtRec>& ops, std::vector<uint32_t>& v, vgpu_matrix& out) {
+    constexpr size_t W = 45;
+    size_t n = ops.size(), h = next_pow2(n);
+    v.assign(h * W, 0);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t* row = &v[i * W];
+        uint32_t a[4], b[4], c[4];
+        word_be(ops[i].a, a); word_be(ops[i].b, b); word_be(ops[i].c, c);
+        std::memcpy(row + 0, b, 16); std::memcpy(row + 4, c, 16);
+        row[21] = a[3];
+        bool is_signed = ops[i].opcode == OP_SLT32 || ops[i].opcode == OP_SLE32;
+        row[ops[i].opcode == OP_LT32 ? 23 : ops[i].opcode == OP_LTE32 ? 24 : ops[i].opcode == OP_SLT32 ? 25 : 26] = 1;
+        for (int k = 0; k < 4; k++) {
+            if (b[k] != c[k]) {
+                uint32_t z = 256u + b[k] - c[k];
+                for (int bit = 0; bit < 9; bit++) row[12 + bit] = (z >> bit) & 1;
+                row[8 + k] = 1;
+                uint32_t diff = (b[k] + P - c[k]) % P;
+                row[27] = fpow(diff, P - 2);
+                break;
+            }
+        }
+        for (int bit = 0; bit < 8; bit++) { row[28 + bit] = (b[0] >> bit) & 1; row[36 + bit] = (c[0] >> bit) & 1; }
+        row[44] = (is_signed && row[28 + 7] != row[36 + 7]) ? 1 : 0;
+        row[22] = 1;
+    }
+    out = {v.data(), h, W};
+}
+
 void zero_chip(std::vector<uint32_t>& v, vgpu_matrix& out, size_t w) { v.assign(w, 0); out = {v.data(), 1, w}; }
 
 }  // namespace
@@ -291,7 +341,7 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
     }
     zero_chip(t.store[6], t.main[6], 14);   // div
     zero_chip(t.store[7], t.main[7], 28);   // shift
-    zero_chip(t.store[8], t.main[8], 45);   // lt
+    build_lt(vm.lts, t.store[8], t.main[8]);   // lt
     zero_chip(t.store[9], t.main[9], 14);   // com
     zero_chip(t.store[10], t.main[10], 79); // bitwise
     zero_chip(t.store[11], t.main[11], 7);  // output

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, u
 }
 
 // K8: partial sums S[c][p] = sum_{rho in block rows} e[rho][c] * x_rho * invden_p[rho] over the first h rows.
-constexpr int BARY_COLS = 4, BARY_THREADS = 256;
+constexpr int BARY_COLS = 8, BARY_THREADS = 256;
 struct BaryParams {
     const uint32_t* mat; uint64_t mcs; uint64_t h; uint32_t log_H; uint32_t w;
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
@@ -51,10 +51,9 @@ struct BaryParams {
 __global__ void __launch_bounds__(BARY_THREADS) bary_kernel(BaryParams p) {
     const uint32_t c0 = blockIdx.y * BARY_COLS;
     const uint32_t nc = min((uint32_t)BARY_COLS, p.w - c0);
-    bb::Acc5 lazy[BARY_COLS][2];
+    E5 acc[BARY_COLS][2];
 #pragma unroll
-    for (int c = 0; c < BARY_COLS; c++) { bb::acc5_zero(lazy[c][0]); bb::acc5_zero(lazy[c][1]); }
-    uint32_t pending = 0;
+    for (int c = 0; c < BARY_COLS; c++) { acc[c][0] = bb::e5_zero(); acc[c][1] = bb::e5_zero(); }
     for (uint64_t r = (uint64_t)blockIdx.x * BARY_THREADS + threadIdx.x; r < p.h; r += (uint64_t)gridDim.x * BARY_THREADS) {
         uint32_t nat = bb::reverse_bits((uint32_t)r, (int)p.log_H);
         uint32_t x = bb::mul(p.s, oroot_pow(p.lo, p.hi, (uint64_t)nat << (VG_LOG_NMAX - p.log_H)));
@@ -64,19 +63,11 @@ __global__ void __launch_bounds__(BARY_THREADS) bary_kernel(BaryParams p) {
         for (int c = 0; c < BARY_COLS; c++) {
             if ((uint32_t)c < nc) {
                 uint32_t e = __ldg(p.mat + (uint64_t)(c0 + c) * p.mcs + r);
-                bb::acc5_fma_base(lazy[c][0], wgt[0], e);
-                if (p.npoints > 1) bb::acc5_fma_base(lazy[c][1], wgt[1], e);
+                acc[c][0] = bb::e5_add(acc[c][0], bb::e5_mul_base(wgt[0], e));
+                if (p.npoints > 1) acc[c][1] = bb::e5_add(acc[c][1], bb::e5_mul_base(wgt[1], e));
             }
         }
-        if (++pending == 3) {   // folded value < 2^61; three products of < 2^62 each keep the sum below 2^64
-            pending = 0;
-#pragma unroll
-            for (int c = 0; c < BARY_COLS; c++) { bb::acc5_fold(lazy[c][0]); bb::acc5_fold(lazy[c][1]); }
-        }
     }
-    E5 acc[BARY_COLS][2];
-#pragma unroll
-    for (int c = 0; c < BARY_COLS; c++) { acc[c][0] = bb::acc5_value(lazy[c][0]); acc[c][1] = bb::acc5_value(lazy[c][1]); }
     // block reduction through shared memory
     __shared__ uint32_t red[BARY_THREADS / 32][BARY_COLS * 2 * 5];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -113,12 +104,7 @@ __global__ void __launch_bounds__(256) reduced_opening_kernel(RoParams p) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.H) return;
     E5 red = bb::e5_zero();
-    bb::Acc5 lazy; bb::acc5_zero(lazy);
-    for (uint32_t c = 0; c < p.w; c++) {
-        bb::acc5_fma_base(lazy, p.apow[c], __ldg(p.mat + (uint64_t)c * p.mcs + i));
-        if ((c & 3) == 3) bb::acc5_flush(lazy, red);
-    }
-    bb::acc5_flush(lazy, red);
+    for (uint32_t c = 0; c < p.w; c++) red = bb::e5_add(red, bb::e5_mul_base(p.apow[c], __ldg(p.mat + (uint64_t)c * p.mcs + i)));
     E5 acc = ld5(p.ro, p.rcs, i);
     for (uint32_t q = 0; q < p.npoints; q++) {
         E5 t = bb::e5_mul(bb::e5_sub(red, p.sum_y[q]), ld5(p.invden[q], p.ics, i));
