@@ -88,6 +88,24 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
 
 
+def tune_oracle_threads(orc, vb):
+    """Pick the OpenMP thread count that proves a small sample fastest (large core counts oversubscribe the
+    oracle's many short parallel regions); returns the chosen count."""
+    t = vb.run_program(vb.fib_program(fib_n_for_log_rows(14)), initial_fp=0x1000)
+    best, best_n = None, None
+    cores = os.cpu_count() or 1
+    for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+        orc.set_threads(n)
+        t0 = time.perf_counter()
+        pr = orc.prove(t.main, t.preprocessed, debug_checks=False)
+        dt = time.perf_counter() - t0
+        del pr
+        if best is None or dt < best:
+            best, best_n = dt, n
+    orc.set_threads(best_n)
+    return best_n
+
+
 def run_reference(args, rank):
     """Reference arm: the oracle prover (CPU restatement of the reference) on a bounded sample."""
     if rank != 0:
@@ -98,6 +116,7 @@ def run_reference(args, rank):
 
     vbuild.build_oracle()
     orc = oracle_binding.Oracle()
+    threads = tune_oracle_threads(orc, vb)
     log_rows = args.ref_log_rows
     n = fib_n_for_log_rows(log_rows)
     t = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
@@ -112,8 +131,9 @@ def run_reference(args, rank):
             times.append(dt)
     total = sum(times)
     value = rows * len(times) / total
-    cores = os.cpu_count()
-    sample = "Fibonacci n=%d: 2^%d CPU rows (mem 2^%d), full prove per step" % (n, log_rows, (t.main[2].shape[0]).bit_length() - 1)
+    cores = threads
+    sample = "Fibonacci n=%d: 2^%d CPU rows (mem 2^%d), full prove per step; %d OpenMP threads (best of a sweep) on %d host cores" % (
+        n, log_rows, (t.main[2].shape[0]).bit_length() - 1, threads, os.cpu_count())
     line = {
         "impl": "reference", "metric": "trace rows/sec proven (Fibonacci)", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -138,7 +158,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-rows", type=int, default=22, help="log2 of the CPU-chip trace height (BASELINE config: 22)")
     ap.add_argument("--ref-log-rows", type=int, default=18, help="bounded sample size of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-log-rows", type=int, default=17)
+    ap.add_argument("--cpu-baseline-log-rows", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -210,14 +230,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    proof_len = 0
-    ctx.set_kernel_timing(True)   # on during warm-up too, so the event pool is populated before the timed region
     for _ in range(args.warmup):
-        proof_len = len(vb.prove_machine(cfg, traces, device_resident=(dm, dp)))
+        vb.prove_machine(cfg, traces, device_resident=(dm, dp))
 
-    # ---- timed: device-resident ----
+    # ---- timed: device-resident, no instrumentation ----
     sampler = ClockSampler(local_rank)
-    ctx.kernel_stats()
     launches0 = ctx.launch_count
     barrier()
     sampler.start()
@@ -230,10 +247,23 @@ def main():
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
-    kstats = ctx.kernel_stats()
-    ctx.set_kernel_timing(False)
     phases = vb.last_prove_phases(ctx)
     value, ms_total_max = aggregate_throughput(dist, rows * args.steps, ms_total, device="cuda")
+
+    # ---- the same K steps again with a CUDA-event pair around every kernel launch (per-kernel roofline) ----
+    ctx.set_kernel_timing(True)
+    vb.prove_machine(cfg, traces, device_resident=(dm, dp))   # populates the event pool
+    ctx.kernel_stats()
+    barrier()
+    ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ei0.record(stream)
+    for _ in range(args.steps):
+        vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+    ei1.record(stream)
+    barrier()
+    ms_instr = ei0.elapsed_time(ei1)
+    kstats = ctx.kernel_stats()
+    ctx.set_kernel_timing(False)
 
     # ---- timed: end to end through the host-buffer C-ABI call ----
     vb.prove_machine(cfg, PinnedTraces)
@@ -260,7 +290,7 @@ def main():
     top = kstats_sorted[0]
     achieved = (top[3] / 1e9) / (top[2] / 1e3)
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "share_of_step": top[2] / ms_total,
+                "peak_source": peak_src, "share_of_step": top[2] / ms_instr, "ms_per_step_instrumented": ms_instr / args.steps,
                 "note": "Keccak-f[1600] kernels are ALU-pipe bound (LOP3/SHF issue), not HBM bound; see DESIGN.md and profiles/"}
     ntt = [k for k in kstats if k[0] == "ntt_pass_kernel"]
     if ntt:
@@ -273,14 +303,16 @@ def main():
 
         vbuild.build_oracle()
         orc = oracle_binding.Oracle()
+        threads = tune_oracle_threads(orc, vb)
         nb = fib_n_for_log_rows(args.cpu_baseline_log_rows)
         tb = vb.run_program(vb.fib_program(nb), initial_fp=0x1000)
         t0 = time.perf_counter()
         ref = orc.prove(tb.main, tb.preprocessed, debug_checks=False)
         dt = time.perf_counter() - t0
         del ref
-        cpu_baseline = {"value": tb.main[0].shape[0] / dt, "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": "Fibonacci n=%d (2^%d CPU rows), one full oracle prove, %.1f s" % (nb, args.cpu_baseline_log_rows, dt)}
+        cpu_baseline = {"value": tb.main[0].shape[0] / dt, "unit": "rows/s", "cores": threads, "kind": "port",
+                        "sample": "Fibonacci n=%d (2^%d CPU rows), one full oracle prove, %.1f s, %d OpenMP threads (best of a sweep) on %d host cores"
+                                  % (nb, args.cpu_baseline_log_rows, dt, threads, os.cpu_count())}
 
     line = {
         "metric": "trace rows/sec proven (Fibonacci)", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

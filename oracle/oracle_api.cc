@@ -9,7 +9,12 @@
 
 using namespace orc;
 
+#include <omp.h>
+
 extern "C" {
+
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_max_threads() { return omp_get_max_threads(); }
 
 void orc_keccak256(const uint8_t* in, uint64_t len, uint8_t* out, uint32_t pad) { keccak256_pad(in, len, out, (uint8_t)pad); }
 

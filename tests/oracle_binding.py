@@ -33,6 +33,12 @@ class Oracle:
         L.orc_default_round_constants(rc)
         self.rc480 = np.array(list(rc), dtype=np.uint32)
 
+    def set_threads(self, n):
+        self.L.orc_set_threads(int(n))
+
+    def max_threads(self):
+        return int(self.L.orc_max_threads())
+
     # ---- primitives ----
     def keccak256(self, data, pad=0x01):
         out = (C.c_uint8 * 32)()
