@@ -64,6 +64,7 @@ static int32_t build_pow_table(vgpu_ctx* ctx, uint32_t base_monty, uint32_t scal
     VG_CUDA(ctx, cudaMemcpyAsync(t->hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
     t->hi_len = (uint32_t)hi_len;
+    t->base = base_monty;
     return 0;
 }
 

@@ -17,6 +17,7 @@ struct PowTable {            // device tables of Montgomery words
     uint32_t* lo = nullptr;  // base^j, j < 4096
     uint32_t* hi = nullptr;  // scale * base^(4096 j), j < hi_len
     uint32_t hi_len = 0;
+    uint32_t base = 0;       // the base itself (Montgomery), without the scale
 };
 
 // kernel classes for the optional per-launch CUDA-event timing (bench.py's roofline line)

@@ -44,6 +44,8 @@ struct PassParams {
     const uint32_t* root_lo; const uint32_t* root_hi;   // w_NMAX tables (two-level: 4096 + 32768 entries)
     const uint32_t* root3;                              // w_NMAX three-level table (3 x 512 entries, stays in L1)
     const uint32_t* tab_lo; const uint32_t* tab_hi;     // shift tables (mode 2)
+    uint32_t tab_base;                                  // the table's base (shift) in Montgomery form
+    uint32_t tab_step;                                  // base^(k_stride * post_k): running-product step of the store phase (host-computed)
 };
 
 __device__ __forceinline__ uint32_t root_pow(const PassParams& p, uint32_t e) {
@@ -174,30 +176,70 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     // ---- all DIF stages, 4 at a time in registers ----
     all_stages<LOG_LEN, 0>(data, tw, T, LS, tid, nt);
     // ---- store (with optional post multiplier) ----
+    // Thread-local view of the tile: fixed group t, positions pos = p0 + (j << lowbits), j < I.  The natural
+    // output index k is then K0 + kk (raw order, kk = bitrev(j)) or p0 + (j << lowbits) (natural order): an
+    // arithmetic progression, so the twiddle / coset multiplier is a running product (one multiply per
+    // element, no table lookups, no per-element exponent arithmetic).
     {
         const bool tfast = (p.dst_gs == 1);
-        for (uint32_t idx = tid; idx < total; idx += nt) {
-            uint32_t t, pos;
-            if (tfast) { t = idx & (T - 1); pos = idx >> log_t; } else { pos = idx & (L - 1); t = idx >> LOG_LEN; }
-            const uint32_t brp = bb::reverse_bits(pos, (int)LOG_LEN);
-            const uint32_t q = p.dst_natural ? brp : pos;      // smem slot holding the value stored at `pos`
-            const uint32_t k = p.dst_natural ? pos : brp;      // its natural output index
-            uint32_t v = data[t * LS + pad(q)];
-            if (p.post_mode) {
+        const uint32_t log_nt = 31 - __clz(nt);
+        const bool fast = tfast ? (nt >= T && log_nt - log_t <= (uint32_t)LOG_LEN) : (L >= nt);
+        if (fast && (p.post_mode == 1 || p.post_mode == 2)) {
+            const uint32_t lowbits = tfast ? (log_nt - log_t) : log_nt;
+            const uint32_t ibits = LOG_LEN - lowbits, I = 1u << ibits;
+            const uint32_t p0 = tfast ? (tid >> log_t) : tid;
+            const uint32_t ngroups_here = tfast ? 1u : T;                 // row-type: the same thread walks every group of the tile
+            for (uint32_t tg = 0; tg < ngroups_here; tg++) {
+                const uint32_t t = tfast ? (tid & (T - 1)) : tg;
                 const uint32_t g = (uint32_t)g0 + t;
                 const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+                // k runs over k_start + i * k_stride, i < I
+                const uint32_t k_start = p.dst_natural ? p0 : (bb::reverse_bits(p0, (int)lowbits) << ibits);
+                const uint32_t k_stride = p.dst_natural ? (1u << lowbits) : 1u;
+                uint32_t m, step;
                 if (p.post_mode == 1) {
-                    uint32_t e = (gval * k) << p.post_shift;          // < 2^27: gval*k < n and shift = 27 - log2(n)
-                    if (p.inverse) e = (0u - e);                      // root_pow masks to 27 bits: w^(-e) = w^(2^27 - e)
-                    v = mul(v, root_pow(p, e));
-                } else if (p.post_mode == 2) {
-                    const uint32_t e = gval * p.post_g + k * p.post_k;
-                    v = mul(v, mul(__ldg(p.tab_lo + (e & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e >> VG_POW_LO_BITS))));
+                    uint32_t e0 = (gval * k_start) << p.post_shift, es = (gval * k_stride) << p.post_shift;
+                    if (p.inverse) { e0 = 0u - e0; es = 0u - es; }
+                    m = root_pow(p, e0); step = root_pow(p, es);
                 } else {
-                    v = mul(v, p.post_scale);
+                    const uint32_t e0 = gval * p.post_g + k_start * p.post_k;
+                    m = mul(__ldg(p.tab_lo + (e0 & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e0 >> VG_POW_LO_BITS)));
+                    step = p.tab_step;
+                }
+                uint32_t* dcol = dst + (uint64_t)g * p.dst_gs;
+                const uint32_t* drow = data + t * LS;
+                for (uint32_t i = 0; i < I; i++) {
+                    const uint32_t j = p.dst_natural ? i : bb::reverse_bits(i, (int)ibits);
+                    const uint32_t pos = p0 + (j << lowbits);
+                    const uint32_t q = p.dst_natural ? bb::reverse_bits(pos, (int)LOG_LEN) : pos;
+                    dcol[(uint64_t)pos * p.dst_rs] = mul(drow[pad(q)], m);
+                    m = mul(m, step);
                 }
             }
-            dst[(uint64_t)pos * p.dst_rs + (g0 + t) * p.dst_gs] = v;
+        } else {
+            for (uint32_t idx = tid; idx < total; idx += nt) {
+                uint32_t t, pos;
+                if (tfast) { t = idx & (T - 1); pos = idx >> log_t; } else { pos = idx & (L - 1); t = idx >> LOG_LEN; }
+                const uint32_t brp = bb::reverse_bits(pos, (int)LOG_LEN);
+                const uint32_t q = p.dst_natural ? brp : pos;      // smem slot holding the value stored at `pos`
+                const uint32_t k = p.dst_natural ? pos : brp;      // its natural output index
+                uint32_t v = data[t * LS + pad(q)];
+                if (p.post_mode) {
+                    const uint32_t g = (uint32_t)g0 + t;
+                    const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+                    if (p.post_mode == 1) {
+                        uint32_t e = (gval * k) << p.post_shift;          // < 2^27: gval*k < n and shift = 27 - log2(n)
+                        if (p.inverse) e = (0u - e);                      // root_pow masks to 27 bits: w^(-e) = w^(2^27 - e)
+                        v = mul(v, root_pow(p, e));
+                    } else if (p.post_mode == 2) {
+                        const uint32_t e = gval * p.post_g + k * p.post_k;
+                        v = mul(v, mul(__ldg(p.tab_lo + (e & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e >> VG_POW_LO_BITS))));
+                    } else {
+                        v = mul(v, p.post_scale);
+                    }
+                }
+                dst[(uint64_t)pos * p.dst_rs + (g0 + t) * p.dst_gs] = v;
+            }
         }
     }
 }
@@ -232,6 +274,14 @@ int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
     if (p.log_len > 14) VG_FAIL(ctx, "ntt: sub-transform 2^%u exceeds the shared-memory tile", p.log_len);
     static bool attr_set = false;
     if (!attr_set) { for (auto k : kernels) VG_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    if (p.post_mode == 2) {   // step of the store phase's running product (see the kernel): base^(k_stride * post_k)
+        uint32_t log_nt = 0; while ((1u << log_nt) < threads) log_nt++;
+        uint32_t log_t = 0; while ((1u << log_t) < p.tile) log_t++;
+        const bool tfast = (p.dst_gs == 1);
+        const uint32_t lowbits = tfast ? (log_nt >= log_t ? log_nt - log_t : 0) : log_nt;
+        const uint64_t k_stride = p.dst_natural ? (1ull << lowbits) : 1ull;
+        p.tab_step = bb::pow(p.tab_base, k_stride * p.post_k);
+    }
     for (uint64_t c0 = 0; c0 < w; c0 += 65535) {     // grid.y limit
         const uint64_t wc = w - c0 < 65535 ? w - c0 : 65535;
         PassParams q = p;
@@ -272,7 +322,7 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
         p.src = src; p.src_cs = src_cs; p.dst = dst; p.dst_cs = dst_cs;
         p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
         p.log_len = log_n; p.groups = 1; p.dst_natural = 1;
-        if (coset) { p.post_mode = 2; p.post_g = 0; p.post_k = 1; p.tab_lo = coset->lo; p.tab_hi = coset->hi; }
+        if (coset) { p.post_mode = 2; p.post_g = 0; p.post_k = 1; p.tab_lo = coset->lo; p.tab_hi = coset->hi; p.tab_base = coset->base; }
         else if (inverse) { p.post_mode = 3; p.post_scale = ninv; }
         return launch_pass(ctx, p, w);
     }
@@ -291,7 +341,7 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
     q.src = tmp; q.src_cs = tmp_cs; q.dst = dst; q.dst_cs = dst_cs;
     q.src_rs = n1; q.src_gs = 1; q.dst_rs = n1; q.dst_gs = 1;
     q.log_len = l2; q.groups = n1; q.dst_natural = 1;
-    if (coset) { q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n1; q.tab_lo = coset->lo; q.tab_hi = coset->hi; }
+    if (coset) { q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n1; q.tab_lo = coset->lo; q.tab_hi = coset->hi; q.tab_base = coset->base; }
     else if (inverse) { q.post_mode = 3; q.post_scale = ninv; }
     return launch_pass(ctx, q, w);
 }
@@ -308,7 +358,7 @@ static int32_t intt_nat2bitrev_scaled(vgpu_ctx* ctx, const uint32_t* src, uint64
         p.src = src; p.src_cs = src_cs; p.dst = buf; p.dst_cs = bcs;
         p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
         p.log_len = log_n; p.groups = 1; p.dst_natural = 0;
-        p.post_mode = 2; p.post_g = 0; p.post_k = 1; p.tab_lo = tab->lo; p.tab_hi = tab->hi;
+        p.post_mode = 2; p.post_g = 0; p.post_k = 1; p.tab_lo = tab->lo; p.tab_hi = tab->hi; p.tab_base = tab->base;
         return launch_pass(ctx, p, w);
     }
     const uint64_t n1 = 1ull << lc, n2 = 1ull << lr;
@@ -325,7 +375,7 @@ static int32_t intt_nat2bitrev_scaled(vgpu_ctx* ctx, const uint32_t* src, uint64
     q.src_rs = 1; q.src_gs = n2; q.dst_rs = 1; q.dst_gs = n2;
     q.log_len = lr; q.groups = n1; q.dst_natural = 0;
     q.g_bits = lc;
-    q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n1; q.tab_lo = tab->lo; q.tab_hi = tab->hi;
+    q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n1; q.tab_lo = tab->lo; q.tab_hi = tab->hi; q.tab_base = tab->base;
     return launch_pass(ctx, q, w);
 }
 
