@@ -146,6 +146,33 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     const uint32_t log_t = 31 - __clz(T);
     {
         const bool tfast = (p.src_gs == 1);
+        const uint32_t log_nt = 31 - __clz(nt);
+        if (p.pre_mode && p.src_bitrev && !tfast && L >= 4 * nt) {
+            // odd-coset row pass: memory position r = tid + (j << log_nt) holds natural index
+            // rnat = (bitrev(tid) << ibits) + bitrev(j); walking i = bitrev(j) upwards makes the pre-multiplier
+            // w^((rnat*pre_r + gval*pre_g) << pre_shift) a running product
+            const uint32_t ibits = LOG_LEN - log_nt, I = 1u << ibits;
+            const uint32_t r_start = bb::reverse_bits(tid, (int)log_nt) << ibits;
+            const uint32_t step = root_pow(p, p.pre_r << p.pre_shift);
+            const uint32_t step2 = mul(step, step), step3 = mul(step2, step), step4 = mul(step2, step2);
+            for (uint32_t t = 0; t < T; t++) {
+                const uint32_t g = (uint32_t)g0 + t;
+                const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+                uint32_t m = root_pow(p, (r_start * p.pre_r + gval * p.pre_g) << p.pre_shift);
+                const uint32_t* srow = src + (uint64_t)g * p.src_gs;
+                uint32_t* drow = data + t * LS;
+                for (uint32_t i = 0; i < I; i += 4) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = srow[tid + (bb::reverse_bits(i + u, (int)ibits) << log_nt)];
+                    drow[pad(r_start + i)] = mul(v[0], m);
+                    drow[pad(r_start + i + 1)] = mul(v[1], mul(m, step));
+                    drow[pad(r_start + i + 2)] = mul(v[2], mul(m, step2));
+                    drow[pad(r_start + i + 3)] = mul(v[3], mul(m, step3));
+                    m = mul(m, step4);
+                }
+            }
+        } else
         for (uint32_t idx0 = tid; idx0 < total; idx0 += 4 * nt) {
             uint32_t v[4], tt[4], rr[4];
 #pragma unroll

@@ -131,6 +131,15 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const uint32_t* cur, uint
     st5(out, ocs, i, r);
 }
 
+// out[i] = sum over blocks of partial[b][i]
+__global__ void __launch_bounds__(256) bary_reduce_kernel(const uint32_t* __restrict__ partial, uint32_t nblocks, uint32_t n, uint32_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t acc = 0;
+    for (uint32_t b = 0; b < nblocks; b++) acc = bb::add(acc, partial[(uint64_t)b * n + i]);
+    out[i] = acc;
+}
+
 __global__ void __launch_bounds__(256) gather_words_kernel(const uint32_t* const* ptrs, uint64_t n, uint32_t* out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = *ptrs[i];
@@ -151,7 +160,7 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
     uint64_t H = lde->h, h = H / 2;
     uint32_t log_H = 0; while ((1ull << log_H) < H) log_H++;
     uint32_t w = (uint32_t)lde->w;
-    unsigned bx = (unsigned)std::min<uint64_t>((h + BARY_THREADS - 1) / BARY_THREADS, 2 * (uint64_t)ctx->sm_count);
+    unsigned bx = (unsigned)std::min<uint64_t>((h + BARY_THREADS - 1) / BARY_THREADS, 8 * (uint64_t)ctx->sm_count);
     unsigned by = (w + BARY_COLS - 1) / BARY_COLS;
     uint32_t* partial = nullptr;
     size_t pn = (size_t)bx * w * npoints * 5;
@@ -165,10 +174,15 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
         bary_kernel<<<dim3(bx, by), BARY_THREADS, 0, ctx->stream>>>(p);
     }
     VG_LAUNCH_CHECK(ctx);
-    std::vector<uint32_t> hp(pn);
-    VG_CUDA(ctx, cudaMemcpyAsync(hp.data(), partial, pn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const uint32_t nout = w * npoints * 5;
+    uint32_t* reduced = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&reduced, nout * 4));
+    bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, bx, nout, reduced);
+    VG_LAUNCH_CHECK(ctx);
+    std::vector<uint32_t> hp(nout);
+    VG_CUDA(ctx, cudaMemcpyAsync(hp.data(), reduced, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    vg_free(ctx, partial);
+    vg_free(ctx, partial); vg_free(ctx, reduced);
     // p(z) = -(z^h - s^h) / (h s^h) * S
     uint32_t log_h = log_H - 1;
     uint32_t s = bb::to_monty(bb::GEN_CANON), sh = s;
@@ -179,11 +193,8 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
         E5 zh = bb::e5_exp_pow2(z[q], (int)log_h);
         E5 norm = bb::e5_neg(bb::e5_mul_base(bb::e5_sub_base(zh, sh), denom_inv));
         for (uint32_t c = 0; c < w; c++) {
-            E5 S = bb::e5_zero();
-            for (unsigned b = 0; b < bx; b++) {
-                const uint32_t* v = &hp[(((size_t)b * w + c) * npoints + q) * 5];
-                for (int l = 0; l < 5; l++) S.c[l] = bb::add(S.c[l], v[l]);
-            }
+            E5 S;
+            for (int l = 0; l < 5; l++) S.c[l] = hp[((size_t)c * npoints + q) * 5 + l];
             (*ys)[(size_t)q * w + c] = bb::e5_mul(S, norm);
         }
     }
