@@ -164,7 +164,19 @@ int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, v
     return 0;
 }
 int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint32_t* host_row_major_out) {
-    return vg_download_rowmajor(ctx, m, repr, host_row_major_out);
+    VG_TRY(vg_download_rowmajor(ctx, m, repr, host_row_major_out));
+    if (m->bitrev_rows && m->h > 1) {   // present the logical (natural) row order to the caller
+        int lg = 0; while ((1ull << lg) < m->h) lg++;
+        std::vector<uint32_t> tmp(m->w);
+        for (uint64_t i = 0; i < m->h; i++) {
+            uint64_t j = bb::reverse_bits((uint32_t)i, lg);
+            if (i < j) {
+                uint32_t* a = host_row_major_out + i * m->w; uint32_t* b = host_row_major_out + j * m->w;
+                std::memcpy(tmp.data(), a, m->w * 4); std::memcpy(a, b, m->w * 4); std::memcpy(b, tmp.data(), m->w * 4);
+            }
+        }
+    }
+    return 0;
 }
 int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width) { *height = m->h; *width = m->w; return 0; }
 void vgpu_dmat_free(vgpu_dmat* m) {
@@ -180,6 +192,7 @@ int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
     if ((1ull << log_n) != m->h) VG_FAIL(ctx, "ntt_batch: height %llu is not a power of two", (unsigned long long)m->h);
     if (log_n > VG_LOG_NMAX) VG_FAIL(ctx, "ntt_batch: height exceeds two-adicity");
     if (log_n > 24) VG_FAIL(ctx, "ntt_batch: heights above 2^24 need a three-pass split (not built yet)");
+    if (m->bitrev_rows) VG_FAIL(ctx, "ntt_batch: matrix rows are stored bit-reversed");
     uint32_t* tmp = nullptr;
     VG_TRY(vg_alloc(ctx, (void**)&tmp, m->h * m->w * 4));
     int32_t rc = vg_ntt_nat2nat(ctx, m->d, m->col_stride, m->d, m->col_stride, log_n, m->w, inverse != 0, nullptr, tmp, m->h);
@@ -191,7 +204,7 @@ int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_bl
     if (log_blowup != 1) VG_FAIL(ctx, "coset_lde: only log_blowup = 1 (FriConfig of basic/src/bin/valida.rs:385-390) is built");
     vgpu_dmat* o = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, in->h * 2, in->w, &o));
-    int32_t rc = vg_coset_lde(ctx, in->d, in->col_stride, in->h, in->w, shift_canonical, o->d, o->col_stride, bit_reversed != 0);
+    int32_t rc = vg_coset_lde(ctx, in->d, in->col_stride, in->h, in->w, shift_canonical, o->d, o->col_stride, bit_reversed != 0, in->bitrev_rows);
     if (rc) { vgpu_dmat_free(o); return rc; }
     *out = o;
     return 0;

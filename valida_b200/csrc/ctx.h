@@ -58,6 +58,7 @@ struct vgpu_dmat {
     uint32_t* d = nullptr;       // column-major: element (r, c) at d[c * col_stride + r], Montgomery form
     uint64_t h = 0, w = 0, col_stride = 0;
     bool owns = true;
+    bool bitrev_rows = false;    // row r of the logical matrix is stored at reverse_bits(r) (quotient-chunk output order)
 };
 
 #define VG_FAIL(ctx, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (ctx)->err = _b; return -1; } while (0)
@@ -90,7 +91,7 @@ int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t sca
 int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, int log_n, uint64_t w,
                        bool inverse, const PowTable* coset_or_null, uint32_t* tmp, uint64_t tmp_cs);
 int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64_t h, uint64_t w, uint32_t shift_canonical,
-                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed);
+                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev = false);
 // staging.cu
 int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);
 int32_t vg_download_rowmajor(vgpu_ctx* ctx, const vgpu_dmat* src, int32_t repr, uint32_t* host);

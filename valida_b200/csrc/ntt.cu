@@ -408,18 +408,22 @@ static int32_t intt_nat2bitrev_scaled(vgpu_ctx* ctx, const uint32_t* src, uint64
 
 // forward coset transform: coefficients in bit-reversed order (c[K] at bitrev_n(K)) -> evaluations in
 // bit-reversed order (E[m] at bitrev_n(m)), out of place.  odd != 0 multiplies c[K] by w_2n^K first.
+// With inverse != 0 and tab != null the same two passes compute the INVERSE transform of bit-reversed-ordered
+// evaluations (the quotient kernel's output order) into bit-reversed-ordered coefficients, coefficient K
+// scaled by tab[K] (= shift^K / n).
 static int32_t ntt_bitrev2bitrev(vgpu_ctx* ctx, const uint32_t* coef, uint64_t ccs, uint32_t* dst, uint64_t dst_cs, uint32_t* tmp, uint64_t tcs,
-                                 int log_n, uint64_t w, bool odd) {
+                                 int log_n, uint64_t w, bool odd, bool inverse = false, const PowTable* tab = nullptr) {
     const uint64_t n = 1ull << log_n;
     int lc, lr;
     split_col_row(log_n, &lc, &lr);
     PassParams p{};
-    p.inverse = 0;
+    p.inverse = inverse ? 1 : 0;
     if (lc == 0) {
         p.src = coef; p.src_cs = ccs; p.dst = dst; p.dst_cs = dst_cs;
         p.src_rs = 1; p.src_gs = n; p.dst_rs = 1; p.dst_gs = n;
         p.log_len = log_n; p.groups = 1; p.src_bitrev = 1; p.dst_natural = 0;
         if (odd) { p.pre_mode = 1; p.pre_r = 1; p.pre_g = 0; p.pre_shift = VG_LOG_NMAX - (log_n + 1); }
+        if (tab) { p.post_mode = 2; p.post_g = 0; p.post_k = 1; p.tab_lo = tab->lo; p.tab_hi = tab->hi; p.tab_base = tab->base; }
         return launch_pass(ctx, p, w);
     }
     const uint64_t n1 = 1ull << lc, n2 = 1ull << lr;
@@ -435,16 +439,21 @@ static int32_t ntt_bitrev2bitrev(vgpu_ctx* ctx, const uint32_t* coef, uint64_t c
     // column pass over rows j1 (k1' = bitrev(j1)) for each column q: -> m1 ; E[m1*n2 + m2] goes to
     // bitrev_n = bitrev(m2)*n1 + bitrev(m1) = q*n1 + raw slot: transposed store, raw order
     PassParams q{};
-    q.inverse = 0;
+    q.inverse = inverse ? 1 : 0;
     q.src = tmp; q.src_cs = tcs; q.dst = dst; q.dst_cs = dst_cs;
     q.src_rs = n2; q.src_gs = 1; q.dst_rs = 1; q.dst_gs = n1;
     q.log_len = lc; q.groups = n2; q.src_bitrev = 1; q.dst_natural = 0;
+    if (tab) {   // natural output index K = m1*n2 + m2 with m1 = k and m2 = bitrev(column position g)
+        q.g_bits = lr; q.post_mode = 2; q.post_g = 1; q.post_k = (uint32_t)n2;
+        q.tab_lo = tab->lo; q.tab_hi = tab->hi; q.tab_base = tab->base;
+    }
     return launch_pass(ctx, q, w);
 }
 
 // coset_lde_batch(mat, added_bits = 1, shift): dst (2h rows per column).
 int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64_t h, uint64_t w, uint32_t shift_canonical,
-                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed) {
+                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev) {
+    if (src_bitrev && !bit_reversed) VG_FAIL(ctx, "coset_lde: a bit-reversed-row input is only supported with bit-reversed output");
     int log_n = 0;
     while ((1ull << log_n) < h) log_n++;
     if ((1ull << log_n) != h) VG_FAIL(ctx, "coset_lde: height %llu is not a power of two", (unsigned long long)h);
@@ -465,7 +474,8 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
     for (uint64_t c0 = 0; c0 < w && rc == 0; c0 += batch) {
         uint64_t wc = w - c0 < batch ? w - c0 : batch;
         if (bit_reversed) {
-            rc = intt_nat2bitrev_scaled(ctx, src + c0 * src_cs, src_cs, coef, h, log_n, wc, tab);
+            rc = src_bitrev ? ntt_bitrev2bitrev(ctx, src + c0 * src_cs, src_cs, coef, h, tmp, h, log_n, wc, false, true, tab)
+                            : intt_nat2bitrev_scaled(ctx, src + c0 * src_cs, src_cs, coef, h, log_n, wc, tab);
             if (rc) break;
             rc = ntt_bitrev2bitrev(ctx, coef, h, dst + c0 * dst_cs, dst_cs, tmp, h, log_n, wc, false);
             if (rc) break;

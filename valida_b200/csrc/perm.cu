@@ -206,6 +206,7 @@ int32_t vg_ext_batch_inverse(vgpu_ctx* ctx, uint32_t* data, uint64_t cs, uint64_
 extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const vgpu_dmat* main, const vgpu_dmat* prep_or_null,
                                    const uint32_t challenges[15], vgpu_dmat** out_perm, uint32_t cumulative_sum_out[5]) {
     if (!chip || !main || !out_perm) VG_FAIL(ctx, "perm_trace: null argument");
+    if (main->bitrev_rows) VG_FAIL(ctx, "perm_trace: main trace rows are stored bit-reversed");
     if (main->w != chip->width) VG_FAIL(ctx, "perm_trace: main width %llu != chip width %u", (unsigned long long)main->w, chip->width);
     if (chip->preprocessed_width && (!prep_or_null || prep_or_null->w != chip->preprocessed_width || prep_or_null->h != main->h)) {
         // interactions of BasicMachine never read preprocessed columns, but the shape must still be coherent when given

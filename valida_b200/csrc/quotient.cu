@@ -4,11 +4,14 @@
 // and p3-uni-stark's decompose_and_flatten / ZerofierOnCoset for log_quotient_degree = 1.
 //
 // The reference gathers LDE rows through a bit-reversed view element by element; here one thread owns
-// the STORAGE row pair (2r, 2r+1) of the committed (bit-reversed) LDEs, i.e. the natural rows
+// one STORAGE row of the committed (bit-reversed) LDEs; lanes (2r, 2r+1) hold the natural rows
 // (j, j+h) with j = bitrev(r): x and -x.  That pair is exactly what the even/odd chunk split needs,
-// so the quotient values never touch HBM: the thread folds all constraints for both rows, divides by
-// Z_H, and writes row j of the h x 10 chunk matrix directly.  "next" rows (j+2) are another storage
-// pair, so every trace load is a coalesced 8-byte access.
+// so the quotient values never touch HBM: each lane folds all constraints of its row, divides by Z_H,
+// the pair exchanges its ext5 value with one shuffle, and the even / odd lane writes the even / odd
+// chunk limbs.  Every trace load and every chunk store is a fully coalesced 4-byte-per-lane access
+// (the chunk matrix is left in bit-reversed row order; the quotient commit's iNTT reads it that way).
+// ncu on the first version (pair per thread, natural-order scatter): 3.2x the algorithmic DRAM reads
+// and 9x the writes; see profiles/r01_summary.md.
 // alpha-folding: acc = sum_i c_i * alpha^(N-1-i) with precomputed powers — the same value as the
 // reference's Horner recurrence acc = acc*alpha + c_i, at 5 instead of 25 multiplications for the
 // base-field constraints.
@@ -69,45 +72,45 @@ __device__ __forceinline__ E5 load_e5(const uint32_t* row, uint64_t cs, uint32_t
 
 template <int CHIP>
 __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
-    const uint64_t h = 1ull << p.log_h;
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= h) return;
+    const uint64_t h = 1ull << p.log_h, H = 2 * h;
+    const uint64_t rho_raw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
+    const bool active = rho_raw < H;
+    const uint64_t rho = active ? rho_raw : (rho_raw & 1);                         // idle lanes shadow rows 0/1 (shuffles need every lane)
+    const uint32_t e = (uint32_t)(rho & 1);                                        // 0: x = +x0 (natural row j), 1: x = -x0 (natural row j + h)
+    const uint64_t r = rho >> 1;
     const uint32_t j = bb::reverse_bits((uint32_t)r, (int)p.log_h);
-    // next rows: natural (j+2) mod 2h for row j, and the partner of that for row j+h
+    // next row: natural (i + 2) mod 2h  ->  pair bitrev((j + 2) mod h), element e ^ carry
     const uint64_t t = (uint64_t)j + 2;
     const uint32_t a = (uint32_t)(t & (h - 1));
     const uint32_t swap = (uint32_t)((t >> p.log_h) & 1);
-    const uint64_t rn = bb::reverse_bits(a, (int)p.log_h);
+    const uint64_t nrow = 2 * (uint64_t)bb::reverse_bits(a, (int)p.log_h) + (e ^ swap);
     const uint32_t x0 = bb::mul(p.s, qroot_pow(p, (uint64_t)j << (VG_LOG_NMAX - p.log_h - 1)));
-    // selectors: 1/(x-1), 1/(x-glast) for x = +-x0, one shared inversion
-    uint32_t den[4] = {bb::sub(x0, bb::R1), bb::sub(x0, p.glast), bb::sub(bb::neg(x0), bb::R1), bb::sub(bb::neg(x0), p.glast)};
-    uint32_t inv[4];
+    const uint32_t x = e ? bb::neg(x0) : x0;
+    // selectors 1/(x-1), 1/(x-glast): both lanes of a pair invert the same symmetric product
+    uint32_t inv_first, inv_last;
     {
-        uint32_t p01 = bb::mul(den[0], den[1]), p23 = bb::mul(den[2], den[3]);
-        uint32_t all = bb::inv(bb::mul(p01, p23));
-        uint32_t i01 = bb::mul(all, p23), i23 = bb::mul(all, p01);
-        inv[0] = bb::mul(i01, den[1]); inv[1] = bb::mul(i01, den[0]);
-        inv[2] = bb::mul(i23, den[3]); inv[3] = bb::mul(i23, den[2]);
+        const uint32_t nx0 = bb::neg(x0);
+        const uint32_t d0 = bb::sub(x0, bb::R1), d1 = bb::sub(x0, p.glast), d2 = bb::sub(nx0, bb::R1), d3 = bb::sub(nx0, p.glast);
+        const uint32_t p01 = bb::mul(d0, d1), p23 = bb::mul(d2, d3);
+        const uint32_t all = bb::inv(bb::mul(p01, p23));
+        const uint32_t i01 = bb::mul(all, p23), i23 = bb::mul(all, p01);
+        inv_first = e ? bb::mul(i23, d3) : bb::mul(i01, d1);
+        inv_last = e ? bb::mul(i23, d2) : bb::mul(i01, d0);
     }
     const DevChip& chip = *p.chip;
     const uint32_t k = chip.n_interactions;
-    E5 q[2];
-#pragma unroll 1
-    for (int e = 0; e < 2; e++) {
-        const uint64_t srow = 2 * r + e, nrow = 2 * rn + (e ^ swap);
-        const uint32_t parity = (e == 0) ? (j & 1) : (uint32_t)((j + h) & 1);
-        const uint32_t x = e ? bb::neg(x0) : x0;
-        const uint32_t zh = p.zh[parity];
-        DevBuilder b;
-        b.lrow = p.main + srow; b.nrow = p.main + nrow; b.cs = p.mcs;
-        b.first = F{bb::mul(zh, inv[2 * e])};
-        b.last = F{bb::mul(zh, inv[2 * e + 1])};
-        b.trans = F{bb::sub(x, p.glast)};
-        b.apow = p.apow; b.idx = 0; b.acc = bb::e5_zero();
-        air::eval_chip<CHIP>(b);
-        // eval_permutation_constraints
-        const uint32_t* ql = p.perm + srow; const uint32_t* qn = p.perm + nrow;
-        const uint32_t* pl = p.prep ? p.prep + srow : nullptr; const uint32_t* pn = p.prep ? p.prep + nrow : nullptr;
+    const uint32_t parity = (uint32_t)(((uint64_t)j + (e ? h : 0)) & 1);
+    const uint32_t zh = p.zh[parity];
+    DevBuilder b;
+    b.lrow = p.main + rho; b.nrow = p.main + nrow; b.cs = p.mcs;
+    b.first = F{bb::mul(zh, inv_first)};
+    b.last = F{bb::mul(zh, inv_last)};
+    b.trans = F{bb::sub(x, p.glast)};
+    b.apow = p.apow; b.idx = 0; b.acc = bb::e5_zero();
+    air::eval_chip<CHIP>(b);
+    {   // eval_permutation_constraints
+        const uint32_t* ql = p.perm + rho; const uint32_t* qn = p.perm + nrow;
+        const uint32_t* pl = p.prep ? p.prep + rho : nullptr; const uint32_t* pn = p.prep ? p.prep + nrow : nullptr;
         const E5 phi_local = load_e5(ql, p.qcs, k), phi_next = load_e5(qn, p.qcs, k);
         E5 rhs = bb::e5_zero(), phi0 = bb::e5_zero();
         for (uint32_t m = 0; m < k; m++) {
@@ -124,14 +127,25 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
         b.z_ext(bb::e5_mul_base(bb::e5_sub(bb::e5_sub(phi_next, phi_local), rhs), b.trans.v));
         b.z_ext(bb::e5_mul_base(bb::e5_sub(phi_local, phi0), b.first.v));
         b.z_ext(bb::e5_mul_base(bb::e5_sub(phi_local, p.cumsum), b.last.v));
-        q[e] = bb::e5_mul_base(b.acc, p.zinv[parity]);
     }
-    // decompose_and_flatten: even = (q(x) + q(-x))/2, odd = (q(x) - q(-x)) / (2 s g^j)
-    const uint32_t ginv_j = qroot_pow(p, (1ull << VG_LOG_NMAX) - ((uint64_t)j << (VG_LOG_NMAX - p.log_h - 1)));
-    const E5 even = bb::e5_mul_base(bb::e5_add(q[0], q[1]), p.half);
-    const E5 odd = bb::e5_mul_base(bb::e5_sub(q[0], q[1]), bb::mul(p.odd_scale, ginv_j));
+    const E5 q = bb::e5_mul_base(b.acc, p.zinv[parity]);
+    // decompose_and_flatten across the lane pair: even = (q(x) + q(-x))/2, odd = (q(x) - q(-x)) / (2 s g^j)
+    E5 other;
 #pragma unroll
-    for (int l = 0; l < 5; l++) { p.out[(uint64_t)l * p.ocs + j] = even.c[l]; p.out[(uint64_t)(5 + l) * p.ocs + j] = odd.c[l]; }
+    for (int l = 0; l < 5; l++) other.c[l] = __shfl_xor_sync(0xffffffffu, q.c[l], 1);
+    E5 outv;
+    if (e == 0) {
+        outv = bb::e5_mul_base(bb::e5_add(q, other), p.half);
+    } else {
+        const uint32_t ginv_j = qroot_pow(p, (1ull << VG_LOG_NMAX) - ((uint64_t)j << (VG_LOG_NMAX - p.log_h - 1)));
+        outv = bb::e5_mul_base(bb::e5_sub(other, q), bb::mul(p.odd_scale, ginv_j));
+    }
+    if (active) {
+        // chunk row j is written at row r = bitrev(j): the chunk matrix leaves this kernel in bit-reversed row order
+        // (coalesced), which the commit's inverse transform consumes directly
+#pragma unroll
+        for (int l = 0; l < 5; l++) p.out[(uint64_t)(5 * e + l) * p.ocs + r] = outv.c[l];
+    }
 }
 
 struct CountBuilder {
@@ -144,7 +158,7 @@ struct CountBuilder {
 template <int CHIP> uint32_t count_base() { CountBuilder c; air::eval_chip<CHIP>(c); return c.n; }
 
 template <int CHIP> void launch(const QParams& p, uint64_t h, cudaStream_t st) {
-    quotient_kernel<CHIP><<<(unsigned)((h + 127) / 128), 128, 0, st>>>(p);
+    quotient_kernel<CHIP><<<(unsigned)((2 * h + 127) / 128), 128, 0, st>>>(p);
 }
 
 }  // namespace
@@ -177,6 +191,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     VG_CUDA(ctx, cudaMemcpyAsync(d_apow, apow.data(), N * sizeof(E5), cudaMemcpyHostToDevice, ctx->stream));
     vgpu_dmat* out = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, h, 10, &out));
+    out->bitrev_rows = true;
     QParams p{};
     p.chip = dchip;
     p.main = main_lde->d; p.mcs = main_lde->col_stride;
