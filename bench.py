@@ -185,8 +185,12 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) torch stream: its handle is non-null, so the library enqueues on it and
+    # torch.cuda.Event timings on this stream see the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = vb.Context(local_rank, stream=stream.cuda_stream)
+    assert stream.cuda_stream != 0
     rc = np.zeros(480, dtype=np.uint32)
     # documented stand-in for the caller's Poseidon RNG: SplitMix64("valida"), 31-bit rejection sampling
     state, k, M = 0x76616C696461, 0, (1 << 64) - 1

@@ -145,6 +145,23 @@ void vgpu_free_bytes(uint8_t* p);
 /* Per-phase device time of the last vgpu_prove* call: names[i] (static strings) / ms[i]; returns the count. */
 uint32_t vgpu_last_prove_phases(const vgpu_ctx* ctx, const char** names, float* ms, uint32_t cap);
 
+/* ---- Machine::verify (machine/src/machine.rs:26-31; body derive/src/lib.rs:492-650) ------------------
+ * Checks a CBOR MachineProof (this library's or the reference's) against the preprocessed traces: the
+ * preprocessed commitment is recomputed on the device, the transcript replayed, the FRI opening proof and
+ * every chip's constraints at zeta checked on the host (machine/src/verify.rs:11-107), and the cumulative
+ * sums must cancel.  Returns 0 when the check RAN; *verdict then holds VGPU_ACCEPT or the first failed
+ * check.  A non-zero return is an API / device error (vgpu_ctx_last_error). */
+#define VGPU_ACCEPT 0
+#define VGPU_REJECT_MALFORMED (-1)        /* not the CBOR shape of MachineProof, or a field element >= p */
+#define VGPU_REJECT_SHAPE (-2)            /* counts / widths / degrees inconsistent with BasicMachine */
+#define VGPU_REJECT_POW (-3)              /* proof-of-work witness */
+#define VGPU_REJECT_INPUT_MERKLE (-4)     /* a query's opening of the main / permutation / quotient commitment */
+#define VGPU_REJECT_FRI_MERKLE (-5)       /* a query's opening of a FRI commit-phase layer */
+#define VGPU_REJECT_FRI_FINAL (-6)        /* folded value != final_poly */
+#define VGPU_REJECT_CUMULATIVE_SUM (-7)   /* LogUp sums over all chips do not cancel (derive/src/lib.rs:640-647) */
+#define VGPU_REJECT_CONSTRAINTS_CHIP0 (-100) /* chip i's constraints at zeta: -100 - i (OodEvaluationMismatch) */
+int32_t vgpu_verify(vgpu_ctx* ctx, const uint8_t* proof, uint64_t proof_len, const vgpu_matrix prep[2], int32_t repr, int32_t* verdict);
+
 /* ---- host witness generation (Chip::generate_trace x14; machine/src/chip.rs:22) -------------------
  * program_words: n_instr x 6 int32 (opcode, a, b, c, d, e) as ProgramROM<i32> (machine/src/program.rs:165-185). */
 int32_t vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,

@@ -7,7 +7,7 @@ import valida_b200 as vb
 import oracle_binding
 log_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 ctx = vb.Context(0, stream=stream.cuda_stream)
 cfg = vb.StarkConfig(ctx, oracle_binding.Oracle().rc480)
 n = ((1 << log_rows) - 17) // 7

@@ -15,6 +15,8 @@ from .api import (  # noqa: F401
     VgpuError,
     StarkConfig,
     prove_machine,
+    verify_machine,
+    VerificationError,
     last_prove_phases,
     fib_program,
     generate_permutation_trace,

@@ -62,6 +62,7 @@ def _load():
         "vgpu_challenger_reset": (C.c_int32, [vp]),
         "vgpu_challenger_observe": (C.c_int32, [vp, u32p, C.c_uint32]),
         "vgpu_challenger_sample_ext": (C.c_int32, [vp, u32p]),
+        "vgpu_verify": (C.c_int32, [vp, C.c_char_p, u64, C.POINTER(_Matrix), C.c_int32, C.POINTER(C.c_int32)]),
         "vgpu_prove": (C.c_int32, [vp, C.POINTER(_Matrix), C.POINTER(_Matrix), C.c_int32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgpu_prove_device": (C.c_int32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgpu_free_bytes": (None, [C.POINTER(C.c_uint8)]),
@@ -327,6 +328,31 @@ def prove_machine(config, traces, device_resident=None):
     proof = C.string_at(out, n.value)
     lib().vgpu_free_bytes(out)
     return proof
+
+
+class VerificationError(Exception):
+    """Machine::verify rejected the proof; .verdict is the VGPU_REJECT_* code of include/valida_b200.h."""
+
+    NAMES = {-1: "malformed proof", -2: "shape mismatch", -3: "invalid proof-of-work witness", -4: "input Merkle opening",
+             -5: "FRI Merkle opening", -6: "FRI final polynomial mismatch", -7: "non-zero cumulative sum"}
+
+    def __init__(self, verdict):
+        self.verdict = verdict
+        what = self.NAMES.get(verdict) or ("out-of-domain evaluation mismatch on chip %d" % (-100 - verdict))
+        super().__init__("proof rejected: %s (verdict %d)" % (what, verdict))
+
+
+def verify_machine(config, proof, preprocessed):
+    """Machine::verify (machine/src/machine.rs:26-31): raises VerificationError unless the proof is accepted.
+
+    proof: CBOR bytes of MachineProof; preprocessed: the two preprocessed traces (program, range), row-major canonical."""
+    ctx = config.ctx
+    keep = [_as_u32(m) for m in preprocessed]
+    b = (_Matrix * 2)(*[_mat(m) for m in keep])
+    verdict = C.c_int32(-1)
+    ctx.check(lib().vgpu_verify(ctx._h, bytes(proof), len(proof), b, REPR_CANONICAL, C.byref(verdict)))
+    if verdict.value != 0:
+        raise VerificationError(verdict.value)
 
 
 def last_prove_phases(ctx):

@@ -42,6 +42,7 @@ struct QParams {
 };
 
 struct DevBuilder {
+    using V = air::F;
     const uint32_t* lrow; const uint32_t* nrow; uint64_t cs;   // pointers already offset to the row
     F first, last, trans;
     const E5* apow; uint32_t idx; E5 acc;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
 }
 
 struct CountBuilder {
+    using V = air::F;
     F first{0}, last{0}, trans{0};
     uint32_t n = 0;
     BB_HD F L(int) const { return F{0}; }
