@@ -1,15 +1,14 @@
 """Uninstrumented + instrumented timing of one workload (development aid): python profiles/quick_bench.py <log_rows> <steps>"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import torch, numpy as np
 import valida_b200 as vb
-import oracle_binding
 log_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 ctx = vb.Context(0, stream=stream.cuda_stream)
-cfg = vb.StarkConfig(ctx, oracle_binding.Oracle().rc480)
+cfg = vb.StarkConfig(ctx, np.random.default_rng(7).integers(0, vb.BABYBEAR_P, 480, dtype=np.uint32))
 n = ((1 << log_rows) - 17) // 7
 t = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
 dm = [ctx.upload(m) for m in t.main]; dp = [ctx.upload(m) for m in t.preprocessed]

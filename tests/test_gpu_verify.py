@@ -80,20 +80,18 @@ def test_rejects_tampering_like_the_oracle(fib25, oracle, what):
     assert product_verdict(vb, cfg, bad, t.preprocessed) == expected(want)
 
 
-def test_constraint_failure_is_attributed_to_the_chip(fib25, oracle):
-    """Proof of a wrong witness that still passes FRI: only the out-of-domain identity of the CPU chip fails."""
+def test_altered_witness_gets_the_oracle_verdict(fib25, oracle):
+    """A witness edited after trace generation: whatever the prover and the oracle verifier make of it (the reference's
+    CPU AIR does not tie the opcode flags to the opcode, so clearing one still proves), this verifier says the same."""
     vb, cfg, t, _ = fib25
     bad = vb.run_program(vb.fib_program(25), initial_fp=0x1000)
-    # opcode flag columns are degree-consistent whatever they hold: swap an is_imm32 flag off on one row
     row = next(i for i in range(bad.main[0].shape[0]) if bad.main[0][i, 22] == 1)
     bad.main[0][row, 22] = 0
     try:
         p = vb.prove_machine(cfg, bad)
     except vb.VgpuError:
         pytest.skip("prover refused the witness")
-    want = oracle.verify(p, bad.preprocessed)
-    got = product_verdict(vb, cfg, p, bad.preprocessed)
-    assert want != 0 and got == expected(want)
+    assert product_verdict(vb, cfg, p, bad.preprocessed) == expected(oracle.verify(p, bad.preprocessed))
 
 
 def test_malformed_bytes(fib25):
