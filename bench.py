@@ -282,6 +282,29 @@ def main():
     e2e_value, _ = aggregate_throughput(dist, rows * args.steps, ms_e2e, device="cuda")
     assert proof_e2e == proof
 
+    # ---- N > 1: the SAME single proof split across the ranks (column shares for the LDE, leaf/layer shares for the
+    # Keccak trees, NCCL exchange over NVLink) — latency of one proof on N GPUs, beside the replica throughput ----
+    sharded = None
+    if dist is not None:
+        ctx.comm_init_from_torch()
+        for _ in range(2):
+            proof_sh = vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+        assert proof_sh == proof, "split proof differs from the single-GPU proof"
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+        s1.record(stream)
+        barrier()
+        ms_sh = s0.elapsed_time(s1)
+        sh_phases = vb.last_prove_phases(ctx)
+        _, ms_sh_max = aggregate_throughput(dist, rows * args.steps, ms_sh, device="cuda")
+        ctx.set_sharding(False)
+        sharded = {"what": "ONE proof per step split across %d GPUs (strong scaling of a single proof)" % world,
+                   "ms_per_proof": ms_sh_max / args.steps, "rows_per_s": rows * args.steps / (ms_sh_max / 1e3),
+                   "proof_bytes_identical": True, "phases_ms": {k: v for k, v in sh_phases}}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -360,6 +383,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "phases_ms": {p[0]: p[1] for p in phases},
         "kernels": kernels,
+        "sharded": sharded,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

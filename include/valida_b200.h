@@ -145,6 +145,22 @@ void vgpu_free_bytes(uint8_t* p);
 /* Per-phase device time of the last vgpu_prove* call: names[i] (static strings) / ms[i]; returns the count. */
 uint32_t vgpu_last_prove_phases(const vgpu_ctx* ctx, const char** names, float* ms, uint32_t cap);
 
+/* ---- multi-GPU: one rank (process) per GPU of one box, NCCL over NVLink -----------------
+ * After vgpu_comm_init every rank of the communicator must make the SAME sequence of library calls with
+ * the SAME (replicated) inputs.  With sharding on (the default after init), vgpu_commit_batches* and the
+ * FRI commit phase inside vgpu_prove* split their work: rank r transforms a contiguous share of every
+ * matrix's columns (coset LDE), the shares are exchanged (broadcast per share, one NCCL group), each rank
+ * hashes a contiguous 1/nranks range of the leaves and compresses the tree layers above that range, and one
+ * grouped all-gather leaves every rank with all digest layers; the top log2(nranks) layers are computed
+ * by every rank.  Results (roots, prover data, proof bytes) are identical on all ranks and identical to
+ * the single-GPU ones.  nranks must be a power of two. */
+#define VGPU_COMM_ID_BYTES 128
+int32_t vgpu_comm_unique_id(uint8_t out[VGPU_COMM_ID_BYTES]);                 /* rank 0 creates, the caller distributes */
+int32_t vgpu_comm_init(vgpu_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t unique_id[VGPU_COMM_ID_BYTES]);
+int32_t vgpu_comm_set_sharding(vgpu_ctx* ctx, int32_t on);                    /* 0: behave as a lone GPU (independent replicas) */
+void vgpu_shard_range(uint64_t total, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* end);   /* the split used for columns */
+void vgpu_tree_share(uint64_t len, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* count, int32_t* split); /* ... for tree layers */
+
 /* ---- Machine::verify (machine/src/machine.rs:26-31; body derive/src/lib.rs:492-650) ------------------
  * Checks a CBOR MachineProof (this library's or the reference's) against the preprocessed traces: the
  * preprocessed commitment is recomputed on the device, the transcript replayed, the FRI opening proof and

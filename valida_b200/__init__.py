@@ -24,4 +24,7 @@ from .api import (  # noqa: F401
     lib,
     lib_path,
     run_program,
+    comm_unique_id,
+    shard_range,
+    tree_share,
 )

@@ -62,6 +62,11 @@ def _load():
         "vgpu_challenger_reset": (C.c_int32, [vp]),
         "vgpu_challenger_observe": (C.c_int32, [vp, u32p, C.c_uint32]),
         "vgpu_challenger_sample_ext": (C.c_int32, [vp, u32p]),
+        "vgpu_comm_unique_id": (C.c_int32, [C.c_char_p]),
+        "vgpu_comm_init": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_char_p]),
+        "vgpu_comm_set_sharding": (C.c_int32, [vp, C.c_int32]),
+        "vgpu_shard_range": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
+        "vgpu_tree_share": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_int32)]),
         "vgpu_verify": (C.c_int32, [vp, C.c_char_p, u64, C.POINTER(_Matrix), C.c_int32, C.POINTER(C.c_int32)]),
         "vgpu_prove": (C.c_int32, [vp, C.POINTER(_Matrix), C.POINTER(_Matrix), C.c_int32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgpu_prove_device": (C.c_int32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
@@ -132,6 +137,24 @@ class Context:
         names = (C.c_char_p * 16)(); ln = (C.c_uint32 * 16)(); ms = (C.c_float * 16)(); by = (C.c_double * 16)()
         n = lib().vgpu_ctx_kernel_stats(self._h, names, ln, ms, by, 16)
         return [(names[i].decode(), int(ln[i]), float(ms[i]), float(by[i])) for i in range(n)]
+
+    # ---- multi-GPU: one rank per GPU (include/valida_b200.h, "multi-GPU") ----
+    def comm_init(self, rank, world_size, unique_id):
+        """Join the NCCL communicator named by unique_id (comm_unique_id() of rank 0, distributed by the caller)."""
+        self.check(lib().vgpu_comm_init(self._h, world_size, rank, bytes(unique_id)))
+        self.rank, self.world_size = rank, world_size
+
+    def comm_init_from_torch(self):
+        """Convenience for torchrun ranks: rank 0 creates the id, torch.distributed carries it to the others."""
+        import torch.distributed as dist
+
+        ids = [comm_unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.comm_init(dist.get_rank(), dist.get_world_size(), ids[0])
+
+    def set_sharding(self, on):
+        """False: this rank works alone (independent replicas); True: commits are split across the ranks."""
+        self.check(lib().vgpu_comm_set_sharding(self._h, 1 if on else 0))
 
     def upload(self, row_major, repr=REPR_CANONICAL):
         """RowMajorMatrix<Val> (numpy h x w uint32) -> DeviceMatrix."""
@@ -328,6 +351,30 @@ def prove_machine(config, traces, device_resident=None):
     proof = C.string_at(out, n.value)
     lib().vgpu_free_bytes(out)
     return proof
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if lib().vgpu_comm_unique_id(buf) != 0:
+        raise VgpuError("NCCL is not available (libnccl.so.2 could not be loaded)")
+    return buf.raw
+
+
+def shard_range(total, world_size, rank):
+    """Contiguous balanced split used for the column shares: (begin, end)."""
+    b, e = C.c_uint64(), C.c_uint64()
+    lib().vgpu_shard_range(total, world_size, rank, C.byref(b), C.byref(e))
+    return int(b.value), int(e.value)
+
+
+def tree_share(length, world_size, rank):
+    """(begin, count, split) — the part of a tree layer a rank derives itself when commits are split."""
+    b, c, sp = C.c_uint64(), C.c_uint64(), C.c_int32()
+    lib().vgpu_tree_share(length, world_size, rank, C.byref(b), C.byref(c), C.byref(sp))
+    return int(b.value), int(c.value), bool(sp.value)
 
 
 class VerificationError(Exception):

@@ -119,6 +119,7 @@ int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
 void vgpu_ctx_destroy(vgpu_ctx* ctx) {
     if (!ctx) return;
     vg_host_state_free(ctx);
+    vg_comm_free(ctx);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         vg_free(ctx, ctx->root_table.lo); vg_free(ctx, ctx->root_table.hi);
@@ -227,13 +228,37 @@ int32_t vgpu_commit_batches(vgpu_ctx* ctx, const vgpu_dmat* const* mats, uint32_
     if (!pd) VG_FAIL(ctx, "out of host memory");
     pd->ctx = ctx;
     int32_t rc = 0;
+    const bool sharded = vg_sharded(ctx);
     for (uint32_t i = 0; i < n && rc == 0; i++) {
         // TwoAdicFriPcs::commit_shifted_batches: shift = generator / coset_shift_i; LDE; bit-reverse rows
         uint32_t cs = coset_shifts_or_null ? coset_shifts_or_null[i] : 1;
         uint32_t shift = bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
         vgpu_dmat* lde = nullptr;
-        rc = vgpu_coset_lde_batch(ctx, mats[i], 1, shift, 1, &lde);
+        if (!sharded) {
+            rc = vgpu_coset_lde_batch(ctx, mats[i], 1, shift, 1, &lde);
+        } else {
+            // this rank extends only its share of the columns; the other shares arrive in the exchange below
+            uint64_t c0, c1;
+            vg_shard_range(mats[i]->w, ctx->comm_size, ctx->comm_rank, &c0, &c1);
+            rc = vg_dmat_alloc(ctx, mats[i]->h * 2, mats[i]->w, &lde);
+            if (rc == 0 && c1 > c0)
+                rc = vg_coset_lde(ctx, mats[i]->d + c0 * mats[i]->col_stride, mats[i]->col_stride, mats[i]->h, c1 - c0, shift,
+                                  lde->d + c0 * lde->col_stride, lde->col_stride, true, mats[i]->bitrev_rows);
+            if (rc && lde) { vgpu_dmat_free(lde); lde = nullptr; }
+        }
         if (rc == 0) pd->ldes.push_back(lde);
+    }
+    if (rc == 0 && sharded) {
+        // exchange of the column shares: one NCCL group, a broadcast per (matrix, owner) — shares are contiguous
+        // runs of whole columns in the column-major LDE
+        rc = vg_comm_group_begin(ctx);
+        for (uint32_t i = 0; i < n && rc == 0; i++)
+            for (int r = 0; r < ctx->comm_size && rc == 0; r++) {
+                uint64_t c0, c1;
+                vg_shard_range(pd->ldes[i]->w, ctx->comm_size, r, &c0, &c1);
+                rc = vg_comm_bcast(ctx, pd->ldes[i]->d + c0 * pd->ldes[i]->col_stride, (c1 - c0) * pd->ldes[i]->col_stride, r);
+            }
+        if (rc == 0) rc = vg_comm_group_end(ctx);
     }
     if (rc == 0) rc = vg_merkle_build(ctx, pd);
     if (rc) { vgpu_prover_data_free(pd); return rc; }

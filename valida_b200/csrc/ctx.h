@@ -48,6 +48,10 @@ struct vgpu_ctx {
     std::multimap<size_t, void*> free_bufs;
     std::map<void*, size_t> live_bufs;
     size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
+    // multi-GPU (host/comm.cc): one rank per GPU, NCCL communicator bound to ctx->stream
+    void* nccl = nullptr;                                        // ncclComm_t
+    int comm_rank = 0, comm_size = 1;
+    bool sharding = false;                                       // commit / FRI-commit work split across ranks
     bool ktiming = false;
     std::vector<KTimer> ktimers;
     std::vector<cudaEvent_t> event_pool;
@@ -86,6 +90,16 @@ int32_t vg_alloc(vgpu_ctx* ctx, void** p, size_t bytes);
 void vg_free(vgpu_ctx* ctx, void* p);
 int32_t vg_dmat_alloc(vgpu_ctx* ctx, uint64_t h, uint64_t w, vgpu_dmat** out);
 int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t scale_canonical, uint64_t max_exp, const PowTable** out);
+
+// host/comm.cc — every rank calls these in the same order with the same sizes
+inline bool vg_sharded(const vgpu_ctx* ctx) { return ctx->sharding && ctx->comm_size > 1; }
+void vg_shard_range(uint64_t total, int nranks, int rank, uint64_t* begin, uint64_t* end);   // contiguous, balanced
+int32_t vg_comm_group_begin(vgpu_ctx* ctx);
+int32_t vg_comm_group_end(vgpu_ctx* ctx);
+// buf holds comm_size consecutive blocks of `words_per_rank` u32; this rank's block is already filled
+int32_t vg_comm_allgather_inplace(vgpu_ctx* ctx, uint32_t* buf, uint64_t words_per_rank);
+int32_t vg_comm_bcast(vgpu_ctx* ctx, uint32_t* buf, uint64_t words, int root);
+void vg_comm_free(vgpu_ctx* ctx);
 
 // ntt.cu
 int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, int log_n, uint64_t w,

@@ -47,9 +47,11 @@ __device__ __forceinline__ uint32_t wrap_mod_p(uint32_t w) {   // F::from_wrappe
 }
 
 // colptr[i] = device pointer to column i of the concatenated row (all matrices of this height).
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const uint32_t* const* __restrict__ colptr, uint32_t nwords, uint64_t nrows, uint32_t* __restrict__ digests) {
+// rows [row0, row0 + nrows) of the layer (a rank's share when the tree is split across GPUs)
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const uint32_t* const* __restrict__ colptr, uint32_t nwords, uint64_t row0, uint64_t nrows, uint32_t* __restrict__ digests) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
+    r += row0;
     uint32_t d[8];
     keccak256_words(nwords, [&](uint32_t i) { return bb::from_monty(__ldg(colptr[i] + r)); }, d);
     uint4* o = reinterpret_cast<uint4*>(digests + r * 8);
@@ -65,9 +67,11 @@ __device__ __forceinline__ void compress_pair(const uint32_t l[8], const uint32_
 }
 
 // next[i] = compress(prev[2i], prev[2i+1]) ; if inject != null: next[i] = compress(next[i], inject[i])
-__global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ inject, uint64_t n_next, uint32_t* __restrict__ next) {
+// parents [i0, i0 + n_next) of the layer
+__global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ inject, uint64_t i0, uint64_t n_next, uint32_t* __restrict__ next) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_next) return;
+    i += i0;
     uint32_t l[8], r[8], o[8];
     const uint4* p = reinterpret_cast<const uint4*>(prev + i * 16);
     uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __r
     w[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint64_t nrows, uint32_t* digests) {
+int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint64_t row0, uint64_t nrows, uint32_t* digests) {
     std::vector<const uint32_t*> cols;
     for (auto* m : mats) for (uint64_t c = 0; c < m->w; c++) cols.push_back(m->d + c * m->col_stride);
     const uint32_t** dcols = nullptr;
@@ -98,7 +102,7 @@ int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint
     // stages synchronously, so it is safe to let `cols` go once the call returns.
     {
         KScope ks(ctx, KC_LEAF_HASH, (double)nrows * (4.0 * cols.size() + 32.0));
-        leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), nrows, digests);
+        leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), row0, nrows, digests);
     }
     VG_LAUNCH_CHECK(ctx);
     vg_free(ctx, dcols);
@@ -107,9 +111,10 @@ int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint
 
 // FRI commit-phase leaf: the pair (v[2i], v[2i+1]) of ext5 values flattened to 10 base words
 // (ExtensionMmcs over a width-2 matrix); v is limb-major: limb l of element e at v[l * cs + e].
-__global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __restrict__ v, uint64_t cs, uint64_t npairs, uint32_t* __restrict__ digests) {
+__global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __restrict__ v, uint64_t cs, uint64_t i0, uint64_t npairs, uint32_t* __restrict__ digests) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
+    i += i0;
     uint32_t w[10];
 #pragma unroll
     for (int l = 0; l < 5; l++) {
@@ -125,29 +130,56 @@ __global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __re
 
 }  // namespace
 
+// Tree layers split across the ranks of the communicator: a layer of `len` nodes with len >= comm_size is cut into
+// comm_size contiguous shares; a rank derives its share of every such layer from its own share of the layer below
+// (parents [k*len/G, (k+1)*len/G) need exactly children [k*2len/G, (k+1)*2len/G)), so no exchange is needed on the
+// way up.  One grouped all-gather then completes every layer on every rank, and the layers shorter than comm_size
+// are computed by all ranks.  Unsplit (single GPU / sharding off): share = the whole layer.
+struct Share { uint64_t begin, count; bool split; };
+static Share share_of(const vgpu_ctx* ctx, uint64_t len) {
+    Share s; int32_t split = 0;
+    vgpu_tree_share(len, vg_sharded(ctx) ? ctx->comm_size : 1, ctx->comm_rank, &s.begin, &s.count, &split);
+    s.split = split != 0;
+    return s;
+}
+// complete the split layers [first, last) of a tree whose layer i starts at layer_ptr[i] and has layer_len[i] nodes
+static int32_t gather_split_layers(vgpu_ctx* ctx, const std::vector<uint32_t*>& layer_ptr, const std::vector<uint64_t>& layer_len, size_t first, size_t last) {
+    if (first >= last) return 0;
+    VG_TRY(vg_comm_group_begin(ctx));
+    for (size_t i = first; i < last; i++) VG_TRY(vg_comm_allgather_inplace(ctx, layer_ptr[i], layer_len[i] / (uint64_t)ctx->comm_size * 8));
+    return vg_comm_group_end(ctx);
+}
+
 // Single-matrix tree over ext5 pairs (p3-fri commit phase): digests = [leaf layer | ... | root].
 int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint64_t npairs, uint32_t* digests,
                             std::vector<uint32_t*>* layer_ptr, std::vector<uint64_t>* layer_len, uint32_t root_out[8]) {
+    Share sh = share_of(ctx, npairs);
     {
-        KScope ks(ctx, KC_FRI_LEAF, (double)npairs * 72.0);
-        fri_leaf_hash_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(v, cs, npairs, digests);
+        KScope ks(ctx, KC_FRI_LEAF, (double)sh.count * 72.0);
+        fri_leaf_hash_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, ctx->stream>>>(v, cs, sh.begin, sh.count, digests);
     }
     VG_LAUNCH_CHECK(ctx);
     uint32_t* layer = digests;
     uint64_t len = npairs;
     layer_ptr->clear(); layer_len->clear();
     layer_ptr->push_back(layer); layer_len->push_back(len);
+    size_t n_split = sh.split ? 1 : 0;
+    bool gathered = !sh.split;
     while (len > 1) {
         uint64_t next_len = len / 2;
         uint32_t* next = layer + len * 8;
+        sh = share_of(ctx, next_len);
+        if (!sh.split && !gathered) { VG_TRY(gather_split_layers(ctx, *layer_ptr, *layer_len, 0, n_split)); gathered = true; }
         {
-            KScope ks(ctx, KC_COMPRESS, (double)next_len * 96.0);
-            compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, nullptr, next_len, next);
+            KScope ks(ctx, KC_COMPRESS, (double)sh.count * 96.0);
+            compress_layer_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, ctx->stream>>>(layer, nullptr, sh.begin, sh.count, next);
         }
         VG_LAUNCH_CHECK(ctx);
         layer_ptr->push_back(next); layer_len->push_back(next_len);
+        if (sh.split) n_split++;
         layer = next; len = next_len;
     }
+    if (!gathered) VG_TRY(gather_split_layers(ctx, *layer_ptr, *layer_len, 0, n_split));
     VG_CUDA(ctx, cudaMemcpyAsync(root_out, layer, 32, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -171,28 +203,35 @@ int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd) {
     uint32_t* layer = pd->digests;
     pd->layer_ptr.clear(); pd->layer_len.clear();
     pd->layer_ptr.push_back(layer); pd->layer_len.push_back(max_h);
-    VG_TRY(hash_rows(ctx, group, max_h, layer));
+    Share sh = share_of(ctx, max_h);
+    VG_TRY(hash_rows(ctx, group, sh.begin, sh.count, layer));
+    size_t n_split = sh.split ? 1 : 0;
+    bool gathered = !sh.split;
     uint32_t* inject_buf = nullptr;
     uint64_t len = max_h;
     while (len > 1) {
         uint64_t next_len = len / 2;
+        sh = share_of(ctx, next_len);
+        if (!sh.split && !gathered) { VG_TRY(gather_split_layers(ctx, pd->layer_ptr, pd->layer_len, 0, n_split)); gathered = true; }
         group.clear();
         while (pos < n && pd->ldes[order[pos]]->h == next_len) group.push_back(pd->ldes[order[pos++]]);
         const uint32_t* inj = nullptr;
         if (!group.empty()) {
             if (!inject_buf) VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (max_h / 2) * 32));
-            VG_TRY(hash_rows(ctx, group, next_len, inject_buf));
+            VG_TRY(hash_rows(ctx, group, sh.begin, sh.count, inject_buf));
             inj = inject_buf;
         }
         uint32_t* next = layer + len * 8;
         {
-            KScope ks(ctx, KC_COMPRESS, (double)next_len * (inj ? 128.0 : 96.0));
-            compress_layer_kernel<<<(unsigned)((next_len + 127) / 128), 128, 0, ctx->stream>>>(layer, inj, next_len, next);
+            KScope ks(ctx, KC_COMPRESS, (double)sh.count * (inj ? 128.0 : 96.0));
+            compress_layer_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, ctx->stream>>>(layer, inj, sh.begin, sh.count, next);
         }
         VG_LAUNCH_CHECK(ctx);
         pd->layer_ptr.push_back(next); pd->layer_len.push_back(next_len);
+        if (sh.split) n_split++;
         layer = next; len = next_len;
     }
+    if (!gathered) VG_TRY(gather_split_layers(ctx, pd->layer_ptr, pd->layer_len, 0, n_split));
     if (inject_buf) vg_free(ctx, inject_buf);
     if (pos != n) VG_FAIL(ctx, "commit: a matrix height does not match any tree layer");
     VG_CUDA(ctx, cudaMemcpyAsync(pd->root, layer, 32, cudaMemcpyDeviceToHost, ctx->stream));
