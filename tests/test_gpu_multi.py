@@ -44,7 +44,7 @@ def _worker(rank, world, port, out):
     res["root_equal"] = bool(np.array_equal(root_single, root_split))
     res["ldes_equal"] = all(np.array_equal(m.download(), ref) for m, ref in zip(pcs.get_ldes(pd), ldes_single))
     pd.free()
-    res["root_oracle"] = bool(np.array_equal(root_split, orc.commit_batches(mats)[0]))
+    res["root_oracle"] = bool(np.array_equal(root_split, orc.commit_batches(mats)))
     proof_split = vb.prove_machine(cfg, t)
     res["proof_equal"] = proof_split == proof_single
     res["verifies"] = orc.verify(proof_split, t.preprocessed) == 0
