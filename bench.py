@@ -165,6 +165,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: NCCL's own version / debug lines (printed to stdout when NCCL_DEBUG is set
+    # in the environment) go to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     if args.impl == "reference":
         run_reference(args, rank)

@@ -111,3 +111,20 @@ def test_ntt_linearity_and_roundtrip_large(ctx):
     assert np.array_equal(dft.idft_batch(da).download(), a)
     # first output row of a DFT is the column sum
     assert np.array_equal(fa[0], (a.astype(np.uint64).sum(axis=0) % P).astype(np.uint32))
+
+
+@pytest.mark.parametrize("w", [1, 51, 64])
+def test_ntt_config2_full_size_vs_oracle(ctx, oracle, w):
+    """BASELINE config 2 at full size (2^20 rows; w = 64 and the w = 1 / w = 51 variants of SURVEY 8(d)): the forward
+    transform equals the oracle's on every word, and the inverse returns the input."""
+    import valida_b200 as vb
+
+    h = 1 << 20
+    r = np.arange(h, dtype=np.uint64)[:, None]
+    c = np.arange(w, dtype=np.uint64)[None, :]
+    x = ((r * 64 + c) * 0x9E3779B1 % P).astype(np.uint32)
+    dft = vb.Radix2Dft(ctx)
+    d = ctx.upload(x)
+    got = dft.dft_batch(d).download()
+    assert np.array_equal(got, oracle.dft(x))
+    assert np.array_equal(dft.idft_batch(d).download(), x)
