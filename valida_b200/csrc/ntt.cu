@@ -20,6 +20,7 @@
 //  * twiddles: a two-level power table of w_(2^27) in global memory (L2-resident) feeds a per-CTA
 //    shared table of w_L^j.
 #include "ctx.h"
+#include <cstdlib>
 
 namespace {
 
@@ -59,36 +60,59 @@ __device__ __forceinline__ uint32_t root_pow(const PassParams& p, uint32_t e) {
 // (spreads bit-reversed accesses, whose lanes differ only in the top five index bits, over all banks)
 __device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 4) + (i >> 9); }
 
+// Padded-tile offset of register-unit element m relative to element 0 of the unit.  With i = blk*2^(LQ+RHO) + m*2^LQ + j
+// (j < 2^LQ) both floor terms of pad(i) split into a unit-constant part and a part that depends on m alone, so the
+// sixteen shared-memory accesses of a unit are one computed address plus compile-time immediates:
+//   i >> 4 : LQ >= 4 -> m*2^(LQ-4) ;  LQ < 4 (and LQ+RHO >= 4) -> m >> (4-LQ)
+//   i >> 9 : LQ >= 9 -> m*2^(LQ-9) ;  LQ < 9 <= LQ+RHO -> m >> (9-LQ) ;  LQ+RHO < 9 -> 0
+template <int LQ, int RHO>
+__device__ __forceinline__ constexpr uint32_t unit_off(uint32_t m) {
+    uint32_t o = m << LQ;
+    o += (LQ >= 4) ? (m << (LQ >= 4 ? LQ - 4 : 0)) : (m >> (LQ < 4 ? 4 - LQ : 0));
+    if (LQ >= 9) o += m << (LQ >= 9 ? LQ - 9 : 0);
+    else if (LQ + RHO >= 9) o += m >> (LQ < 9 ? 9 - LQ : 0);
+    return o;
+}
+
 // RHO DIF stages (S .. S+RHO-1) of one register unit: the 2^RHO elements base + m*q, q = L >> (S+RHO).
 // LOG_LEN and S are compile-time so that every shift, pad() term and twiddle offset folds to an immediate.
 template <int RHO, int LOG_LEN, int S>
 __device__ __forceinline__ void radix_unit(uint32_t* __restrict__ grp, const uint32_t* __restrict__ tw, uint32_t u) {
     constexpr int R = 1 << RHO;
     constexpr int LQ = LOG_LEN - S - RHO;
+    constexpr bool IMM = (LQ + RHO >= 4);           // unit_off() is exact
     const uint32_t j = u & ((1u << LQ) - 1), blk = u >> LQ;
     const uint32_t base = (blk << (LQ + RHO)) + j;
+    uint32_t* const g0 = grp + pad(base);
     uint32_t x[R];
 #pragma unroll
-    for (int m = 0; m < R; m++) x[m] = grp[pad(base + ((uint32_t)m << LQ))];
+    for (int m = 0; m < R; m++) x[m] = IMM ? g0[unit_off<LQ, RHO>(m)] : grp[pad(base + ((uint32_t)m << LQ))];
 #pragma unroll
     for (int a = 0; a < RHO; a++) {
-        constexpr int dummy = 0; (void)dummy;
         const int half = R >> (a + 1);
+        constexpr int E0 = LQ + S;                  // twiddle index of butterfly mm at stage a: (j << (S+a)) + (mm << (E0+a))
         const uint32_t tj = j << (S + a);
+        const uint32_t* const tw0 = tw + tj + (tj >> 5);
 #pragma unroll
         for (int m0 = 0; m0 < R; m0++) {
             if ((m0 & half) == 0) {
                 const int m1 = m0 + half, mm = m0 & (half - 1);
                 const uint32_t A = x[m0], B = x[m1];
                 x[m0] = add(A, B);
-                const uint32_t d = sub(A, B);
-                if (a == RHO - 1 && LQ == 0) x[m1] = d;                       // last stage of the transform: twiddle 1
-                else { const uint32_t ti = tj + ((uint32_t)mm << (LQ + S + a)); x[m1] = mul(d, tw[ti + (ti >> 5)]); }
+                if (a == RHO - 1 && LQ == 0) x[m1] = sub(A, B);              // last stage of the transform: twiddle 1
+                else {
+                    // the Montgomery product reduces any 32-bit left factor: the difference goes in unreduced (A - B + p < 2^32)
+                    const uint32_t d = A - B + bb::P;
+                    uint32_t wv;
+                    if (E0 + a >= 5) wv = tw0[((uint32_t)mm << (E0 + a)) + ((uint32_t)mm << (E0 + a >= 5 ? E0 + a - 5 : 0))];   // padded index splits likewise
+                    else { const uint32_t ti = tj + ((uint32_t)mm << (E0 + a)); wv = tw[ti + (ti >> 5)]; }
+                    x[m1] = mul(d, wv);
+                }
             }
         }
     }
 #pragma unroll
-    for (int m = 0; m < R; m++) grp[pad(base + ((uint32_t)m << LQ))] = x[m];
+    for (int m = 0; m < R; m++) { if (IMM) g0[unit_off<LQ, RHO>(m)] = x[m]; else grp[pad(base + ((uint32_t)m << LQ))] = x[m]; }
 }
 
 template <int RHO, int LOG_LEN, int S>
@@ -331,7 +355,9 @@ __global__ void zero_pad_kernel(const uint32_t* src, uint64_t src_cs, uint32_t* 
 // split for the passes that have one strided and one contiguous sub-transform
 void split_col_row(int log_n, int* l_col, int* l_row) {
     if (log_n <= LOG_ROW_MAX) { *l_col = 0; *l_row = log_n; return; }
-    int lc = log_n - LOG_ROW_MAX;
+    static const int row_split = [] { const char* e = getenv("VGPU_NTT_LOG_ROW"); int v = e ? atoi(e) : LOG_ROW_MAX; return v < 8 || v > LOG_ROW_MAX ? LOG_ROW_MAX : v; }();   // tuning knob (profiles/)
+    int lc = log_n - row_split;
+    if (lc > 10) lc = 10;
     if (lc < 4) lc = 4;
     *l_col = lc; *l_row = log_n - lc;
 }
