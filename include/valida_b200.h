@@ -131,6 +131,15 @@ int32_t vgpu_challenger_reset(vgpu_ctx* ctx);
 int32_t vgpu_challenger_observe(vgpu_ctx* ctx, const uint32_t* values, uint32_t n);
 int32_t vgpu_challenger_sample_ext(vgpu_ctx* ctx, uint32_t out[5]);
 
+/* ---- pcs.open_multi_batches (derive/src/lib.rs:384-392) -------------------------------------------------
+ * rounds[r] = prover data of one commitment; for every matrix of every round (in order) n_points[.] opening points
+ * (1 or 2), each 5 canonical words in `points`.  Samples / observes on the context's challenger
+ * (vgpu_challenger_*), i.e. the caller has already observed the commitments.  Output: CBOR of the Rust tuple
+ * (opened_values: Vec<Vec<Vec<Vec<Challenge>>>>, proof: TwoAdicFriPcsProof) = a 2-element array; free with
+ * vgpu_free_bytes. */
+int32_t vgpu_open(vgpu_ctx* ctx, const vgpu_prover_data* const* rounds, uint32_t n_rounds, const uint32_t* n_points, const uint32_t* points,
+                  uint8_t** out_cbor, uint64_t* out_len);
+
 /* ---- Machine::prove (machine/src/machine.rs:22-24; body derive/src/lib.rs:275-446) -------------------
  * main: the 14 chip traces in BasicMachine order; prep: preprocessed traces (program 7 cols, range 1 col).
  * Runs steps 3-23 of the reference's prove() on the device (transcript on the host) and returns the

@@ -65,6 +65,42 @@ static inline std::vector<Digest> dec_digests(CborDec& d) { uint64_t n = d.array
 static inline void enc_exts(CborEnc& e, const std::vector<Ext5>& v) { e.array(v.size()); for (auto& x : v) enc_ext(e, x); }
 static inline std::vector<Ext5> dec_exts(CborDec& d) { uint64_t n = d.array(); std::vector<Ext5> v; for (uint64_t i = 0; i < n; i++) v.push_back(dec_ext(d)); return v; }
 
+static inline void enc_opening_proof(CborEnc& e, const PcsProof& op) {
+    e.map(2);
+    const FriProof& f = op.fri;
+    e.text("fri_proof"); e.map(4);
+    e.text("commit_phase_commits"); enc_digests(e, f.commit_phase_commits);
+    e.text("query_proofs"); e.array(f.query_proofs.size());
+    for (auto& q : f.query_proofs) {
+        e.map(1); e.text("commit_phase_openings"); e.array(q.steps.size());
+        for (auto& s : q.steps) { e.map(2); e.text("sibling_value"); enc_ext(e, s.sibling_value); e.text("opening_proof"); enc_digests(e, s.opening_proof); }
+    }
+    e.text("final_poly"); enc_ext(e, f.final_poly);
+    e.text("pow_witness"); enc_bb(e, f.pow_witness);
+    e.text("query_openings"); e.array(op.query_openings.size());
+    for (auto& q : op.query_openings) {
+        e.array(q.size());
+        for (auto& b : q) {
+            e.map(2);
+            e.text("opened_values"); e.array(b.opened_values.size());
+            for (auto& row : b.opened_values) { e.array(row.size()); for (uint32_t x : row) enc_bb(e, x); }
+            e.text("opening_proof"); enc_digests(e, b.opening_proof);
+        }
+    }
+}
+// the Rust tuple (OpenedValues, TwoAdicFriPcsProof) returned by open_multi_batches: a 2-element array
+static inline std::vector<uint8_t> encode_opening(const OpenedValues& values, const PcsProof& proof) {
+    CborEnc e;
+    e.array(2);
+    e.array(values.size());
+    for (auto& round : values) {
+        e.array(round.size());
+        for (auto& mat : round) { e.array(mat.size()); for (auto& at_point : mat) enc_exts(e, at_point); }
+    }
+    enc_opening_proof(e, proof);
+    return e.out;
+}
+
 static inline std::vector<uint8_t> encode_proof(const MachineProof& pr) {
     CborEnc e;
     e.map(3);
@@ -72,29 +108,7 @@ static inline std::vector<uint8_t> encode_proof(const MachineProof& pr) {
     e.text("main_trace"); enc_digest(e, pr.main_trace);
     e.text("perm_trace"); enc_digest(e, pr.perm_trace);
     e.text("quotient_chunks"); enc_digest(e, pr.quotient_chunks);
-    e.text("opening_proof"); e.map(2);
-    {
-        const FriProof& f = pr.opening_proof.fri;
-        e.text("fri_proof"); e.map(4);
-        e.text("commit_phase_commits"); enc_digests(e, f.commit_phase_commits);
-        e.text("query_proofs"); e.array(f.query_proofs.size());
-        for (auto& q : f.query_proofs) {
-            e.map(1); e.text("commit_phase_openings"); e.array(q.steps.size());
-            for (auto& s : q.steps) { e.map(2); e.text("sibling_value"); enc_ext(e, s.sibling_value); e.text("opening_proof"); enc_digests(e, s.opening_proof); }
-        }
-        e.text("final_poly"); enc_ext(e, f.final_poly);
-        e.text("pow_witness"); enc_bb(e, f.pow_witness);
-        e.text("query_openings"); e.array(pr.opening_proof.query_openings.size());
-        for (auto& q : pr.opening_proof.query_openings) {
-            e.array(q.size());
-            for (auto& b : q) {
-                e.map(2);
-                e.text("opened_values"); e.array(b.opened_values.size());
-                for (auto& row : b.opened_values) { e.array(row.size()); for (uint32_t x : row) enc_bb(e, x); }
-                e.text("opening_proof"); enc_digests(e, b.opening_proof);
-            }
-        }
-    }
+    e.text("opening_proof"); enc_opening_proof(e, pr.opening_proof);
     e.text("chip_proofs"); e.array(pr.chip_proofs.size());
     for (auto& c : pr.chip_proofs) {
         e.map(3);

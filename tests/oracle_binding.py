@@ -134,6 +134,27 @@ class Oracle:
         return int(self.L.orc_verify(bytes(proof_bytes), C.c_uint64(len(proof_bytes)), _p(preps[0]), C.c_uint64(preps[0].shape[0]),
                                      _p(preps[1]), C.c_uint64(preps[1].shape[0]), _p(np.ascontiguousarray(rc))))
 
+    def open(self, rounds, points, observe, shifts=None, rc=None, sample_ext_first=False):
+        """rounds: [[matrix, ...], ...]; points: per matrix a list of ext5 points (canonical 5-tuples); observe: words
+        absorbed before opening.  Returns the CBOR of (opened_values, proof)."""
+        rc = self.rc480 if rc is None else rc
+        flat = [np.ascontiguousarray(m, dtype=np.uint32) for r in rounds for m in r]
+        n = len(flat)
+        per_round = np.array([len(r) for r in rounds], dtype=np.uint32)
+        ptrs = (u32p * n)(*[_p(m) for m in flat])
+        hs = (C.c_uint64 * n)(*[m.shape[0] for m in flat])
+        ws = (C.c_uint64 * n)(*[m.shape[1] for m in flat])
+        npts = np.array([len(p) for p in points], dtype=np.uint32)
+        pts = np.array([w for p in points for z in p for w in z], dtype=np.uint32)
+        obs = np.ascontiguousarray(observe, dtype=np.uint32).reshape(-1)
+        sh = _p(np.ascontiguousarray(shifts, dtype=np.uint32)) if shifts is not None else None
+        self.L.orc_open.restype = C.c_uint64
+        args = (_p(np.ascontiguousarray(rc)), C.c_uint32(len(rounds)), _p(per_round), ptrs, hs, ws, sh, _p(npts), _p(pts), _p(obs), C.c_uint32(obs.size), C.c_uint32(1 if sample_ext_first else 0))
+        size = self.L.orc_open(*args, None, C.c_uint64(0))
+        buf = (C.c_uint8 * size)()
+        self.L.orc_open(*args, buf, C.c_uint64(size))
+        return bytes(buf)
+
     def chip_width(self, chip):
         return int(self.L.orc_chip_width(chip))
 

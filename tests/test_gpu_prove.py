@@ -107,23 +107,7 @@ def test_prove_reference_test_programs_bytes_equal(ctx, oracle, name):
     assert oracle.verify(proof, t.preprocessed) == 0
 
 
-def mixed_program(iters):
-    """Multi-chip synthetic loop (cpu + mem + add + lt + range + program): LCG-style value stream with
-    add / lt / lte / slt / sle (incl. left immediates) and a bne back-edge."""
-    B = 24
-    return np.array([
-        [7, -4, 0, 0, 0, 0],                                  # i = 0
-        [7, -8, 0x12, 0x34, 0x56, 0x78],                      # x = seed
-        [100, -8, -8, 1013904223, 0, 1],                      # x += c            (add32 imm)
-        [100, -12, -8, -4, 0, 0],                             # y = x + i         (add32)
-        [104, -16, -12, -8, 0, 0],                            # y < x             (lt32)
-        [117, -20, -8, -12, 0, 0],                            # x <s y            (slt32)
-        [115, -24, 77, -8, 1, 0],                             # 77 <= x           (lte32, left immediate)
-        [118, -28, -12, 1000, 0, 1],                          # y <=s 1000        (sle32, right immediate)
-        [100, -4, -4, 1, 0, 1],                               # i += 1
-        [6, 2 * B, -4, iters, 0, 1],                          # bne loop, i, iters
-        [8, 0, 0, 0, 0, 0],
-    ], dtype=np.int32)
+from programs import config5_program, mixed_program  # noqa: E402
 
 
 def test_prove_mixed_chip_program(ctx, oracle):
@@ -138,6 +122,23 @@ def test_prove_mixed_chip_program(ctx, oracle):
     assert oracle.verify(proof, t.preprocessed) == 0
     # larger instance: verifier accepts (oracle prover not run)
     t2 = vb.run_program(mixed_program(20000), initial_fp=0x1000)
+    assert t2.main[0].shape[0] == 1 << 18
+    p2 = gpu_prove(ctx, oracle, t2)
+    assert oracle.verify(p2, t2.preprocessed) == 0
+
+
+def test_prove_config5_program(ctx, oracle):
+    """BASELINE config 5 shape at test size: add, sub, lt family, and/or/xor chips all carry real rows."""
+    import valida_b200 as vb
+
+    t = vb.run_program(config5_program(60), initial_fp=0x1000)
+    assert t.main[4].shape[0] == 128 and t.main[10].shape[0] == 512 and t.main[8].shape[0] == 256
+    ref = oracle.prove(t.main, t.preprocessed, debug_checks=True)
+    assert ref.constraint_failures() == [-1] * 14 and ref.cumulative_sum_zero()
+    proof = gpu_prove(ctx, oracle, t)
+    assert proof == ref.cbor()
+    vb.verify_machine(vb.StarkConfig(ctx, oracle.rc480), proof, t.preprocessed)
+    t2 = vb.run_program(config5_program(16000), initial_fp=0x1000)
     assert t2.main[0].shape[0] == 1 << 18
     p2 = gpu_prove(ctx, oracle, t2)
     assert oracle.verify(p2, t2.preprocessed) == 0

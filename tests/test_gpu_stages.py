@@ -108,3 +108,43 @@ def test_quotient_random_traces_exercise_every_constraint(ctx, oracle, chip):
     exp = oracle.quotient(chip, log_degree, None, ml.download(), pl.download(), cs, ch, alpha)
     got = vb.quotient(ctx, chip, log_degree, None, ml, pl, cs, ch, alpha).download()
     assert np.array_equal(got, exp)
+
+
+def test_open_multi_batches_stand_alone(ctx, oracle):
+    """vgpu_open = pcs.open_multi_batches on its own: two commitments (mixed heights, one with per-matrix shifts),
+    one- and two-point openings, transcript seeded with the two roots — bytes equal to the oracle's."""
+    import ctypes as C
+    import valida_b200 as vb
+
+    rng = np.random.default_rng(77)
+    P = 2013265921
+    r0 = [rng.integers(0, P, (1 << 9, 6), dtype=np.uint32), rng.integers(0, P, (1 << 11, 3), dtype=np.uint32), rng.integers(0, P, (1, 4), dtype=np.uint32)]
+    r1 = [rng.integers(0, P, (1 << 9, 10), dtype=np.uint32), rng.integers(0, P, (1 << 11, 10), dtype=np.uint32)]
+    shifts1 = [961, 961]
+    cfg = vb.StarkConfig(ctx, oracle.rc480)
+    pcs = cfg.pcs()
+    root0, pd0 = pcs.commit_batches(r0)
+    root1, pd1 = pcs.commit_shifted_batches(r1, shifts1)
+    assert np.array_equal(root0, oracle.commit_batches(r0)) and np.array_equal(root1, oracle.commit_batches(r1, coset_shifts=shifts1))
+    L = vb.lib()
+    ctx.check(L.vgpu_challenger_reset(ctx._h))
+    obs = np.concatenate([root0, root1]).astype(np.uint32)
+    ctx.check(L.vgpu_challenger_observe(ctx._h, obs.ctypes.data_as(C.POINTER(C.c_uint32)), obs.size))
+    zeta = (C.c_uint32 * 5)()
+    ctx.check(L.vgpu_challenger_sample_ext(ctx._h, zeta))
+    z = [int(v) for v in zeta]
+
+    def ext_mul_base(e, b):
+        return [int(v) * b % P for v in e]
+
+    def gen(log_h):
+        return pow(0x1A427A41, 1 << (27 - log_h), P)
+
+    pts0 = [[z, ext_mul_base(z, gen(9))], [z, ext_mul_base(z, gen(11))], [z]]
+    z2 = [int(v) for v in oracle.ext_mul(z, z)]
+    pts1 = [[z2], [z2]]
+    got = pcs.open_multi_batches([(pd0, pts0), (pd1, pts1)])
+    # the oracle's challenger: same observations, then the same sample (its value is checked through the opening)
+    want = oracle.open([r0, r1], pts0 + pts1, obs, shifts=[1, 1, 1] + shifts1, sample_ext_first=True)
+    assert got == want
+    pd0.free(); pd1.free()

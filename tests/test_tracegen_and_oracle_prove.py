@@ -125,3 +125,30 @@ def test_reference_test_programs_vm_state_and_oracle_proof(built, oracle, name):
     assert pr.constraint_failures() == [-1] * 14     # check_constraints (debug builds of the reference)
     assert pr.cumulative_sum_zero()                  # check_cumulative_sums
     assert oracle.verify(pr.cbor(), t.preprocessed) == 0
+
+
+def test_config5_program_trace_satisfies_every_air(built, oracle):
+    """add + sub + lt family + and/or/xor: the host witness generator's rows satisfy the restated AIRs on every row
+    (the reference's debug-build check_constraints), all LogUp sums cancel, and the oracle proof verifies."""
+    import valida_b200 as vb
+    from programs import config5_program
+
+    t = vb.run_program(config5_program(60), initial_fp=0x1000)
+    # 60 iterations: 2 sub, 6 bitwise, 4 lt, 2 add per iteration
+    assert t.main[4].shape[0] == 128 and t.main[10].shape[0] == 512 and t.main[8].shape[0] == 256 and t.main[3].shape[0] == 128
+    # VM state: replay the loop in Python
+    M = 0xFFFFFFFF
+    x, m = 0x9E3779B9, 0x0FF055AA
+    for i in range(60):
+        x = (x + 1013904223) & M
+        y = x ^ m
+        z = y & 0x00FFFF00
+        w = z | i
+        d = (x - w) & M
+        e = (d - 12345) & M
+        x ^= e
+        m = ((m & y) | 0x01010101) & M
+    assert t.mem_cell(0x1000 - 8) == x and t.mem_cell(0x1000 - 32) == m and t.mem_cell(0x1000 - 4) == 60
+    ref = oracle.prove(t.main, t.preprocessed, debug_checks=True)
+    assert ref.constraint_failures() == [-1] * 14 and ref.cumulative_sum_zero()
+    assert oracle.verify(ref.cbor(), t.preprocessed) == 0

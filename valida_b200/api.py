@@ -67,6 +67,7 @@ def _load():
         "vgpu_comm_set_sharding": (C.c_int32, [vp, C.c_int32]),
         "vgpu_shard_range": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
         "vgpu_tree_share": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_int32)]),
+        "vgpu_open": (C.c_int32, [vp, C.POINTER(vp), C.c_uint32, u32p, u32p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgpu_verify": (C.c_int32, [vp, C.c_char_p, u64, C.POINTER(_Matrix), C.c_int32, C.POINTER(C.c_int32)]),
         "vgpu_prove": (C.c_int32, [vp, C.POINTER(_Matrix), C.POINTER(_Matrix), C.c_int32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgpu_prove_device": (C.c_int32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
@@ -277,6 +278,20 @@ class TwoAdicFriPcs:
             arr = (_Matrix * n)(*[_mat(a) for a in keep])
             self.ctx.check(lib().vgpu_commit_batches_host(self.ctx._h, arr, n, REPR_CANONICAL, shifts, digest, C.byref(out)))
         return np.array(list(digest), dtype=np.uint32), ProverData(self.ctx, out, n)
+
+    def open_multi_batches(self, rounds, challenger=None):
+        """rounds: [(ProverData, [[point, ...] per matrix])], points as 5 canonical words.  Uses the context's
+        challenger (StarkConfig.challenger()).  Returns the CBOR bytes of (opened_values, proof)."""
+        handles = (C.c_void_p * len(rounds))(*[pd._h for pd, _ in rounds])
+        npts = np.array([len(p) for _, pts in rounds for p in pts], dtype=np.uint32)
+        flat = np.array([w for _, pts in rounds for p in pts for z in p for w in z], dtype=np.uint32)
+        out = C.POINTER(C.c_uint8)()
+        n = C.c_uint64()
+        self.ctx.check(lib().vgpu_open(self.ctx._h, handles, len(rounds), npts.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       flat.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(out), C.byref(n)))
+        data = C.string_at(out, n.value)
+        lib().vgpu_free_bytes(out)
+        return data
 
     def get_ldes(self, prover_data):
         """Committed LDEs (rows stored bit-reversed), borrowed views."""

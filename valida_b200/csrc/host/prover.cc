@@ -224,6 +224,30 @@ struct Cbor {
     void exts(const std::vector<ExtC>& v) { arr(v.size()); for (auto& e : v) ext(e); }
 };
 
+// TwoAdicFriPcsProof { fri_proof, query_openings } as serde/ciborium writes it
+void write_opening_proof(Cbor& w, const OpeningH& op) {
+    w.map(2);
+    w.key("fri_proof"); w.map(4);
+    w.key("commit_phase_commits"); w.digests(op.fri.commit_phase_commits);
+    w.key("query_proofs"); w.arr(op.fri.query_proofs.size());
+    for (auto& q : op.fri.query_proofs) {
+        w.map(1); w.key("commit_phase_openings"); w.arr(q.steps.size());
+        for (auto& s : q.steps) { w.map(2); w.key("sibling_value"); w.ext(s.sibling_value); w.key("opening_proof"); w.digests(s.opening_proof); }
+    }
+    w.key("final_poly"); w.ext(op.fri.final_poly);
+    w.key("pow_witness"); w.felt(op.fri.pow_witness);
+    w.key("query_openings"); w.arr(op.query_openings.size());
+    for (auto& q : op.query_openings) {
+        w.arr(q.size());
+        for (auto& bo : q) {
+            w.map(2);
+            w.key("opened_values"); w.arr(bo.opened_values.size());
+            for (auto& row : bo.opened_values) { w.arr(row.size()); for (uint32_t x : row) w.felt(x); }
+            w.key("opening_proof"); w.digests(bo.opening_proof);
+        }
+    }
+}
+
 struct Phase {
     vgpu_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
     Phase(vgpu_ctx* c, const char* n) : ctx(c), name(n) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
@@ -269,6 +293,41 @@ int32_t vgpu_challenger_sample_ext(vgpu_ctx* ctx, uint32_t out[5]) {
     if (!ctx->challenger) VG_TRY(vgpu_challenger_reset(ctx));
     E5 e = ((vgh::Challenger*)ctx->challenger)->sample_ext();
     for (int i = 0; i < 5; i++) out[i] = bb::from_monty(e.c[i]);
+    return 0;
+}
+
+int32_t vgpu_open(vgpu_ctx* ctx, const vgpu_prover_data* const* rounds, uint32_t n_rounds, const uint32_t* n_points, const uint32_t* points,
+                  uint8_t** out_cbor, uint64_t* out_len) {
+    if (!rounds || !n_points || !points || !out_cbor || !out_len) VG_FAIL(ctx, "open: null argument");
+    if (!ctx->challenger) VG_TRY(vgpu_challenger_reset(ctx));
+    std::vector<OpenRound> rds(n_rounds);
+    size_t mi = 0, pi = 0;
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        if (!rounds[r]) VG_FAIL(ctx, "open: round %u has no prover data", r);
+        rds[r].pd = rounds[r];
+        for (size_t m = 0; m < rounds[r]->ldes.size(); m++, mi++) {
+            std::vector<E5> pts;
+            for (uint32_t q = 0; q < n_points[mi]; q++, pi++) {
+                E5 z; for (int l = 0; l < 5; l++) z.c[l] = bb::to_monty(points[5 * pi + l] % bb::P);
+                pts.push_back(z);
+            }
+            rds[r].points.push_back(std::move(pts));
+        }
+    }
+    OpeningH op;
+    VG_TRY(open_multi_batches(ctx, rds, *(vgh::Challenger*)ctx->challenger, &op));
+    Cbor w;
+    w.arr(2);
+    w.arr(op.values.size());
+    for (auto& round : op.values) {
+        w.arr(round.size());
+        for (auto& mat : round) { w.arr(mat.size()); for (auto& at_point : mat) w.exts(at_point); }
+    }
+    write_opening_proof(w, op);
+    uint8_t* buf = (uint8_t*)std::malloc(w.b.size());
+    if (!buf) VG_FAIL(ctx, "out of host memory");
+    std::memcpy(buf, w.b.data(), w.b.size());
+    *out_cbor = buf; *out_len = w.b.size();
     return 0;
 }
 
@@ -363,26 +422,7 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
     w.key("main_trace"); w.digest(main_commit);
     w.key("perm_trace"); w.digest(perm_commit);
     w.key("quotient_chunks"); w.digest(quot_commit);
-    w.key("opening_proof"); w.map(2);
-    w.key("fri_proof"); w.map(4);
-    w.key("commit_phase_commits"); w.digests(op.fri.commit_phase_commits);
-    w.key("query_proofs"); w.arr(op.fri.query_proofs.size());
-    for (auto& q : op.fri.query_proofs) {
-        w.map(1); w.key("commit_phase_openings"); w.arr(q.steps.size());
-        for (auto& s : q.steps) { w.map(2); w.key("sibling_value"); w.ext(s.sibling_value); w.key("opening_proof"); w.digests(s.opening_proof); }
-    }
-    w.key("final_poly"); w.ext(op.fri.final_poly);
-    w.key("pow_witness"); w.felt(op.fri.pow_witness);
-    w.key("query_openings"); w.arr(op.query_openings.size());
-    for (auto& q : op.query_openings) {
-        w.arr(q.size());
-        for (auto& bo : q) {
-            w.map(2);
-            w.key("opened_values"); w.arr(bo.opened_values.size());
-            for (auto& row : bo.opened_values) { w.arr(row.size()); for (uint32_t x : row) w.felt(x); }
-            w.key("opening_proof"); w.digests(bo.opening_proof);
-        }
-    }
+    w.key("opening_proof"); write_opening_proof(w, op);
     w.key("chip_proofs"); w.arr(VGPU_NUM_CHIPS);
     const std::vector<ExtC> none;
     for (int i = 0; i < VGPU_NUM_CHIPS; i++) {

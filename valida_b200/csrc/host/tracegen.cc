@@ -31,13 +31,14 @@ inline uint32_t from_i32(int32_t x) { return x < 0 ? (P - (uint32_t)(-(int64_t)x
 inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
 
 enum : uint32_t { OP_LOAD32 = 1, OP_STORE32 = 2, OP_JAL = 3, OP_JALV = 4, OP_BEQ = 5, OP_BNE = 6, OP_IMM32 = 7, OP_STOP = 8, OP_LOADFP = 10,
-                  OP_ADD32 = 100, OP_SUB32 = 101, OP_LT32 = 104, OP_LTE32 = 115, OP_SLT32 = 117, OP_SLE32 = 118 };
+                  OP_ADD32 = 100, OP_SUB32 = 101, OP_LT32 = 104, OP_AND32 = 107, OP_OR32 = 108, OP_XOR32 = 109, OP_LTE32 = 115, OP_SLT32 = 117, OP_SLE32 = 118 };
 enum CpuOp : uint8_t { K_STORE32, K_LOAD32, K_JAL, K_JALV, K_BEQ, K_BNE, K_IMM32, K_BUS, K_STOP, K_LOADFP, K_BUS_LEFT_IMM };
 
 struct MemOp { uint32_t clk, addr, value; uint8_t is_write; };
 struct CpuRec { uint32_t pc, fp; uint32_t instr; CpuOp kind; bool has_imm; uint32_t imm; };
 struct AluRec { uint32_t a, b, c; };
 struct LtRec { uint32_t a, b, c; uint32_t opcode; };
+using BitRec = LtRec;
 
 struct Vm {
     const int32_t* prog; size_t n_instr;
@@ -47,6 +48,7 @@ struct Vm {
     std::vector<CpuRec> cpu;
     std::vector<AluRec> adds, subs;
     std::vector<LtRec> lts;
+    std::vector<BitRec> bits;
     std::vector<uint32_t> prog_counts;
     uint32_t range_count[256] = {0};
     std::string err;
@@ -85,6 +87,15 @@ struct Vm {
                 (opcode == OP_ADD32 ? adds : subs).push_back({av, bv, cv});
                 pc++; push(K_BUS, pc0, pc0, fp0, imm, cv);
                 range_check(av); break; }
+            case OP_AND32: case OP_OR32: case OP_XOR32: {
+                // alu_u32/src/bitwise/mod.rs:150-262: read b, read c or take it as the immediate, no range check
+                uint32_t bv, cv; bool imm = (e == 1);
+                if (!read(at(b), bv)) return -1;
+                if (imm) cv = (uint32_t)c; else if (!read(at(c), cv)) return -1;
+                uint32_t av = opcode == OP_AND32 ? (bv & cv) : opcode == OP_OR32 ? (bv | cv) : (bv ^ cv);
+                write(at(a), av);
+                bits.push_back({av, bv, cv, opcode});
+                pc++; push(K_BUS, pc0, pc0, fp0, imm, cv); break; }
             case OP_LT32: case OP_LTE32: case OP_SLT32: case OP_SLE32: {
                 // alu_u32/src/lt/mod.rs:162-205 (execute_with_closure): d == 1 -> left operand is the immediate b;
                 // e == 1 -> right operand is the immediate c (and `imm` then holds c, as in the reference)
@@ -292,6 +303,24 @@ void build_lt(const std::vector<LtRec>& ops, std::vector<uint32_t>& v, vgpu_matr
     out = {v.data(), h, W};
 }
 
+// Bitwise32Chip::op_to_row / set_cols (alu_u32/src/bitwise/mod.rs:84-131): input_1 0..3, input_2 4..7,
+// bits_1[byte][bit] 8 + 8*byte + bit, bits_2 40 + ..., output 72..75, is_and 76, is_or 77, is_xor 78
+void build_bitwise(const std::vector<BitRec>& ops, std::vector<uint32_t>& v, vgpu_matrix& out) {
+    constexpr size_t W = 79;
+    size_t n = ops.size(), h = next_pow2(n);
+    v.assign(h * W, 0);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t* row = &v[i * W];
+        uint32_t a[4], b[4], c[4];
+        word_be(ops[i].a, a); word_be(ops[i].b, b); word_be(ops[i].c, c);
+        std::memcpy(row + 0, b, 16); std::memcpy(row + 4, c, 16); std::memcpy(row + 72, a, 16);
+        for (int k = 0; k < 4; k++)
+            for (int bit = 0; bit < 8; bit++) { row[8 + 8 * k + bit] = (b[k] >> bit) & 1; row[40 + 8 * k + bit] = (c[k] >> bit) & 1; }
+        row[ops[i].opcode == OP_AND32 ? 76 : ops[i].opcode == OP_OR32 ? 77 : 78] = 1;
+    }
+    out = {v.data(), h, W};
+}
+
 void zero_chip(std::vector<uint32_t>& v, vgpu_matrix& out, size_t w) { v.assign(w, 0); out = {v.data(), 1, w}; }
 
 }  // namespace
@@ -343,7 +372,7 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
     zero_chip(t.store[7], t.main[7], 28);   // shift
     build_lt(vm.lts, t.store[8], t.main[8]);   // lt
     zero_chip(t.store[9], t.main[9], 14);   // com
-    zero_chip(t.store[10], t.main[10], 79); // bitwise
+    build_bitwise(vm.bits, t.store[10], t.main[10]);   // bitwise
     zero_chip(t.store[11], t.main[11], 7);  // output
     {  // range: (mult, counter) + preprocessed counter
         t.store[12].assign(256 * 2, 0); t.store[15].assign(256, 0);
