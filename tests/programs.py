@@ -26,22 +26,25 @@ def mixed_program(iters):
 
 def config5_program(iters):
     """cpu + mem + add + sub + lt + bitwise + range + program.  x <- x*1664525 + 1013904223 is replaced by an
-    add/xor/and/or mix (no mul); every ALU flavour appears with a memory operand and with an immediate."""
+    add/xor/and/or mix (no mul); every ALU flavour appears with a memory operand and with an immediate.
+    The sub operands are shaped so that no byte borrows (minuend bytes >= 0x80 > subtrahend bytes): the reference's
+    Sub32Chip::op_to_row derives each borrow from the operand bytes alone (alu_u32/src/sub/mod.rs:103-111) and its AIR
+    has no top-byte borrow (sub/stark.rs:42-45), so a subtraction that borrows is unprovable in the reference too."""
     return np.array([
         [7, -4, 0, 0, 0, 0],                                  # i = 0
         [7, -8, 0x9e, 0x37, 0x79, 0xb9],                      # x = seed
         [7, -32, 0x0f, 0xf0, 0x55, 0xaa],                     # m = mask
         [100, -8, -8, 1013904223, 0, 1],                      # x += c                       (add32 imm)     <- loop
         [109, -12, -8, -32, 0, 0],                            # y = x ^ m                    (xor32)
-        [107, -16, -12, 0x00ffff00, 0, 1],                    # z = y & 0x00ffff00           (and32 imm)
-        [108, -20, -16, -4, 0, 0],                            # w = z | i                    (or32)
-        [101, -24, -8, -20, 0, 0],                            # d = x - w                    (sub32)
-        [101, -28, -24, 12345, 0, 1],                         # e = d - 12345                (sub32 imm)
+        [107, -16, -12, 0x7f7f7f7f, 0, 1],                    # t = y & 0x7f7f7f7f           (and32 imm)
+        [108, -20, -8, -0x7f7f7f80, 0, 1],                    # s = x | 0x80808080           (or32 imm)
+        [101, -24, -20, -16, 0, 0],                           # d = s - t                    (sub32)
+        [101, -28, -20, 12345, 0, 1],                         # e = s - 12345                (sub32 imm)
         [109, -8, -8, -28, 0, 0],                             # x ^= e                       (xor32)
         [104, -36, -24, -8, 0, 0],                            # d < x                        (lt32)
         [118, -40, -28, -12, 0, 0],                           # e <=s y                      (sle32)
         [117, -44, 5, -28, 1, 0],                             # 5 <s e                       (slt32 left imm)
-        [115, -48, -20, 4096, 0, 1],                          # w <= 4096                    (lte32 imm)
+        [115, -48, -20, 4096, 0, 1],                          # s <= 4096                    (lte32 imm)
         [107, -32, -32, -12, 0, 0],                           # m &= y                       (and32)
         [108, -32, -32, 0x01010101, 0, 1],                    # m |= 0x01010101              (or32 imm)
         [100, -4, -4, 1, 0, 1],                               # i += 1

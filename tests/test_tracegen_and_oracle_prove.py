@@ -142,10 +142,8 @@ def test_config5_program_trace_satisfies_every_air(built, oracle):
     for i in range(60):
         x = (x + 1013904223) & M
         y = x ^ m
-        z = y & 0x00FFFF00
-        w = z | i
-        d = (x - w) & M
-        e = (d - 12345) & M
+        s = x | 0x80808080
+        e = (s - 12345) & M
         x ^= e
         m = ((m & y) | 0x01010101) & M
     assert t.mem_cell(0x1000 - 8) == x and t.mem_cell(0x1000 - 32) == m and t.mem_cell(0x1000 - 4) == 60
