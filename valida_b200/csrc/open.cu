@@ -40,55 +40,93 @@ __global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, u
     st5(out, H, i, d);
 }
 
-// K8: partial sums S[c][p] = sum_{rho in block rows} e[rho][c] * x_rho * invden_p[rho] over the first h rows.
-constexpr int BARY_COLS = 8, BARY_THREADS = 256;
+// K8: out-of-domain evaluation.  With x/(x - z) = 1 + z/(x - z) the barycentric sum splits into
+//     S_c(z) = sum_i p_c(x_i) + z * sum_i p_c(x_i) / (x_i - z)
+// so the kernel needs no domain points at all: per column a base-field sum and, per point, an ext5 dot product with
+// the inverse denominators.  Dot products are accumulated LAZILY: raw 64-bit products of Montgomery words
+// (< 2^62 each) are added three at a time into a 64-bit accumulator which is then folded with
+// hi*2^32 + lo == hi*R1 + lo (mod p) — one IMAD.WIDE per term instead of a full modular multiply-add.
+// A CTA stages the inverse denominators of a tile of rows in shared memory once and every warp sweeps that tile
+// for its own BARY_COLS columns, so the denominators are read from HBM once per group of 32 columns.
+constexpr int BARY_COLS = 2, BARY_WARPS = 16, BARY_THREADS = 32 * BARY_WARPS, BARY_TILE = 1024, BARY_GROUP = BARY_COLS * BARY_WARPS;
+constexpr int BARY_OUT = 11;                       // per column: 2 points x 5 limbs, then the plain column sum
 struct BaryParams {
-    const uint32_t* mat; uint64_t mcs; uint64_t h; uint32_t log_H; uint32_t w;
+    const uint32_t* mat; uint64_t mcs; uint64_t h; uint32_t w;
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
-    uint32_t s; const uint32_t* lo; const uint32_t* hi;
-    uint32_t* partial;       // [gridDim.x][w][npoints][5]
+    uint32_t* partial;       // [gridDim.x][w][BARY_OUT]
 };
-__global__ void __launch_bounds__(BARY_THREADS) bary_kernel(BaryParams p) {
-    const uint32_t c0 = blockIdx.y * BARY_COLS;
-    const uint32_t nc = min((uint32_t)BARY_COLS, p.w - c0);
-    E5 acc[BARY_COLS][2];
+__device__ __forceinline__ uint64_t lazy_fold(uint64_t a) { return (a & 0xffffffffull) + (a >> 32) * (uint64_t)bb::R1; }
+__global__ void __launch_bounds__(BARY_THREADS, 1) bary_kernel(BaryParams p) {
+    __shared__ uint32_t dsm[2][5][BARY_TILE];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t c0 = blockIdx.y * BARY_GROUP + wid * BARY_COLS;
+    const uint32_t* col[BARY_COLS];
 #pragma unroll
-    for (int c = 0; c < BARY_COLS; c++) { acc[c][0] = bb::e5_zero(); acc[c][1] = bb::e5_zero(); }
-    for (uint64_t r = (uint64_t)blockIdx.x * BARY_THREADS + threadIdx.x; r < p.h; r += (uint64_t)gridDim.x * BARY_THREADS) {
-        uint32_t nat = bb::reverse_bits((uint32_t)r, (int)p.log_H);
-        uint32_t x = bb::mul(p.s, oroot_pow(p.lo, p.hi, (uint64_t)nat << (VG_LOG_NMAX - p.log_H)));
-        E5 wgt[2];
-        for (uint32_t q = 0; q < p.npoints; q++) wgt[q] = bb::e5_mul_base(ld5(p.invden[q], p.ics, r), x);
+    for (int c = 0; c < BARY_COLS; c++) col[c] = p.mat + (uint64_t)min(c0 + c, p.w - 1) * p.mcs;   // surplus columns shadow the last one (never written)
+    uint64_t acc[BARY_COLS][2][5];
+    uint64_t sum[BARY_COLS];
 #pragma unroll
-        for (int c = 0; c < BARY_COLS; c++) {
-            if ((uint32_t)c < nc) {
-                uint32_t e = __ldg(p.mat + (uint64_t)(c0 + c) * p.mcs + r);
-                acc[c][0] = bb::e5_add(acc[c][0], bb::e5_mul_base(wgt[0], e));
-                if (p.npoints > 1) acc[c][1] = bb::e5_add(acc[c][1], bb::e5_mul_base(wgt[1], e));
+    for (int c = 0; c < BARY_COLS; c++) { sum[c] = 0; for (int q = 0; q < 2; q++) for (int l = 0; l < 5; l++) acc[c][q][l] = 0; }
+    const uint64_t ntiles = (p.h + BARY_TILE - 1) / BARY_TILE;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t row0 = t * BARY_TILE;
+        const uint32_t rows = (uint32_t)min((uint64_t)BARY_TILE, p.h - row0);
+        __syncthreads();
+        for (uint32_t q = 0; q < p.npoints; q++)
+#pragma unroll
+            for (int l = 0; l < 5; l++)
+                for (uint32_t r = threadIdx.x; r < rows; r += BARY_THREADS) dsm[q][l][r] = __ldg(p.invden[q] + (uint64_t)l * p.ics + row0 + r);
+        __syncthreads();
+        if (c0 < p.w) {
+            // six row-slices per step: twelve independent global loads in flight per lane, a fold per three products
+            for (uint32_t r = lane; r < rows; r += 192) {
+                uint32_t e[6][BARY_COLS], rr[6];
+#pragma unroll
+                for (int u = 0; u < 6; u++) {
+                    const uint32_t ru = r + 32 * u;
+                    rr[u] = ru < rows ? ru : r;
+#pragma unroll
+                    for (int c = 0; c < BARY_COLS; c++) e[u][c] = ru < rows ? __ldg(col[c] + row0 + ru) : 0u;   // a zero term adds nothing
+                }
+#pragma unroll
+                for (int g = 0; g < 6; g += 3) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        if ((uint32_t)q < p.npoints) {
+#pragma unroll
+                            for (int l = 0; l < 5; l++) {
+                                const uint32_t d0 = dsm[q][l][rr[g]], d1 = dsm[q][l][rr[g + 1]], d2 = dsm[q][l][rr[g + 2]];
+#pragma unroll
+                                for (int c = 0; c < BARY_COLS; c++)
+                                    acc[c][q][l] = lazy_fold(acc[c][q][l] + (uint64_t)e[g][c] * d0 + (uint64_t)e[g + 1][c] * d1 + (uint64_t)e[g + 2][c] * d2);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < BARY_COLS; c++)
+#pragma unroll
+                    for (int u = 0; u < 6; u++) sum[c] += e[u][c];
             }
         }
     }
-    // block reduction through shared memory
-    __shared__ uint32_t red[BARY_THREADS / 32][BARY_COLS * 2 * 5];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (c0 >= p.w) return;
+    // reduce to field elements, then across the warp
 #pragma unroll
-    for (int c = 0; c < BARY_COLS; c++)
+    for (int c = 0; c < BARY_COLS; c++) {
+        uint32_t v[BARY_OUT];
 #pragma unroll
         for (int q = 0; q < 2; q++)
 #pragma unroll
-            for (int l = 0; l < 5; l++) {
-                uint32_t v = acc[c][q].c[l];
+            for (int l = 0; l < 5; l++) v[q * 5 + l] = bb::monty_reduce64(acc[c][q][l]);
+        v[10] = (uint32_t)(sum[c] % bb::P);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = bb::add(v, __shfl_xor_sync(0xffffffffu, v, o));
-                if (lane == 0) red[wid][(c * 2 + q) * 5 + l] = v;
-            }
-    __syncthreads();
-    if (threadIdx.x < BARY_COLS * 2 * 5) {
-        uint32_t v = 0;
-        for (int w = 0; w < BARY_THREADS / 32; w++) v = bb::add(v, red[w][threadIdx.x]);
-        int c = threadIdx.x / 10, q = (threadIdx.x / 5) % 2, l = threadIdx.x % 5;
-        if ((uint32_t)c < nc && (uint32_t)q < p.npoints)
-            p.partial[(((uint64_t)blockIdx.x * p.w + c0 + c) * p.npoints + q) * 5 + l] = v;
+        for (int k = 0; k < BARY_OUT; k++) {
+            uint32_t x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = bb::add(x, __shfl_xor_sync(0xffffffffu, x, o));
+            if (lane == 0 && c0 + c < p.w) p.partial[((uint64_t)blockIdx.x * p.w + c0 + c) * BARY_OUT + k] = x;
+        }
     }
 }
 
@@ -100,11 +138,39 @@ struct RoParams {
     E5 sum_y[2]; E5 alpha_off[2];     // per point: sum_c alpha^c y_c and alpha^offset
     uint32_t* ro; uint64_t rcs;       // accumulator, limb-major, height H
 };
+// one thread per LDE row; sum_c alpha^c p_c(x_i) accumulated lazily (see K8), three columns per fold
 __global__ void __launch_bounds__(256) reduced_opening_kernel(RoParams p) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.H) return;
-    E5 red = bb::e5_zero();
-    for (uint32_t c = 0; c < p.w; c++) red = bb::e5_add(red, bb::e5_mul_base(p.apow[c], __ldg(p.mat + (uint64_t)c * p.mcs + i)));
+    uint64_t a[5] = {0, 0, 0, 0, 0};
+    const uint32_t* m = p.mat + i;
+    uint32_t c = 0;
+    for (; c + 6 <= p.w; c += 6) {   // six loads in flight, two folds
+        uint32_t e[6];
+#pragma unroll
+        for (int u = 0; u < 6; u++) e[u] = __ldg(m + (uint64_t)(c + u) * p.mcs);
+#pragma unroll
+        for (int g = 0; g < 6; g += 3) {
+            const E5 a0 = p.apow[c + g], a1 = p.apow[c + g + 1], a2 = p.apow[c + g + 2];
+#pragma unroll
+            for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l] + (uint64_t)a0.c[l] * e[g] + (uint64_t)a1.c[l] * e[g + 1] + (uint64_t)a2.c[l] * e[g + 2]);
+        }
+    }
+    for (; c + 3 <= p.w; c += 3) {
+        const uint32_t e0 = __ldg(m + (uint64_t)c * p.mcs), e1 = __ldg(m + (uint64_t)(c + 1) * p.mcs), e2 = __ldg(m + (uint64_t)(c + 2) * p.mcs);
+        const E5 a0 = p.apow[c], a1 = p.apow[c + 1], a2 = p.apow[c + 2];
+#pragma unroll
+        for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l] + (uint64_t)a0.c[l] * e0 + (uint64_t)a1.c[l] * e1 + (uint64_t)a2.c[l] * e2);
+    }
+    for (; c < p.w; c++) {
+        const uint32_t e0 = __ldg(m + (uint64_t)c * p.mcs);
+        const E5 a0 = p.apow[c];
+#pragma unroll
+        for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l] + (uint64_t)a0.c[l] * e0);
+    }
+    E5 red;
+#pragma unroll
+    for (int l = 0; l < 5; l++) red.c[l] = bb::monty_reduce64(a[l]);
     E5 acc = ld5(p.ro, p.rcs, i);
     for (uint32_t q = 0; q < p.npoints; q++) {
         E5 t = bb::e5_mul(bb::e5_sub(red, p.sum_y[q]), ld5(p.invden[q], p.ics, i));
@@ -160,21 +226,22 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
     uint64_t H = lde->h, h = H / 2;
     uint32_t log_H = 0; while ((1ull << log_H) < H) log_H++;
     uint32_t w = (uint32_t)lde->w;
-    unsigned bx = (unsigned)std::min<uint64_t>((h + BARY_THREADS - 1) / BARY_THREADS, 8 * (uint64_t)ctx->sm_count);
-    unsigned by = (w + BARY_COLS - 1) / BARY_COLS;
+    const uint64_t ntiles = (h + BARY_TILE - 1) / BARY_TILE;
+    unsigned by = (w + BARY_GROUP - 1) / BARY_GROUP;
+    unsigned bx = (unsigned)std::min<uint64_t>(ntiles, std::max<uint64_t>(1, 2 * (uint64_t)ctx->sm_count / by));
     uint32_t* partial = nullptr;
-    size_t pn = (size_t)bx * w * npoints * 5;
+    size_t pn = (size_t)bx * w * BARY_OUT;
     VG_TRY(vg_alloc(ctx, (void**)&partial, pn * 4));
     BaryParams p{};
-    p.mat = lde->d; p.mcs = lde->col_stride; p.h = h; p.log_H = log_H; p.w = w;
+    p.mat = lde->d; p.mcs = lde->col_stride; p.h = h; p.w = w;
     p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = H; p.npoints = npoints;
-    p.s = bb::to_monty(bb::GEN_CANON); p.lo = ctx->root_table.lo; p.hi = ctx->root_table.hi; p.partial = partial;
+    p.partial = partial;
     {
         KScope ks(ctx, KC_BARY, 4.0 * (double)h * w);
         bary_kernel<<<dim3(bx, by), BARY_THREADS, 0, ctx->stream>>>(p);
     }
     VG_LAUNCH_CHECK(ctx);
-    const uint32_t nout = w * npoints * 5;
+    const uint32_t nout = w * BARY_OUT;
     uint32_t* reduced = nullptr;
     VG_TRY(vg_alloc(ctx, (void**)&reduced, nout * 4));
     bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, bx, nout, reduced);
@@ -193,8 +260,9 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
         E5 zh = bb::e5_exp_pow2(z[q], (int)log_h);
         E5 norm = bb::e5_neg(bb::e5_mul_base(bb::e5_sub_base(zh, sh), denom_inv));
         for (uint32_t c = 0; c < w; c++) {
-            E5 S;
-            for (int l = 0; l < 5; l++) S.c[l] = hp[((size_t)c * npoints + q) * 5 + l];
+            E5 D;   // sum_i p_c(x_i) / (x_i - z_q)
+            for (int l = 0; l < 5; l++) D.c[l] = hp[(size_t)c * BARY_OUT + q * 5 + l];
+            const E5 S = bb::e5_add_base(bb::e5_mul(z[q], D), hp[(size_t)c * BARY_OUT + 10]);
             (*ys)[(size_t)q * w + c] = bb::e5_mul(S, norm);
         }
     }
