@@ -10,7 +10,7 @@ def rand_mat(rng, h, w):
     return rng.integers(0, P, size=(h, w), dtype=np.uint32)
 
 
-@pytest.mark.parametrize("log_h,w", [(0, 1), (1, 3), (2, 2), (5, 7), (8, 51), (10, 16), (12, 5), (13, 3), (14, 2), (16, 4), (17, 3)])
+@pytest.mark.parametrize("log_h,w", [(0, 1), (1, 3), (2, 2), (5, 7), (8, 51), (10, 16), (12, 5), (13, 3), (14, 2), (16, 4), (17, 3), (18, 2), (22, 2), (23, 1)])
 def test_ntt_forward_inverse_bit_exact(ctx, oracle, log_h, w):
     import valida_b200 as vb
 
@@ -45,7 +45,7 @@ def test_ntt_monty_repr_and_host_entry(ctx, oracle):
     assert np.array_equal(buf, oracle.dft(m))
 
 
-@pytest.mark.parametrize("log_h,w,shift", [(0, 2, 31), (1, 1, 31), (3, 4, 31), (9, 14, 31), (12, 3, 31), (13, 5, 31), (15, 2, 7), (16, 2, pow(31, P - 2, P))])
+@pytest.mark.parametrize("log_h,w,shift", [(0, 2, 31), (1, 1, 31), (3, 4, 31), (9, 14, 31), (12, 3, 31), (13, 5, 31), (15, 2, 7), (16, 2, pow(31, P - 2, P)), (18, 3, 31), (20, 2, 31), (22, 2, 31), (23, 1, 961)])
 def test_coset_lde_bit_exact(ctx, oracle, log_h, w, shift):
     import valida_b200 as vb
 

@@ -142,3 +142,18 @@ def test_prove_config5_program(ctx, oracle):
     assert t2.main[0].shape[0] == 1 << 18
     p2 = gpu_prove(ctx, oracle, t2)
     assert oracle.verify(p2, t2.preprocessed) == 0
+
+
+def test_prove_full_size_2p22_verifies(ctx, oracle):
+    """BASELINE config 3 at full size (Fibonacci, 2^22 CPU rows, 2^24 memory rows): both verifiers accept the proof,
+    and a second run yields the same bytes (the proof is a pure function of the traces and the challenger)."""
+    import valida_b200 as vb
+
+    n = ((1 << 22) - 17) // 7
+    t = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
+    assert t.main[0].shape[0] == 1 << 22 and t.main[2].shape[0] == 1 << 24
+    cfg = vb.StarkConfig(ctx, oracle.rc480)
+    proof = vb.prove_machine(cfg, t)
+    assert oracle.verify(proof, t.preprocessed) == 0
+    vb.verify_machine(cfg, proof, t.preprocessed)
+    assert vb.prove_machine(cfg, t) == proof

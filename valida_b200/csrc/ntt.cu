@@ -142,6 +142,157 @@ __device__ __forceinline__ void all_stages(uint32_t* data, const uint32_t* tw, u
     }
 }
 
+// ---- standard-shape tile movement ---------------------------------------------------------------------------
+// Every pass over a column longer than one tile runs 512 threads on a tile of exactly 2^14 elements
+// (T = 2^(14 - LOG_LEN) sub-transforms of length L).  For that shape the per-thread sequence of 32 elements is a
+// compile-time pattern: one base address / base slot per thread, everything else immediates (bit reversals of the
+// step counter, padded-slot corrections, group pitches).  The generic index arithmetic below these helpers remains
+// for short columns and unusual shapes.  (ncu, profiles/r01_summary.md: the generic paths cost 45 - 90 executed
+// instructions per element, more than the butterflies.)
+__host__ __device__ constexpr uint32_t cbrev(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+template <int LOG_LEN> struct Std {
+    static constexpr int LOG_T = 14 - LOG_LEN;
+    static constexpr uint32_t T = 1u << (LOG_T > 0 ? LOG_T : 0), L = 1u << LOG_LEN;
+    static constexpr uint32_t LS = (L + (L >> 4) + (L >> 9)) | 1;
+    static constexpr int LR0 = LOG_LEN - 5;      // strided ("column") view: 2^LR0 rows per step, 32 steps
+    static constexpr int LB = LOG_LEN - 9;       // contiguous ("row") view: 2^LB steps of 512 per sub-transform
+};
+// padded slot of (B << 5) + c, c < 32, relative to the B part
+__device__ __forceinline__ constexpr uint32_t off_b5(uint32_t c) { return c + (c >> 4); }
+// strided view, natural slots r0 + (k << LR0), r0 < 2^LR0 <= 2^7: offset of step k
+template <int LR0> __device__ __forceinline__ constexpr uint32_t off_strided(uint32_t k) {
+    return (k << LR0) + (LR0 >= 4 ? (k << (LR0 >= 4 ? LR0 - 4 : 0)) : (k >> (LR0 < 4 ? 4 - LR0 : 0))) + (k >> (9 - LR0));
+}
+template <int LR0> __device__ __forceinline__ uint32_t base_strided(uint32_t r0) { return r0 + (LR0 >= 4 ? (r0 >> 4) : 0u); }
+// contiguous view, bit-reversed slots (B << LB) + c with B = bitrev9(tid), c < 2^LB
+template <int LB> __device__ __forceinline__ uint32_t base_rowrev(uint32_t B) { return (B << LB) + ((B << LB) >> 4) + (B >> (9 - LB)); }
+template <int LB> __device__ __forceinline__ constexpr uint32_t off_rowrev(uint32_t c) { return c + (LB >= 4 ? (c >> 4) : 0u); }
+
+// strided load (src_gs == 1): element r of sub-transform g0 + tt at src[r * src_rs + g0 + tt]
+template <int LOG_LEN, bool BITREV>
+__device__ __forceinline__ void load_strided_std(const PassParams& p, const uint32_t* __restrict__ src, uint32_t* __restrict__ data, uint64_t g0, uint32_t tid) {
+    using S = Std<LOG_LEN>;
+    const uint32_t tt = tid & (S::T - 1), r0 = tid >> S::LOG_T;
+    const uint32_t* g = src + g0 + tt + (uint64_t)r0 * p.src_rs;
+    const uint64_t ks = p.src_rs << S::LR0;
+    uint32_t* sl;
+    if (BITREV) { const uint32_t B = bb::reverse_bits(r0, S::LR0); sl = data + tt * S::LS + (B << 5) + (B << 1) + (B >> 4); }
+    else sl = data + tt * S::LS + base_strided<S::LR0>(r0);
+#pragma unroll
+    for (int kb = 0; kb < 32; kb += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = __ldg(g + (uint64_t)(kb + u) * ks);
+#pragma unroll
+        for (int u = 0; u < 8; u++) sl[BITREV ? off_b5(cbrev(kb + u, 5)) : off_strided<S::LR0>(kb + u)] = v[u];
+    }
+}
+// contiguous load (src_rs == 1): sub-transform g at src[g * src_gs + r]
+template <int LOG_LEN, bool BITREV>
+__device__ __forceinline__ void load_rows_std(const PassParams& p, const uint32_t* __restrict__ src, uint32_t* __restrict__ data, uint64_t g0, uint32_t tid) {
+    using S = Std<LOG_LEN>;
+    constexpr uint32_t I = 1u << S::LB;
+    const uint32_t sb = BITREV ? base_rowrev<S::LB>(bb::reverse_bits(tid, 9)) : tid + (tid >> 4);
+#pragma unroll
+    for (uint32_t t = 0; t < S::T; t++) {
+        const uint32_t* g = src + (g0 + t) * p.src_gs + tid;
+        uint32_t* sl = data + t * S::LS + sb;
+#pragma unroll
+        for (uint32_t kb = 0; kb < I; kb += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8 && kb + u < I; u++) v[u] = __ldg(g + 512 * (kb + u));
+#pragma unroll
+            for (uint32_t u = 0; u < 8 && kb + u < I; u++) sl[BITREV ? off_rowrev<S::LB>(cbrev(kb + u, S::LB)) : (kb + u) * 545u] = v[u];
+        }
+    }
+}
+
+// multiplier state of one thread-local output sequence (natural output index k = k_start + i * k_stride)
+__device__ __forceinline__ void post_begin(const PassParams& p, uint32_t gval, uint32_t k_start, uint32_t k_stride, uint32_t* m, uint32_t* step) {
+    if (p.post_mode == 1) {
+        uint32_t e0 = (gval * k_start) << p.post_shift, es = (gval * k_stride) << p.post_shift;
+        if (p.inverse) { e0 = 0u - e0; es = 0u - es; }
+        *m = root_pow(p, e0); *step = root_pow(p, es);
+    } else if (p.post_mode == 2) {
+        const uint32_t e0 = gval * p.post_g + k_start * p.post_k;
+        *m = mul(__ldg(p.tab_lo + (e0 & (VG_POW_LO - 1))), __ldg(p.tab_hi + (e0 >> VG_POW_LO_BITS)));
+        *step = p.tab_step;
+    } else { *m = p.post_mode == 3 ? p.post_scale : bb::R1; *step = bb::R1; }
+}
+// contiguous store (dst_rs == 1), L >= 512: thread positions tid + 512 j of every sub-transform of the tile
+template <int LOG_LEN, bool NAT>
+__device__ __forceinline__ void store_rows_std(const PassParams& p, uint32_t* __restrict__ dst, const uint32_t* __restrict__ data, uint64_t g0, uint32_t tid) {
+    using S = Std<LOG_LEN>;
+    constexpr uint32_t I = 1u << S::LB;
+    const uint32_t B = bb::reverse_bits(tid, 9);
+    const uint32_t sb = NAT ? base_rowrev<S::LB>(B) : tid + (tid >> 4);
+    const bool running = p.post_mode == 1 || p.post_mode == 2;
+#pragma unroll
+    for (uint32_t t = 0; t < S::T; t++) {
+        const uint32_t g = (uint32_t)g0 + t;
+        const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+        uint32_t m, step;
+        post_begin(p, gval, NAT ? tid : (B << S::LB), NAT ? 512u : 1u, &m, &step);
+        uint32_t* d = dst + (uint64_t)g * p.dst_gs + tid;
+        const uint32_t* sl = data + t * S::LS + sb;
+#pragma unroll
+        for (uint32_t i = 0; i < I; i++) {
+            // raw order: the i-th natural output of this thread sits at position tid + 512 * bitrev(i)
+            const uint32_t j = NAT ? i : cbrev(i, S::LB);
+            const uint32_t v = sl[NAT ? off_rowrev<S::LB>(cbrev(i, S::LB)) : j * 545u];
+            d[512 * j] = p.post_mode ? mul(v, m) : v;
+            if (running) m = mul(m, step);
+        }
+    }
+}
+// contiguous store (dst_rs == 1) of short sub-transforms (L < 512), no running multiplier: position tid & (L-1) of
+// sub-transforms (tid >> LOG_LEN) + k * (512 / L)
+template <int LOG_LEN, bool NAT>
+__device__ __forceinline__ void store_short_rows_std(const PassParams& p, uint32_t* __restrict__ dst, const uint32_t* __restrict__ data, uint64_t g0, uint32_t tid) {
+    using S = Std<LOG_LEN>;
+    constexpr uint32_t GPS = 512u >> LOG_LEN;           // sub-transforms per step
+    const uint32_t pos = tid & (S::L - 1), t0 = tid >> LOG_LEN;
+    const uint32_t q = NAT ? bb::reverse_bits(pos, LOG_LEN) : pos;
+    uint32_t* d = dst + (g0 + t0) * p.dst_gs + pos;
+    const uint64_t ks = p.dst_gs * GPS;
+    const uint32_t* sl = data + t0 * S::LS + pad(q);
+#pragma unroll
+    for (uint32_t kb = 0; kb < 32; kb += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) v[u] = sl[(kb + u) * GPS * S::LS];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) d[(uint64_t)(kb + u) * ks] = p.post_mode == 3 ? mul(v[u], p.post_scale) : v[u];
+    }
+}
+// strided store (dst_gs == 1): output position pos of sub-transform g at dst[pos * dst_rs + g]
+template <int LOG_LEN, bool NAT>
+__device__ __forceinline__ void store_strided_std(const PassParams& p, uint32_t* __restrict__ dst, const uint32_t* __restrict__ data, uint64_t g0, uint32_t tid) {
+    using S = Std<LOG_LEN>;
+    const uint32_t tt = tid & (S::T - 1), r0 = tid >> S::LOG_T;
+    const uint32_t g = (uint32_t)g0 + tt;
+    const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+    const uint32_t Bq = bb::reverse_bits(r0, S::LR0);
+    uint32_t m, step;
+    post_begin(p, gval, NAT ? r0 : (Bq << 5), NAT ? (1u << S::LR0) : 1u, &m, &step);
+    const bool running = p.post_mode == 1 || p.post_mode == 2;
+    uint32_t* d = dst + g + (uint64_t)r0 * p.dst_rs;
+    const uint64_t ks = p.dst_rs << S::LR0;
+    const uint32_t* sl = data + tt * S::LS + (NAT ? (Bq << 5) + (Bq << 1) + (Bq >> 4) : base_strided<S::LR0>(r0));
+#pragma unroll
+    for (uint32_t i = 0; i < 32; i++) {
+        const uint32_t j = NAT ? i : cbrev(i, 5);       // position r0 + (j << LR0); its natural index advances by k_stride with i
+        const uint32_t v = sl[NAT ? off_b5(cbrev(i, 5)) : off_strided<S::LR0>(j)];
+        d[(uint64_t)j * ks] = p.post_mode ? mul(v, m) : v;
+        if (running) m = mul(m, step);
+    }
+}
+
 // One CTA = one tile of `tile` sub-transforms of one column.  grid.x = tiles_per_col, grid.y = column.
 template <int LOG_LEN>
 __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
@@ -165,10 +316,28 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
             tw[j + (j >> 5)] = __ldg(p.root_hi + (e >> VG_POW_LO_BITS));
         }
     }
-    // ---- load (4 independent global loads in flight per thread) ----
+    // ---- load ----
     const uint32_t total = L * T;
     const uint32_t log_t = 31 - __clz(T);
-    {
+    bool std_shape = false, loaded = false;
+    if constexpr (LOG_LEN >= 8 && LOG_LEN <= 14) {
+        std_shape = (T == Std<LOG_LEN>::T) && nt == 512;
+        if (std_shape && !p.pre_mode) {
+            if constexpr (LOG_LEN <= 12) {
+                if (p.src_gs == 1) {
+                    if (p.src_bitrev) load_strided_std<LOG_LEN, true>(p, src, data, g0, tid); else load_strided_std<LOG_LEN, false>(p, src, data, g0, tid);
+                    loaded = true;
+                }
+            }
+            if constexpr (LOG_LEN >= 9) {
+                if (!loaded && p.src_rs == 1 && p.src_gs != 1) {
+                    if (p.src_bitrev) load_rows_std<LOG_LEN, true>(p, src, data, g0, tid); else load_rows_std<LOG_LEN, false>(p, src, data, g0, tid);
+                    loaded = true;
+                }
+            }
+        }
+    }
+    if (!loaded) {   // generic shapes: 4 independent global loads in flight per thread
         const bool tfast = (p.src_gs == 1);
         const uint32_t log_nt = 31 - __clz(nt);
         if (p.pre_mode && p.src_bitrev && !tfast && L >= 4 * nt) {
@@ -231,7 +400,29 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     // output index k is then K0 + kk (raw order, kk = bitrev(j)) or p0 + (j << lowbits) (natural order): an
     // arithmetic progression, so the twiddle / coset multiplier is a running product (one multiply per
     // element, no table lookups, no per-element exponent arithmetic).
-    {
+    bool stored = false;
+    if constexpr (LOG_LEN >= 8 && LOG_LEN <= 14) {
+        if (std_shape) {
+            if constexpr (LOG_LEN <= 12) {
+                if (p.dst_gs == 1) {
+                    if (p.dst_natural) store_strided_std<LOG_LEN, true>(p, dst, data, g0, tid); else store_strided_std<LOG_LEN, false>(p, dst, data, g0, tid);
+                    stored = true;
+                }
+            }
+            if (!stored && p.dst_rs == 1 && p.dst_gs != 1) {
+                if constexpr (LOG_LEN >= 9) {
+                    if (p.dst_natural) store_rows_std<LOG_LEN, true>(p, dst, data, g0, tid); else store_rows_std<LOG_LEN, false>(p, dst, data, g0, tid);
+                    stored = true;
+                } else {
+                    if (p.post_mode == 0 || p.post_mode == 3) {
+                        if (p.dst_natural) store_short_rows_std<LOG_LEN, true>(p, dst, data, g0, tid); else store_short_rows_std<LOG_LEN, false>(p, dst, data, g0, tid);
+                        stored = true;
+                    }
+                }
+            }
+        }
+    }
+    if (!stored) {
         const bool tfast = (p.dst_gs == 1);
         const uint32_t log_nt = 31 - __clz(nt);
         const bool fast = tfast ? (nt >= T && log_nt - log_t <= (uint32_t)LOG_LEN) : (L >= nt);
