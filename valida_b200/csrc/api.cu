@@ -128,6 +128,7 @@ void vgpu_ctx_destroy(vgpu_ctx* ctx) {
         for (auto& kv : ctx->free_bufs) cudaFree(kv.second);
         for (auto& kv : ctx->live_bufs) cudaFree(kv.first);
         for (auto e : ctx->event_pool) cudaEventDestroy(e);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -165,6 +166,7 @@ int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, v
     return 0;
 }
 int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint32_t* host_row_major_out) {
+    VG_TRY(vg_dmat_materialize(ctx, m));
     VG_TRY(vg_download_rowmajor(ctx, m, repr, host_row_major_out));
     if (m->bitrev_rows && m->h > 1) {   // present the logical (natural) row order to the caller
         int lg = 0; while ((1ull << lg) < m->h) lg++;
@@ -182,6 +184,11 @@ int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint
 int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width) { *height = m->h; *width = m->w; return 0; }
 void vgpu_dmat_free(vgpu_dmat* m) {
     if (!m) return;
+    if (m->pend_stage) {   // an upload that was never consumed: let the copy finish, then release
+        cudaEventSynchronize(m->pend_ev);
+        vg_free(m->ctx, m->pend_stage);
+        m->ctx->event_pool.push_back(m->pend_ev);
+    }
     if (m->owns) vg_free(m->ctx, m->d);
     delete m;
 }
@@ -194,6 +201,7 @@ int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
     if (log_n > VG_LOG_NMAX) VG_FAIL(ctx, "ntt_batch: height exceeds two-adicity");
     if (log_n > 24) VG_FAIL(ctx, "ntt_batch: heights above 2^24 need a three-pass split (not built yet)");
     if (m->bitrev_rows) VG_FAIL(ctx, "ntt_batch: matrix rows are stored bit-reversed");
+    VG_TRY(vg_dmat_materialize(ctx, m));
     uint32_t* tmp = nullptr;
     VG_TRY(vg_alloc(ctx, (void**)&tmp, m->h * m->w * 4));
     int32_t rc = vg_ntt_nat2nat(ctx, m->d, m->col_stride, m->d, m->col_stride, log_n, m->w, inverse != 0, nullptr, tmp, m->h);
@@ -203,6 +211,7 @@ int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
 
 int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_blowup, uint32_t shift_canonical, int32_t bit_reversed, vgpu_dmat** out) {
     if (log_blowup != 1) VG_FAIL(ctx, "coset_lde: only log_blowup = 1 (FriConfig of basic/src/bin/valida.rs:385-390) is built");
+    VG_TRY(vg_dmat_materialize(ctx, in));
     vgpu_dmat* o = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, in->h * 2, in->w, &o));
     int32_t rc = vg_coset_lde(ctx, in->d, in->col_stride, in->h, in->w, shift_canonical, o->d, o->col_stride, bit_reversed != 0, in->bitrev_rows);
@@ -227,40 +236,48 @@ int32_t vgpu_commit_batches(vgpu_ctx* ctx, const vgpu_dmat* const* mats, uint32_
     vgpu_prover_data* pd = new (std::nothrow) vgpu_prover_data();
     if (!pd) VG_FAIL(ctx, "out of host memory");
     pd->ctx = ctx;
-    int32_t rc = 0;
     const bool sharded = vg_sharded(ctx);
-    for (uint32_t i = 0; i < n && rc == 0; i++) {
-        // TwoAdicFriPcs::commit_shifted_batches: shift = generator / coset_shift_i; LDE; bit-reverse rows
-        uint32_t cs = coset_shifts_or_null ? coset_shifts_or_null[i] : 1;
-        uint32_t shift = bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
-        vgpu_dmat* lde = nullptr;
-        if (!sharded) {
-            rc = vgpu_coset_lde_batch(ctx, mats[i], 1, shift, 1, &lde);
-        } else {
-            // this rank extends only its share of the columns; the other shares arrive in the exchange below
-            uint64_t c0, c1;
-            vg_shard_range(mats[i]->w, ctx->comm_size, ctx->comm_rank, &c0, &c1);
-            rc = vg_dmat_alloc(ctx, mats[i]->h * 2, mats[i]->w, &lde);
-            if (rc == 0 && c1 > c0)
-                rc = vg_coset_lde(ctx, mats[i]->d + c0 * mats[i]->col_stride, mats[i]->col_stride, mats[i]->h, c1 - c0, shift,
-                                  lde->d + c0 * lde->col_stride, lde->col_stride, true, mats[i]->bitrev_rows);
-            if (rc && lde) { vgpu_dmat_free(lde); lde = nullptr; }
-        }
-        if (rc == 0) pd->ldes.push_back(lde);
+    pd->ldes.assign(n, nullptr);
+    std::vector<uint64_t> heights(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!mats[i]) { vgpu_prover_data_free(pd); VG_FAIL(ctx, "commit: matrix %u is null", i); }
+        heights[i] = mats[i]->h * 2;
     }
-    if (rc == 0 && sharded) {
-        // exchange of the column shares: one NCCL group, a broadcast per (matrix, owner) — shares are contiguous
-        // runs of whole columns in the column-major LDE
-        rc = vg_comm_group_begin(ctx);
-        for (uint32_t i = 0; i < n && rc == 0; i++)
-            for (int r = 0; r < ctx->comm_size && rc == 0; r++) {
+    // One height group at a time, when the tree reaches that height: TwoAdicFriPcs::commit_shifted_batches for the group
+    // (shift = generator / coset_shift_i; LDE; bit-reversed rows).  A matrix whose upload is still in flight is waited
+    // for here, not earlier.
+    auto extend_group = [&](const std::vector<size_t>& group) -> int32_t {
+        for (size_t i : group) {
+            VG_TRY(vg_dmat_materialize(ctx, mats[i]));
+            uint32_t cs = coset_shifts_or_null ? coset_shifts_or_null[i] : 1;
+            uint32_t shift = bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
+            if (!sharded) {
+                VG_TRY(vgpu_coset_lde_batch(ctx, mats[i], 1, shift, 1, &pd->ldes[i]));
+            } else {
+                // this rank extends only its share of the columns; the other shares arrive in the exchange below
                 uint64_t c0, c1;
-                vg_shard_range(pd->ldes[i]->w, ctx->comm_size, r, &c0, &c1);
-                rc = vg_comm_bcast(ctx, pd->ldes[i]->d + c0 * pd->ldes[i]->col_stride, (c1 - c0) * pd->ldes[i]->col_stride, r);
+                vg_shard_range(mats[i]->w, ctx->comm_size, ctx->comm_rank, &c0, &c1);
+                VG_TRY(vg_dmat_alloc(ctx, mats[i]->h * 2, mats[i]->w, &pd->ldes[i]));
+                if (c1 > c0)
+                    VG_TRY(vg_coset_lde(ctx, mats[i]->d + c0 * mats[i]->col_stride, mats[i]->col_stride, mats[i]->h, c1 - c0, shift,
+                                        pd->ldes[i]->d + c0 * pd->ldes[i]->col_stride, pd->ldes[i]->col_stride, true, mats[i]->bitrev_rows));
             }
-        if (rc == 0) rc = vg_comm_group_end(ctx);
-    }
-    if (rc == 0) rc = vg_merkle_build(ctx, pd);
+        }
+        if (sharded) {
+            // exchange of the column shares: one NCCL group per height group, a broadcast per (matrix, owner) — shares
+            // are contiguous runs of whole columns in the column-major LDE
+            VG_TRY(vg_comm_group_begin(ctx));
+            for (size_t i : group)
+                for (int r = 0; r < ctx->comm_size; r++) {
+                    uint64_t c0, c1;
+                    vg_shard_range(pd->ldes[i]->w, ctx->comm_size, r, &c0, &c1);
+                    VG_TRY(vg_comm_bcast(ctx, pd->ldes[i]->d + c0 * pd->ldes[i]->col_stride, (c1 - c0) * pd->ldes[i]->col_stride, r));
+                }
+            VG_TRY(vg_comm_group_end(ctx));
+        }
+        return 0;
+    };
+    int32_t rc = vg_merkle_build(ctx, pd, heights, extend_group);
     if (rc) { vgpu_prover_data_free(pd); return rc; }
     if (digest_out) std::memcpy(digest_out, pd->root, 32);
     *out = pd;

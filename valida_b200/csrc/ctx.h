@@ -52,6 +52,7 @@ struct vgpu_ctx {
     void* nccl = nullptr;                                        // ncclComm_t
     int comm_rank = 0, comm_size = 1;
     bool sharding = false;                                       // commit / FRI-commit work split across ranks
+    cudaStream_t copy_stream = nullptr;                         // H2D copies of a pipelined vgpu_prove (staging.cu)
     bool ktiming = false;
     std::vector<KTimer> ktimers;
     std::vector<cudaEvent_t> event_pool;
@@ -63,6 +64,11 @@ struct vgpu_dmat {
     uint64_t h = 0, w = 0, col_stride = 0;
     bool owns = true;
     bool bitrev_rows = false;    // row r of the logical matrix is stored at reverse_bits(r) (quotient-chunk output order)
+    // pipelined upload: the row-major image is (being) copied into pend_stage on the copy stream; the transpose into
+    // `d` runs on the context's stream at first use (vg_dmat_materialize)
+    uint32_t* pend_stage = nullptr;
+    cudaEvent_t pend_ev = nullptr;
+    int32_t pend_repr = 0;
 };
 
 #define VG_FAIL(ctx, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (ctx)->err = _b; return -1; } while (0)
@@ -107,5 +113,7 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
 int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64_t h, uint64_t w, uint32_t shift_canonical,
                      uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev = false);
 // staging.cu
+int32_t vg_upload_begin(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);   // async copy only
+int32_t vg_dmat_materialize(vgpu_ctx* ctx, const vgpu_dmat* m);                                                       // no-op unless an upload is pending
 int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);
 int32_t vg_download_rowmajor(vgpu_ctx* ctx, const vgpu_dmat* src, int32_t repr, uint32_t* host);

@@ -9,6 +9,7 @@
 #include "../open.h"
 #include "../devchip.h"
 #include "challenger.h"
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cstring>
@@ -449,15 +450,24 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
 
 int32_t vgpu_prove(vgpu_ctx* ctx, const vgpu_matrix main[VGPU_NUM_CHIPS], const vgpu_matrix prep[2], int32_t repr,
                    uint8_t** proof_out, uint64_t* proof_len) {
+    // Host-buffer entry: the H2D copies run on a copy stream in the order the commits consume the traces (preprocessed,
+    // then main traces tallest first — the Merkle tree hashes the tallest LDEs first and extends the shorter matrices
+    // only when a tree layer of their height is reached), each transpose is deferred to the matrix's first use, so
+    // copies of later matrices overlap the LDE / Keccak kernels of earlier ones.
     MatGuard dm, dp;
     ctx->phases.clear();
     auto t0 = std::chrono::steady_clock::now();
-    for (int i = 0; i < VGPU_NUM_CHIPS; i++) { vgpu_dmat* m = nullptr; VG_TRY(vgpu_dmat_upload(ctx, &main[i], repr, &m)); dm.v.push_back(m); }
-    for (int i = 0; i < 2; i++) { vgpu_dmat* m = nullptr; VG_TRY(vgpu_dmat_upload(ctx, &prep[i], repr, &m)); dp.v.push_back(m); }
-    cudaStreamSynchronize(ctx->stream);
+    dm.v.assign(VGPU_NUM_CHIPS, nullptr); dp.v.assign(2, nullptr);
+    for (int i = 0; i < 2; i++) VG_TRY(vg_dmat_alloc(ctx, prep[i].height, prep[i].width, &dp.v[i]));
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) VG_TRY(vg_dmat_alloc(ctx, main[i].height, main[i].width, &dm.v[i]));
+    for (int i = 0; i < 2; i++) VG_TRY(vg_upload_begin(ctx, prep[i].data, prep[i].height, prep[i].width, repr, dp.v[i]));
+    std::vector<int> order(VGPU_NUM_CHIPS);
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return main[a].height > main[b].height; });
+    for (int i : order) VG_TRY(vg_upload_begin(ctx, main[i].data, main[i].height, main[i].width, repr, dm.v[i]));
     float up = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     int32_t rc = vgpu_prove_device(ctx, dm.v.data(), dp.v.data(), proof_out, proof_len);
-    ctx->phases.insert(ctx->phases.begin(), {"upload traces (H2D + transpose)", up});
+    ctx->phases.insert(ctx->phases.begin(), {"upload traces (H2D enqueue; copies overlap the commits)", up});
     return rc;
 }
 

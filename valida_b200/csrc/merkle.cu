@@ -185,21 +185,34 @@ int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint6
     return 0;
 }
 
-// Build the mixed-height tree over the (already bit-reversed) LDE matrices in `pd->ldes`.
-int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd) {
-    size_t n = pd->ldes.size();
+// Build the mixed-height tree over the bit-reversed LDE matrices of `pd` (see merkle.h for `need`).
+int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd, const std::vector<uint64_t>& heights,
+                        const std::function<int32_t(const std::vector<size_t>&)>& need) {
+    size_t n = heights.size();
     if (!n) VG_FAIL(ctx, "commit: no matrices");
     std::vector<size_t> order(n);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pd->ldes[a]->h > pd->ldes[b]->h; });
-    uint64_t max_h = pd->ldes[order[0]]->h;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return heights[a] > heights[b]; });
+    uint64_t max_h = heights[order[0]];
     if (max_h & (max_h - 1)) VG_FAIL(ctx, "commit: heights must be powers of two");
     pd->max_height = max_h;
     // all layers in one allocation: max_h + max_h/2 + ... + 1 = 2*max_h - 1 digests
     VG_TRY(vg_alloc(ctx, (void**)&pd->digests, (2 * max_h) * 32));
     size_t pos = 0;
+    std::vector<size_t> idx;
     std::vector<const vgpu_dmat*> group;
-    while (pos < n && pd->ldes[order[pos]]->h == max_h) group.push_back(pd->ldes[order[pos++]]);
+    auto take = [&](uint64_t height) -> int32_t {   // the matrices of that height, extended on demand
+        idx.clear(); group.clear();
+        while (pos < n && heights[order[pos]] == height) idx.push_back(order[pos++]);
+        if (idx.empty()) return 0;
+        if (need) VG_TRY(need(idx));
+        for (size_t i : idx) {
+            if (!pd->ldes[i] || pd->ldes[i]->h != height) VG_FAIL(ctx, "commit: matrix %zu was not extended to height %llu", i, (unsigned long long)height);
+            group.push_back(pd->ldes[i]);
+        }
+        return 0;
+    };
+    VG_TRY(take(max_h));
     uint32_t* layer = pd->digests;
     pd->layer_ptr.clear(); pd->layer_len.clear();
     pd->layer_ptr.push_back(layer); pd->layer_len.push_back(max_h);
@@ -213,8 +226,7 @@ int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd) {
         uint64_t next_len = len / 2;
         sh = share_of(ctx, next_len);
         if (!sh.split && !gathered) { VG_TRY(gather_split_layers(ctx, pd->layer_ptr, pd->layer_len, 0, n_split)); gathered = true; }
-        group.clear();
-        while (pos < n && pd->ldes[order[pos]]->h == next_len) group.push_back(pd->ldes[order[pos++]]);
+        VG_TRY(take(next_len));
         const uint32_t* inj = nullptr;
         if (!group.empty()) {
             if (!inject_buf) VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (max_h / 2) * 32));

@@ -212,6 +212,34 @@ __device__ __forceinline__ void load_rows_std(const PassParams& p, const uint32_
     }
 }
 
+// contiguous load of bit-reversed-ordered coefficients with the odd-coset pre-multiplier w^((rnat*pre_r + gval*pre_g) << pre_shift):
+// memory position tid + 512 * bitrev(i) holds natural index rnat = (bitrev9(tid) << LB) + i, so walking i upwards turns the
+// multiplier into a running product (one multiply per element, no table lookups)
+template <int LOG_LEN>
+__device__ __forceinline__ void load_rows_odd_std(const PassParams& p, const uint32_t* __restrict__ src, uint32_t* __restrict__ data, uint64_t g0, uint32_t tid) {
+    using S = Std<LOG_LEN>;
+    constexpr uint32_t I = 1u << S::LB;
+    const uint32_t B = bb::reverse_bits(tid, 9);
+    const uint32_t sb = base_rowrev<S::LB>(B);
+    const uint32_t step = root_pow(p, p.pre_r << p.pre_shift);
+#pragma unroll
+    for (uint32_t t = 0; t < S::T; t++) {
+        const uint32_t g = (uint32_t)g0 + t;
+        const uint32_t gval = p.g_bits ? bb::reverse_bits(g, (int)p.g_bits) : g;
+        uint32_t m = root_pow(p, (((B << S::LB) * p.pre_r) + gval * p.pre_g) << p.pre_shift);
+        const uint32_t* gp = src + (uint64_t)g * p.src_gs + tid;
+        uint32_t* sl = data + t * S::LS + sb;
+#pragma unroll
+        for (uint32_t ib = 0; ib < I; ib += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8 && ib + u < I; u++) v[u] = __ldg(gp + 512 * cbrev(ib + u, S::LB));
+#pragma unroll
+            for (uint32_t u = 0; u < 8 && ib + u < I; u++) { sl[off_rowrev<S::LB>(ib + u)] = mul(v[u], m); m = mul(m, step); }
+        }
+    }
+}
+
 // multiplier state of one thread-local output sequence (natural output index k = k_start + i * k_stride)
 __device__ __forceinline__ void post_begin(const PassParams& p, uint32_t gval, uint32_t k_start, uint32_t k_stride, uint32_t* m, uint32_t* step) {
     if (p.post_mode == 1) {
@@ -322,6 +350,9 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     bool std_shape = false, loaded = false;
     if constexpr (LOG_LEN >= 8 && LOG_LEN <= 14) {
         std_shape = (T == Std<LOG_LEN>::T) && nt == 512;
+        if constexpr (LOG_LEN >= 9) {
+            if (std_shape && p.pre_mode && p.src_bitrev && p.src_rs == 1 && p.src_gs != 1) { load_rows_odd_std<LOG_LEN>(p, src, data, g0, tid); loaded = true; }
+        }
         if (std_shape && !p.pre_mode) {
             if constexpr (LOG_LEN <= 12) {
                 if (p.src_gs == 1) {

@@ -212,6 +212,8 @@ extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, co
         // interactions of BasicMachine never read preprocessed columns, but the shape must still be coherent when given
         if (prep_or_null) VG_FAIL(ctx, "perm_trace: preprocessed trace shape mismatch");
     }
+    VG_TRY(vg_dmat_materialize(ctx, main));
+    VG_TRY(vg_dmat_materialize(ctx, prep_or_null));
     DevChip* dchip = nullptr;
     VG_TRY(vg_upload_devchip(ctx, chip, challenges, &dchip));
     uint64_t h = main->h;

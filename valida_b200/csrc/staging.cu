@@ -40,19 +40,50 @@ __global__ void __launch_bounds__(256) cm_to_rm_kernel(const uint32_t* __restric
 }
 }  // namespace
 
-int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst) {
-    if (h == 0 || w == 0) return 0;
-    uint32_t* stage = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&stage, h * w * 4));
-    VG_CUDA(ctx, cudaMemcpyAsync(stage, host, h * w * 4, cudaMemcpyHostToDevice, ctx->stream));
+static int32_t transpose_in(vgpu_ctx* ctx, const uint32_t* stage, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst) {
     for (uint64_t c0 = 0; c0 < w; c0 += TW) {
         uint32_t wc = (uint32_t)(w - c0 < TW ? w - c0 : TW);
         KScope ks(ctx, KC_TRANSPOSE, 8.0 * (double)h * wc);
         rm_to_cm_kernel<<<(unsigned)((h + TR - 1) / TR), 256, 0, ctx->stream>>>(stage, h, w, dst->d, dst->col_stride, repr == VGPU_REPR_CANONICAL, c0, wc);
         VG_LAUNCH_CHECK(ctx);
     }
-    vg_free(ctx, stage);
     return 0;
+}
+
+int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst) {
+    if (h == 0 || w == 0) return 0;
+    uint32_t* stage = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&stage, h * w * 4));
+    VG_CUDA(ctx, cudaMemcpyAsync(stage, host, h * w * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = transpose_in(ctx, stage, h, w, repr, dst);
+    vg_free(ctx, stage);
+    return rc;
+}
+
+// Pipelined form used by vgpu_prove: the copy is queued on the context's copy stream (so it overlaps the kernels of
+// matrices that arrived earlier) and the transpose is deferred to the matrix's first use on the compute stream.
+int32_t vg_upload_begin(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst) {
+    if (h == 0 || w == 0) return 0;
+    if (!ctx->copy_stream) VG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    VG_TRY(vg_alloc(ctx, (void**)&dst->pend_stage, h * w * 4));
+    VG_CUDA(ctx, cudaMemcpyAsync(dst->pend_stage, host, h * w * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (!ctx->event_pool.empty()) { dst->pend_ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else VG_CUDA(ctx, cudaEventCreate(&dst->pend_ev));
+    VG_CUDA(ctx, cudaEventRecord(dst->pend_ev, ctx->copy_stream));
+    dst->pend_repr = repr;
+    return 0;
+}
+
+int32_t vg_dmat_materialize(vgpu_ctx* ctx, const vgpu_dmat* cm) {
+    vgpu_dmat* m = const_cast<vgpu_dmat*>(cm);   // completing a pending upload does not change the matrix's value
+    if (!m || !m->pend_stage) return 0;
+    VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->pend_ev, 0));
+    int32_t rc = transpose_in(ctx, m->pend_stage, m->h, m->w, m->pend_repr, m);
+    vg_free(ctx, m->pend_stage);                 // reused only by later work on the compute stream, i.e. after the transpose
+    m->pend_stage = nullptr;
+    ctx->event_pool.push_back(m->pend_ev);
+    m->pend_ev = nullptr;
+    return rc;
 }
 
 int32_t vg_download_rowmajor(vgpu_ctx* ctx, const vgpu_dmat* src, int32_t repr, uint32_t* host) {
