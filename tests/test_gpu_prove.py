@@ -46,7 +46,7 @@ def test_prove_device_resident_entry_matches_host_entry(ctx, oracle):
     dp = [ctx.upload(m) for m in t.preprocessed]
     assert vb.prove_machine(cfg, t, device_resident=(dm, dp)) == vb.prove_machine(cfg, t)
     phases = vb.last_prove_phases(ctx)
-    assert [p[0] for p in phases][:2] == ["upload traces (H2D + transpose)", "commit preprocessed"]
+    assert phases[0][0].startswith("upload traces") and phases[1][0] == "commit preprocessed"
 
 
 def test_gpu_proof_tampering_rejected(ctx, oracle):
