@@ -579,7 +579,7 @@ void split_col_row(int log_n, int* l_col, int* l_row) {
     if (log_n <= LOG_ROW_MAX) { *l_col = 0; *l_row = log_n; return; }
     static const int row_split = [] { const char* e = getenv("VGPU_NTT_LOG_ROW"); int v = e ? atoi(e) : LOG_ROW_MAX; return v < 8 || v > LOG_ROW_MAX ? LOG_ROW_MAX : v; }();   // tuning knob (profiles/)
     int lc = log_n - row_split;
-    if (lc > 10) lc = 10;
+    if (lc > LOG_COL_MAX) lc = LOG_COL_MAX;          // then the contiguous part takes the rest (<= LOG_ROW_MAX for log_n <= 26)
     if (lc < 4) lc = 4;
     *l_col = lc; *l_row = log_n - lc;
 }
@@ -706,7 +706,7 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
     while ((1ull << log_n) < h) log_n++;
     if ((1ull << log_n) != h) VG_FAIL(ctx, "coset_lde: height %llu is not a power of two", (unsigned long long)h);
     if (log_n + 1 > VG_LOG_NMAX) VG_FAIL(ctx, "coset_lde: LDE height 2^%d exceeds BabyBear two-adicity", log_n + 1);
-    if (log_n > LOG_ROW_MAX + 10) VG_FAIL(ctx, "coset_lde: heights above 2^%d are not built", LOG_ROW_MAX + 10);
+    if (log_n > LOG_ROW_MAX + LOG_COL_MAX) VG_FAIL(ctx, "coset_lde: heights above 2^%d are not built", LOG_ROW_MAX + LOG_COL_MAX);
     const PowTable* tab = nullptr;
     uint32_t ninv_canon = bb::from_monty(bb::inv(bb::to_monty((uint32_t)(h % bb::P))));
     VG_TRY(vg_get_shift_table(ctx, shift_canonical, ninv_canon, h, &tab));
