@@ -157,3 +157,17 @@ def test_prove_full_size_2p22_verifies(ctx, oracle):
     assert oracle.verify(proof, t.preprocessed) == 0
     vb.verify_machine(cfg, proof, t.preprocessed)
     assert vb.prove_machine(cfg, t) == proof
+
+
+def test_prove_config4_2p24_rows_on_one_gpu(ctx, oracle):
+    """BASELINE config 4's trace (Fibonacci, 2^24 CPU rows; memory chip 2^26 rows, LDE 2^27 = BabyBear's two-adicity) on a
+    single B200: both verifiers accept."""
+    import valida_b200 as vb
+
+    n = ((1 << 24) - 17) // 7
+    t = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
+    assert t.main[0].shape[0] == 1 << 24 and t.main[2].shape[0] == 1 << 26
+    cfg = vb.StarkConfig(ctx, oracle.rc480)
+    proof = vb.prove_machine(cfg, t)
+    vb.verify_machine(cfg, proof, t.preprocessed)
+    assert oracle.verify(proof, t.preprocessed) == 0
