@@ -32,6 +32,15 @@ def fib_n_for_log_rows(log_rows):
     return ((1 << log_rows) - 17) // 7
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -164,7 +173,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the real reference (Rust + un-vendored Plonky3) cannot be built here; this is oracle/, the C++ restatement, OpenMP on all host threads",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(log_rows):
@@ -186,9 +195,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries exactly one JSON line: NCCL's own version / debug lines (printed to stdout when NCCL_DEBUG is set
-    # in the environment) go to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner comes out of
+    # a C printf on rank 0), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to
+    # a private duplicate of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args, rank)
@@ -426,7 +439,7 @@ def main():
         "kernels": kernels,
         "sharded": sharded,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
