@@ -99,6 +99,8 @@ int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t sca
 
 // host/comm.cc — every rank calls these in the same order with the same sizes
 inline bool vg_sharded(const vgpu_ctx* ctx) { return ctx->sharding && ctx->comm_size > 1; }
+// row-wise sweeps over n rows are cut into comm_size contiguous ranges when every range keeps >= 4096 rows
+inline bool vg_split_rows(const vgpu_ctx* ctx, uint64_t n) { return vg_sharded(ctx) && n >= (uint64_t)ctx->comm_size * 4096; }
 void vg_shard_range(uint64_t total, int nranks, int rank, uint64_t* begin, uint64_t* end);   // contiguous, balanced
 int32_t vg_comm_group_begin(vgpu_ctx* ctx);
 int32_t vg_comm_group_end(vgpu_ctx* ctx);

@@ -116,6 +116,7 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
     int log_max = 31;
     while (log_max >= 0 && !ro[log_max]) log_max--;
     if (log_max < LOG_BLOWUP) VG_FAIL(ctx, "open: nothing to open");
+    for (int lg = 0; lg <= log_max; lg++) if (ro[lg]) VG_TRY(vg_reduced_openings_complete(ctx, ro[lg], 1ull << lg));
     std::vector<FriLayer> layers;
     uint32_t* current = ro[log_max];
     uint64_t cur_n = 1ull << log_max;

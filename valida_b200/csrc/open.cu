@@ -30,9 +30,10 @@ __device__ __forceinline__ void st5(uint32_t* v, uint64_t cs, uint64_t i, const 
 }
 
 // out[i] = x_i - z,  x_i = s * w_H^bitrev(i)   (storage order of a committed LDE of height H = 2^log_h)
-__global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, uint64_t H, uint32_t log_h, uint32_t s, E5 z, const uint32_t* lo, const uint32_t* hi) {
+__global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, uint64_t H, uint64_t begin, uint64_t count, uint32_t log_h, uint32_t s, E5 z, const uint32_t* lo, const uint32_t* hi) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= H) return;
+    if (i >= count) return;
+    i += begin;
     uint32_t nat = bb::reverse_bits((uint32_t)i, (int)log_h);
     uint32_t x = bb::mul(s, oroot_pow(lo, hi, (uint64_t)nat << (VG_LOG_NMAX - log_h)));
     E5 d = bb::e5_neg(z);
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, u
 constexpr int BARY_COLS = 2, BARY_WARPS = 16, BARY_THREADS = 32 * BARY_WARPS, BARY_TILE = 1024, BARY_GROUP = BARY_COLS * BARY_WARPS;
 constexpr int BARY_OUT = 11;                       // per column: 2 points x 5 limbs, then the plain column sum
 struct BaryParams {
-    const uint32_t* mat; uint64_t mcs; uint64_t h; uint32_t w;
+    const uint32_t* mat; uint64_t mcs; uint64_t h; uint32_t w;   // h rows starting at row_begin
+    uint64_t row_begin;
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
     uint32_t* partial;       // [gridDim.x][w][BARY_OUT]
 };
@@ -69,8 +71,8 @@ __global__ void __launch_bounds__(BARY_THREADS, 1) bary_kernel(BaryParams p) {
     for (int c = 0; c < BARY_COLS; c++) { sum[c] = 0; for (int q = 0; q < 2; q++) for (int l = 0; l < 5; l++) acc[c][q][l] = 0; }
     const uint64_t ntiles = (p.h + BARY_TILE - 1) / BARY_TILE;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint64_t row0 = t * BARY_TILE;
-        const uint32_t rows = (uint32_t)min((uint64_t)BARY_TILE, p.h - row0);
+        const uint32_t rows = (uint32_t)min((uint64_t)BARY_TILE, p.h - t * BARY_TILE);
+        const uint64_t row0 = p.row_begin + t * BARY_TILE;
         __syncthreads();
         for (uint32_t q = 0; q < p.npoints; q++)
 #pragma unroll
@@ -137,11 +139,12 @@ struct RoParams {
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
     E5 sum_y[2]; E5 alpha_off[2];     // per point: sum_c alpha^c y_c and alpha^offset
     uint32_t* ro; uint64_t rcs;       // accumulator, limb-major, height H
+    uint64_t row_begin, row_end;      // rows swept by this launch
 };
 // one thread per LDE row; sum_c alpha^c p_c(x_i) accumulated lazily (see K8), three columns per fold
 __global__ void __launch_bounds__(256) reduced_opening_kernel(RoParams p) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.H) return;
+    uint64_t i = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.row_end) return;
     uint64_t a[5] = {0, 0, 0, 0, 0};
     const uint32_t* m = p.mat + i;
     uint32_t c = 0;
@@ -213,12 +216,23 @@ __global__ void __launch_bounds__(256) gather_words_kernel(const uint32_t* const
 
 }  // namespace
 
+static int32_t inverse_denominators_range(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint32_t* out, uint64_t begin, uint64_t count) {
+    uint64_t H = 1ull << log_H;
+    KScope ks(ctx, KC_INVDEN, 20.0 * (double)count);
+    coset_minus_point_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, H, begin, count, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
+    VG_LAUNCH_CHECK(ctx);
+    return vg_ext_batch_inverse(ctx, out + begin, H, count, 1);
+}
+// When the row sweeps of this height are split across ranks, a rank only ever reads 1/(x - z) on its range of the
+// reduced-opening sweep (all H rows) and on its range of the barycentric sweep (the first H/2 rows); rank 0's second
+// range lies inside its first.
 int32_t vg_inverse_denominators(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint32_t* out) {
     uint64_t H = 1ull << log_H;
-    KScope ks(ctx, KC_INVDEN, 20.0 * (double)H);
-    coset_minus_point_kernel<<<(unsigned)((H + 255) / 256), 256, 0, ctx->stream>>>(out, H, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
-    VG_LAUNCH_CHECK(ctx);
-    return vg_ext_batch_inverse(ctx, out, H, H, 1);
+    if (!vg_split_rows(ctx, H / 2)) return inverse_denominators_range(ctx, log_H, z, out, 0, H);
+    const uint64_t G = (uint64_t)ctx->comm_size, r = (uint64_t)ctx->comm_rank;
+    VG_TRY(inverse_denominators_range(ctx, log_H, z, out, r * (H / G), H / G));
+    if (r > 0) VG_TRY(inverse_denominators_range(ctx, log_H, z, out, r * (H / 2 / G), H / 2 / G));
+    return 0;
 }
 
 // p_c(z_q) for every column c and point q (q < npoints <= 2) of a committed LDE (height H = 2h).
@@ -226,26 +240,35 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
     uint64_t H = lde->h, h = H / 2;
     uint32_t log_H = 0; while ((1ull << log_H) < H) log_H++;
     uint32_t w = (uint32_t)lde->w;
-    const uint64_t ntiles = (h + BARY_TILE - 1) / BARY_TILE;
+    // split across ranks: each rank sums its contiguous range of the h rows, the per-rank sums meet in one small all-gather
+    const bool split = vg_split_rows(ctx, h);
+    const uint64_t rows = split ? h / ctx->comm_size : h, row_begin = split ? rows * ctx->comm_rank : 0;
+    const uint64_t ntiles = (rows + BARY_TILE - 1) / BARY_TILE;
     unsigned by = (w + BARY_GROUP - 1) / BARY_GROUP;
     unsigned bx = (unsigned)std::min<uint64_t>(ntiles, std::max<uint64_t>(1, 2 * (uint64_t)ctx->sm_count / by));
     uint32_t* partial = nullptr;
     size_t pn = (size_t)bx * w * BARY_OUT;
     VG_TRY(vg_alloc(ctx, (void**)&partial, pn * 4));
     BaryParams p{};
-    p.mat = lde->d; p.mcs = lde->col_stride; p.h = h; p.w = w;
+    p.mat = lde->d; p.mcs = lde->col_stride; p.h = rows; p.row_begin = row_begin; p.w = w;
     p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = H; p.npoints = npoints;
     p.partial = partial;
     {
-        KScope ks(ctx, KC_BARY, 4.0 * (double)h * w);
+        KScope ks(ctx, KC_BARY, 4.0 * (double)rows * w);
         bary_kernel<<<dim3(bx, by), BARY_THREADS, 0, ctx->stream>>>(p);
     }
     VG_LAUNCH_CHECK(ctx);
     const uint32_t nout = w * BARY_OUT;
     uint32_t* reduced = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&reduced, nout * 4));
-    bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, bx, nout, reduced);
+    VG_TRY(vg_alloc(ctx, (void**)&reduced, (size_t)nout * 4 * (split ? ctx->comm_size + 1 : 1)));
+    uint32_t* mine = split ? reduced + (size_t)nout * (1 + ctx->comm_rank) : reduced;     // [total | rank 0 | rank 1 | ...]
+    bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, bx, nout, mine);
     VG_LAUNCH_CHECK(ctx);
+    if (split) {
+        VG_TRY(vg_comm_allgather_inplace(ctx, reduced + nout, nout));
+        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(reduced + nout, (uint32_t)ctx->comm_size, nout, reduced);
+        VG_LAUNCH_CHECK(ctx);
+    }
     std::vector<uint32_t> hp(nout);
     VG_CUDA(ctx, cudaMemcpyAsync(hp.data(), reduced, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -276,12 +299,24 @@ int32_t vg_reduced_opening_accumulate(vgpu_ctx* ctx, const vgpu_dmat* lde, const
     p.npoints = npoints; p.ics = lde->h;
     for (uint32_t q = 0; q < npoints; q++) { p.invden[q] = invden[q]; p.sum_y[q] = sum_y[q]; p.alpha_off[q] = alpha_off[q]; }
     p.ro = ro; p.rcs = lde->h;
+    // split across ranks: a rank accumulates only its range of rows; vg_reduced_openings_complete() joins the ranges
+    const bool split = vg_split_rows(ctx, lde->h / 2);
+    const uint64_t rows = split ? lde->h / ctx->comm_size : lde->h;
+    p.row_begin = split ? rows * ctx->comm_rank : 0; p.row_end = p.row_begin + rows;
     {
-        KScope ks(ctx, KC_REDUCED_OPENING, (double)lde->h * (4.0 * lde->w + 40.0));
-        reduced_opening_kernel<<<(unsigned)((lde->h + 255) / 256), 256, 0, ctx->stream>>>(p);
+        KScope ks(ctx, KC_REDUCED_OPENING, (double)rows * (4.0 * lde->w + 40.0));
+        reduced_opening_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(p);
     }
     VG_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// after the last vg_reduced_opening_accumulate of a height: every rank gets the whole vector (5 limbs x H)
+int32_t vg_reduced_openings_complete(vgpu_ctx* ctx, uint32_t* ro, uint64_t H) {
+    if (!vg_split_rows(ctx, H / 2)) return 0;
+    VG_TRY(vg_comm_group_begin(ctx));
+    for (int l = 0; l < 5; l++) VG_TRY(vg_comm_allgather_inplace(ctx, ro + (uint64_t)l * H, H / ctx->comm_size));
+    return vg_comm_group_end(ctx);
 }
 
 int32_t vg_fri_fold(vgpu_ctx* ctx, const uint32_t* cur, uint64_t n, const E5& beta, const uint32_t* add_or_null, uint32_t* out) {

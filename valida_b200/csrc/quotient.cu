@@ -32,6 +32,7 @@ struct QParams {
     uint32_t* out; uint64_t ocs;            // h x 10 chunk matrix
     const E5* apow;                         // apow[i] = alpha^(N-1-i)
     uint32_t log_h;
+    uint64_t row_begin, row_end;            // storage rows of the LDE swept by this launch (a rank's range when the sweep is split)
     uint32_t s;                             // coset shift (Montgomery)
     uint32_t glast;                         // g_subgroup^-1
     uint32_t zh[2], zinv[2];                // Z_H on even / odd natural rows, and inverses
@@ -74,8 +75,8 @@ __device__ __forceinline__ E5 load_e5(const uint32_t* row, uint64_t cs, uint32_t
 template <int CHIP>
 __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
     const uint64_t h = 1ull << p.log_h, H = 2 * h;
-    const uint64_t rho_raw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
-    const bool active = rho_raw < H;
+    const uint64_t rho_raw = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
+    const bool active = rho_raw < p.row_end;
     const uint64_t rho = active ? rho_raw : (rho_raw & 1);                         // idle lanes shadow rows 0/1 (shuffles need every lane)
     const uint32_t e = (uint32_t)(rho & 1);                                        // 0: x = +x0 (natural row j), 1: x = -x0 (natural row j + h)
     const uint64_t r = rho >> 1;
@@ -160,7 +161,8 @@ struct CountBuilder {
 template <int CHIP> uint32_t count_base() { CountBuilder c; air::eval_chip<CHIP>(c); return c.n; }
 
 template <int CHIP> void launch(const QParams& p, uint64_t h, cudaStream_t st) {
-    quotient_kernel<CHIP><<<(unsigned)((2 * h + 127) / 128), 128, 0, st>>>(p);
+    (void)h;
+    quotient_kernel<CHIP><<<(unsigned)((p.row_end - p.row_begin + 127) / 128), 128, 0, st>>>(p);
 }
 
 }  // namespace
@@ -214,6 +216,9 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     p.odd_scale = bb::mul(p.half, bb::inv(p.s));
     for (int i = 0; i < 5; i++) p.cumsum.c[i] = bb::to_monty(cumulative_sum[i] % bb::P);
     p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi;
+    const bool split = vg_split_rows(ctx, 2 * h);
+    p.row_begin = split ? (2 * h / ctx->comm_size) * ctx->comm_rank : 0;
+    p.row_end = split ? p.row_begin + 2 * h / ctx->comm_size : 2 * h;
     KScope* ks = new KScope(ctx, KC_QUOTIENT, 8.0 * (double)h * (main_lde->w + perm_lde->w + (prep_lde ? prep_lde->w : 0)) + 40.0 * (double)h);
     switch (chip->chip_id) {
         case 0: launch<0>(p, h, ctx->stream); break;   case 1: launch<1>(p, h, ctx->stream); break;
@@ -226,6 +231,11 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     }
     delete ks;
     VG_LAUNCH_CHECK(ctx);
+    if (split) {   // every rank wrote chunk rows [rank*h/G, (rank+1)*h/G) of each of the 10 columns
+        VG_TRY(vg_comm_group_begin(ctx));
+        for (int c = 0; c < 10; c++) VG_TRY(vg_comm_allgather_inplace(ctx, out->d + (uint64_t)c * out->col_stride, h / ctx->comm_size));
+        VG_TRY(vg_comm_group_end(ctx));
+    }
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // apow host vector / device temporaries
     vg_free(ctx, d_apow); vg_free(ctx, dchip);
     *out_chunks = out;
