@@ -49,22 +49,30 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_ratio():
-    """DRAM bytes moved / algorithmic bytes for ntt_pass_kernel, from the committed `ncu --set full` raw page
-    (profiles/r01_ntt_v5_raw.csv: 8 launches over a 2^22 x 16 matrix, 8 B per element per launch)."""
+def ncu_traffic_ratio(kernel):
+    """DRAM bytes moved / algorithmic bytes for one kernel class, from the committed `ncu --set full` raw pages:
+    ntt_pass_kernel: profiles/r01_ntt_v5_raw.csv (8 launches over a 2^22 x 16 matrix, 8 B per element per launch);
+    compress_layer_kernel: profiles/r01_keccak_big_raw.csv (tree layers of 2^24 and 2^23 nodes, 96 B per node)."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r01_ntt_v5_raw.csv")
+    spec = {"ntt_pass_kernel": ("r01_ntt_v5_raw.csv", "ntt_pass", lambda gx, gy: 8.0 * gx * gy * (1 << 14)),      # a 2^14-element tile per CTA
+            "compress_layer_kernel": ("r01_keccak_big_raw.csv", "compress_layer", lambda gx, gy: 96.0 * gx * 128)}  # a node per thread
+    if kernel not in spec:
+        return None, None
+    fname, tag, alg_bytes = spec[kernel]
+    path = os.path.join(ROOT, "profiles", fname)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
-        ir, iw, ig = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Grid Size")
+        ir, iw, ig, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Grid Size"), hdr.index("Kernel Name")
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         tot, alg = 0.0, 0.0
         for r in rows[2:]:
+            if tag not in r[ik]:
+                continue
             tot += float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
             gx, gy = [int(v) for v in r[ig].strip("()").split(",")[:2]]
-            alg += 8.0 * gx * gy * (1 << 14)            # every CTA of that capture owns a 2^14-element tile
+            alg += alg_bytes(gx, gy)
         return tot / alg, os.path.relpath(path, ROOT)
     except Exception:
         return None, None
@@ -365,9 +373,10 @@ def main():
             g = kk[0][3] / bytes_per_perm / (kk[0][2] / 1e3) / 1e9     # >= 1 permutation per `bytes_per_perm` algorithmic bytes
             keccak[name] = {"achieved_gperm_s": g, "frac_of_alu_ceiling": g / KECCAK_PEAK_GPERM}
     roofline["int_alu_ceiling"] = {"unit": "G Keccak-f/s", "peak": KECCAK_PEAK_GPERM, "kernels": keccak,
-                                   "note": "lower bounds: injected layers and multi-block leaves run more permutations than counted"}
-    ratio, ratio_src = ncu_traffic_ratio()
-    if ratio is not None and top[0] == "ntt_pass_kernel":
+                                   "note": "lower bounds: injected layers and multi-block leaves run more permutations than counted",
+                                   "ncu": "profiles/r01_keccak_big_raw.csv: sm__inst_executed_pipe_alu 99.8 % (compress_layer_kernel, 2^24 nodes in 3.96 ms = 4.24 G/s), 92.8 % (leaf_hash_kernel)"}
+    ratio, ratio_src = ncu_traffic_ratio(top[0])
+    if ratio is not None:
         # GB per launch, like `achieved`: the measured DRAM/algorithmic ratio of the committed capture applied to this
         # run's average launch (ncu cannot run inside the timed region)
         roofline["traffic"] = ratio * (top[3] / top[1]) / 1e9
