@@ -88,9 +88,55 @@ BB_HD void acc5_flush(Acc5& a, E5& r) { for (int i = 0; i < 5; i++) { r.c[i] = a
 BB_HD void acc5_fold(Acc5& a) { for (int i = 0; i < 5; i++) a.c[i] = (a.c[i] & 0xffffffffull) + (a.c[i] >> 32) * (uint64_t)R1; }
 BB_HD E5 acc5_value(const Acc5& a) { E5 r; for (int i = 0; i < 5; i++) r.c[i] = monty_reduce64(a.c[i]); return r; }
 
+#ifdef __CUDACC__
+// ---- lazy ext5 accumulation on the device ----------------------------------------------------------------------
+// a*b + c as ONE IMAD.WIDE (the C++ form `c + (uint64_t)a * b` is not reliably fused: ptxas was seen emitting a
+// 64 x 32 multiply — IMAD.WIDE + IMAD + IADD3 — when the 32-bit factor came out of a predicated load).
+__device__ __forceinline__ uint64_t madw(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+// x = hi*2^32 + lo == hi*R1 + lo (mod p): value kept, size back under 2^60 + 2^32
+__device__ __forceinline__ uint64_t lazy_fold(uint64_t a) { return madw((uint32_t)(a >> 32), R1, (uint64_t)(uint32_t)a); }
+
+// Five 64-bit accumulators (one per ext5 limb) that absorb raw products of Montgomery words in lockstep.  Invariant:
+// a folded limb is < 2^60 + 2^32 and every product is < p^2, so FOUR products may be pending before the next fold
+// (4 p^2 + 2^60 + 2^32 = 1.737e19 < 2^64 = 1.845e19).  `np` is the pending count; in straight-line (unrolled) code it
+// folds to a compile-time constant.  value() is the Montgomery reduction of the sum: sum(aR * bR) / R = sum(ab) R.
+struct Lazy5 {
+    uint64_t a[5]; int np;
+    __device__ __forceinline__ void init() { for (int l = 0; l < 5; l++) a[l] = 0; np = 0; }
+    __device__ __forceinline__ void fold() { for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l]); np = 0; }
+    __device__ __forceinline__ void step() { if (np == 4) fold(); np++; }
+    // += x * y, y in the base field (any 32-bit word times words < p keeps the bound only for y < p: callers pass reduced words)
+    __device__ __forceinline__ void fma_base(const E5& x, uint32_t y) {
+        step();
+#pragma unroll
+        for (int l = 0; l < 5; l++) a[l] = madw(x.c[l], y, a[l]);
+    }
+    // += x * y in F_p[X]/(X^5 - 2); y2 = 2*y (limb-wise, reduced) feeds the wrapped terms.  Round r adds x_r * y_(k-r) to limb k.
+    __device__ __forceinline__ void fma_ext(const E5& x, const E5& y, const E5& y2) {
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            step();
+#pragma unroll
+            for (int k = 0; k < 5; k++) a[k] = madw(x.c[r], k >= r ? y.c[k - r] : y2.c[k - r + 5], a[k]);
+        }
+    }
+    __device__ __forceinline__ E5 value() const { E5 r; for (int l = 0; l < 5; l++) r.c[l] = monty_reduce64(a[l]); return r; }
+};
+__device__ __forceinline__ E5 e5_dbl(const E5& a) { E5 r; for (int i = 0; i < 5; i++) r.c[i] = dbl(a.c[i]); return r; }
+#endif
+
 // Schoolbook product with X^5 = 2.  Products a_i*b_j < p^2 < 2^62, so up to 4 of them fit in 64 bits
 // before one Montgomery reduction.
 BB_HD E5 e5_mul(const E5& a, const E5& b) {
+#ifdef __CUDA_ARCH__
+    // device: 25 + 5 IMAD.WIDE and five reductions (the wrapped terms use 2*b) instead of nine reductions
+    Lazy5 t; t.init(); t.fma_ext(a, b, e5_dbl(b));
+    return t.value();
+#else
     E5 r;
 #define PR(i, j) ((uint64_t)a.c[i] * b.c[j])
     // low parts t_k = sum_{i+j=k}, high parts u_k = sum_{i+j=k+5} (to be doubled)
@@ -110,6 +156,7 @@ BB_HD E5 e5_mul(const E5& a, const E5& b) {
     r.c[3] = add(l3, dbl(h3));
     r.c[4] = l4;
     return r;
+#endif
 }
 BB_HD E5 e5_sqr(const E5& a) { return e5_mul(a, a); }
 BB_HD E5 e5_pow(E5 a, uint64_t e) {

@@ -53,61 +53,83 @@ int log2u(uint64_t n) { int l = 0; while ((1ull << l) < n) l++; return l; }
 
 int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, vgh::Challenger& ch, OpeningH* out) {
     const E5 alpha = ch.sample_ext();
-    // alpha^c table
+    // alpha^c table (host; the reduced-opening kernel takes its powers through the kernel parameters)
     uint32_t max_w = 1;
     for (auto& r : rounds) for (auto* m : r.pd->ldes) max_w = std::max<uint32_t>(max_w, (uint32_t)m->w);
-    std::vector<E5> apow(max_w);
-    { E5 a = bb::e5_one(); for (uint32_t c = 0; c < max_w; c++) { apow[c] = a; a = bb::e5_mul(a, alpha); } }
-    E5* d_apow = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&d_apow, max_w * sizeof(E5)));
-    VG_CUDA(ctx, cudaMemcpyAsync(d_apow, apow.data(), max_w * sizeof(E5), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<E5> apow(max_w + 1);
+    { E5 a = bb::e5_one(); for (uint32_t c = 0; c <= max_w; c++) { apow[c] = a; a = bb::e5_mul(a, alpha); } }
 
     std::map<PointKey, uint32_t*> invden;       // (height, point) -> 1/(x - z) over the whole coset
     uint32_t* ro[32] = {nullptr};
     uint64_t num_reduced[32] = {0};
+    uint32_t* d_sums = nullptr;
     auto cleanup = [&]() {
         for (auto& kv : invden) vg_free(ctx, kv.second);
         invden.clear();
-        vg_free(ctx, d_apow);
+        vg_free(ctx, d_sums); d_sums = nullptr;
     };
-    out->values.clear();
-    for (const OpenRound& rd : rounds) {
-        out->values.emplace_back();
+    // Pass 1 — enqueue, for every matrix, the inverse denominators of its points and the column sums behind p_c(z_q); nothing
+    // here waits for the device.  One copy brings the sums of all matrices back.
+    struct Job { const vgpu_dmat* lde; uint32_t log_H, w; const std::vector<E5>* pts; const uint32_t* dens[2]; size_t sums_at; };
+    std::vector<Job> jobs;
+    size_t sums_words = 0;
+    for (const OpenRound& rd : rounds)
         for (size_t mi = 0; mi < rd.pd->ldes.size(); mi++) {
-            const vgpu_dmat* lde = rd.pd->ldes[mi];
-            const uint32_t log_H = (uint32_t)log2u(lde->h), w = (uint32_t)lde->w;
-            const std::vector<E5>& pts = rd.points[mi];
-            if (pts.empty() || pts.size() > 2) { cleanup(); VG_FAIL(ctx, "open: 1 or 2 points per matrix are supported"); }
-            if (!ro[log_H]) {
-                VG_TRY(vg_alloc(ctx, (void**)&ro[log_H], 5 * lde->h * 4));
-                VG_CUDA(ctx, cudaMemsetAsync(ro[log_H], 0, 5 * lde->h * 4, ctx->stream));
+            Job j{};
+            j.lde = rd.pd->ldes[mi]; j.log_H = (uint32_t)log2u(j.lde->h); j.w = (uint32_t)j.lde->w; j.pts = &rd.points[mi];
+            if (j.pts->empty() || j.pts->size() > 2) VG_FAIL(ctx, "open: 1 or 2 points per matrix are supported");
+            j.sums_at = sums_words; sums_words += vg_eval_columns_words(j.w);
+            jobs.push_back(j);
+        }
+    VG_TRY(vg_alloc(ctx, (void**)&d_sums, sums_words * 4));
+    for (Job& j : jobs) {
+        if (!ro[j.log_H]) {
+            VG_TRY(vg_alloc(ctx, (void**)&ro[j.log_H], 5 * j.lde->h * 4));
+            VG_CUDA(ctx, cudaMemsetAsync(ro[j.log_H], 0, 5 * j.lde->h * 4, ctx->stream));
+        }
+        for (size_t q = 0; q < j.pts->size(); q++) {
+            PointKey key; key.log_H = j.log_H; std::memcpy(key.c, (*j.pts)[q].c, 20);
+            auto it = invden.find(key);
+            if (it == invden.end()) {
+                uint32_t* buf = nullptr;
+                VG_TRY(vg_alloc(ctx, (void**)&buf, 5 * j.lde->h * 4));
+                VG_TRY(vg_inverse_denominators(ctx, j.log_H, (*j.pts)[q], buf));
+                it = invden.emplace(key, buf).first;
             }
-            const uint32_t* dens[2] = {nullptr, nullptr};
-            for (size_t q = 0; q < pts.size(); q++) {
-                PointKey key; key.log_H = log_H; std::memcpy(key.c, pts[q].c, 20);
-                auto it = invden.find(key);
-                if (it == invden.end()) {
-                    uint32_t* buf = nullptr;
-                    VG_TRY(vg_alloc(ctx, (void**)&buf, 5 * lde->h * 4));
-                    VG_TRY(vg_inverse_denominators(ctx, log_H, pts[q], buf));
-                    it = invden.emplace(key, buf).first;
+            j.dens[q] = it->second;
+        }
+        VG_TRY(vg_eval_columns_enqueue(ctx, j.lde, (uint32_t)j.pts->size(), j.dens, d_sums + j.sums_at));
+    }
+    std::vector<uint32_t> sums(sums_words);
+    VG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums, sums_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // Pass 2 — opened values on the host, then the reduced openings of every matrix (again without waiting)
+    out->values.clear();
+    {
+        size_t ji = 0;
+        std::vector<E5> apow_off(max_w);
+        for (const OpenRound& rd : rounds) {
+            out->values.emplace_back();
+            for (size_t mi = 0; mi < rd.pd->ldes.size(); mi++, ji++) {
+                const Job& j = jobs[ji];
+                const uint32_t w = j.w, np = (uint32_t)j.pts->size();
+                std::vector<E5> ys;
+                vg_eval_columns_finish(sums.data() + j.sums_at, j.lde->h, w, np, j.pts->data(), &ys);
+                E5 sum_y[2];
+                out->values.back().emplace_back();
+                for (uint32_t q = 0; q < np; q++) {
+                    E5 s = bb::e5_zero();
+                    std::vector<ExtC> yc(w);
+                    for (uint32_t c = 0; c < w; c++) { s = bb::e5_add(s, bb::e5_mul(apow[c], ys[q * w + c])); yc[c] = canon(ys[q * w + c]); }
+                    sum_y[q] = s;
+                    out->values.back().back().push_back(std::move(yc));
                 }
-                dens[q] = it->second;
+                // point q's terms carry alpha^(num_reduced + q * w): the power table is shifted by the first offset
+                const E5 a_off = bb::e5_pow(alpha, num_reduced[j.log_H]);
+                num_reduced[j.log_H] += (uint64_t)w * np;
+                for (uint32_t c = 0; c < w; c++) apow_off[c] = bb::e5_mul(a_off, apow[c]);
+                VG_TRY(vg_reduced_opening_accumulate(ctx, j.lde, apow_off.data(), apow[w], np, j.dens, sum_y, ro[j.log_H]));
             }
-            std::vector<E5> ys;
-            VG_TRY(vg_eval_columns(ctx, lde, (uint32_t)pts.size(), pts.data(), dens, &ys));
-            E5 sum_y[2], alpha_off[2];
-            out->values.back().emplace_back();
-            for (size_t q = 0; q < pts.size(); q++) {
-                E5 s = bb::e5_zero();
-                std::vector<ExtC> yc(w);
-                for (uint32_t c = 0; c < w; c++) { s = bb::e5_add(s, bb::e5_mul(apow[c], ys[q * w + c])); yc[c] = canon(ys[q * w + c]); }
-                sum_y[q] = s;
-                alpha_off[q] = bb::e5_pow(alpha, num_reduced[log_H]);
-                num_reduced[log_H] += w;
-                out->values.back().back().push_back(std::move(yc));
-            }
-            VG_TRY(vg_reduced_opening_accumulate(ctx, lde, d_apow, (uint32_t)pts.size(), dens, sum_y, alpha_off, ro[log_H]));
         }
     }
     cleanup();

@@ -9,6 +9,8 @@
 #include "ctx.h"
 #include "devchip.h"
 #include "open.h"
+#include <algorithm>
+#include <memory>
 
 namespace {
 
@@ -44,81 +46,107 @@ __global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, u
 // K8: out-of-domain evaluation.  With x/(x - z) = 1 + z/(x - z) the barycentric sum splits into
 //     S_c(z) = sum_i p_c(x_i) + z * sum_i p_c(x_i) / (x_i - z)
 // so the kernel needs no domain points at all: per column a base-field sum and, per point, an ext5 dot product with
-// the inverse denominators.  Dot products are accumulated LAZILY: raw 64-bit products of Montgomery words
-// (< 2^62 each) are added three at a time into a 64-bit accumulator which is then folded with
-// hi*2^32 + lo == hi*R1 + lo (mod p) — one IMAD.WIDE per term instead of a full modular multiply-add.
-// A CTA stages the inverse denominators of a tile of rows in shared memory once and every warp sweeps that tile
-// for its own BARY_COLS columns, so the denominators are read from HBM once per group of 32 columns.
-constexpr int BARY_COLS = 2, BARY_WARPS = 16, BARY_THREADS = 32 * BARY_WARPS, BARY_TILE = 1024, BARY_GROUP = BARY_COLS * BARY_WARPS;
+// the inverse denominators — a (w x h) by (h x 5*NP) product over F_p.  Dot products are accumulated LAZILY
+// (bb::madw / bb::lazy_fold: one IMAD.WIDE per term, one more per four terms), which makes the sweep bound by the
+// half-rate IMAD.WIDE issue: 5 * NP * 1.25 of them per element.
+// A CTA (16 warps) double-buffers tiles of 1024 rows of the inverse denominators in shared memory (cp.async) and its
+// warps form a (column pair) x (row slice) grid over the tile: narrow matrices (the 2^24-row memory chip has 14 / 10
+// columns) put several warps on the same column pair, so all 16 warps work whatever the width.  A lane owns four
+// consecutive rows of a 128-row chunk: one 16-byte global load per column and one 16-byte shared load per limb.
+constexpr int BARY_COLS = 2, BARY_WARPS = 16, BARY_THREADS = 32 * BARY_WARPS, BARY_TILE = 1024, BARY_CHUNKS = BARY_TILE / 128;
 constexpr int BARY_OUT = 11;                       // per column: 2 points x 5 limbs, then the plain column sum
 struct BaryParams {
     const uint32_t* mat; uint64_t mcs; uint64_t h; uint32_t w;   // h rows starting at row_begin
     uint64_t row_begin;
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
-    uint32_t* partial;       // [gridDim.x][w][BARY_OUT]
+    uint32_t cpg, rs;        // columns per CTA (even, <= 32) and row slices per column pair: (cpg / 2) * rs <= 16 warps
+    uint32_t* partial;       // [gridDim.x * rs][w][BARY_OUT]
 };
-__device__ __forceinline__ uint64_t lazy_fold(uint64_t a) { return (a & 0xffffffffull) + (a >> 32) * (uint64_t)bb::R1; }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int NP>
 __global__ void __launch_bounds__(BARY_THREADS, 1) bary_kernel(BaryParams p) {
-    __shared__ uint32_t dsm[2][5][BARY_TILE];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t c0 = blockIdx.y * BARY_GROUP + wid * BARY_COLS;
+    extern __shared__ __align__(16) uint32_t dsm[];          // [2][NP * 5][BARY_TILE]
+    constexpr uint32_t BUF = NP * 5 * BARY_TILE;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ncg = p.cpg / BARY_COLS;
+    const uint32_t cw = wid % ncg, rsl = wid / ncg;
+    const uint32_t c0 = blockIdx.y * p.cpg + cw * BARY_COLS;
+    const bool worker = rsl < p.rs && c0 < p.w;
     const uint32_t* col[BARY_COLS];
 #pragma unroll
-    for (int c = 0; c < BARY_COLS; c++) col[c] = p.mat + (uint64_t)min(c0 + c, p.w - 1) * p.mcs;   // surplus columns shadow the last one (never written)
-    uint64_t acc[BARY_COLS][2][5];
+    for (int c = 0; c < BARY_COLS; c++) col[c] = p.mat + (uint64_t)min(c0 + c, p.w - 1) * p.mcs + p.row_begin + 4 * lane;   // a surplus column shadows the last one (never written)
+    uint64_t acc[BARY_COLS][NP][5];
     uint64_t sum[BARY_COLS];
 #pragma unroll
-    for (int c = 0; c < BARY_COLS; c++) { sum[c] = 0; for (int q = 0; q < 2; q++) for (int l = 0; l < 5; l++) acc[c][q][l] = 0; }
-    const uint64_t ntiles = (p.h + BARY_TILE - 1) / BARY_TILE;
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t rows = (uint32_t)min((uint64_t)BARY_TILE, p.h - t * BARY_TILE);
+    for (int c = 0; c < BARY_COLS; c++) { sum[c] = 0; for (int q = 0; q < NP; q++) for (int l = 0; l < 5; l++) acc[c][q][l] = 0; }
+    const uint64_t ntiles = p.h / BARY_TILE;
+    auto stage = [&](uint32_t buf, uint64_t t) {
         const uint64_t row0 = p.row_begin + t * BARY_TILE;
+        for (uint32_t i = threadIdx.x; i < NP * 5 * (BARY_TILE / 4); i += BARY_THREADS) {
+            const uint32_t ql = i / (BARY_TILE / 4), v = i % (BARY_TILE / 4);
+            cp_async16(dsm + buf * BUF + ql * BARY_TILE + 4 * v, (ql < 5 ? p.invden[0] : p.invden[1]) + (uint64_t)(ql % 5) * p.ics + row0 + 4 * v);
+        }
+        cp_async_commit();
+    };
+    uint32_t buf = 0;
+    if (blockIdx.x < ntiles) stage(0, blockIdx.x);
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const bool more = t + gridDim.x < ntiles;
+        if (more) stage(buf ^ 1, t + gridDim.x);
+        uint4 e[BARY_COLS];
+        if (worker) {
+#pragma unroll
+            for (int c = 0; c < BARY_COLS; c++) e[c] = __ldg(reinterpret_cast<const uint4*>(col[c] + t * BARY_TILE + rsl * 128));
+        }
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
-        for (uint32_t q = 0; q < p.npoints; q++)
+        if (worker) {
+            const uint32_t* d = dsm + buf * BUF + 4 * lane;
+            for (uint32_t ck = rsl; ck < BARY_CHUNKS; ck += p.rs) {
+                uint4 nx[BARY_COLS];
+                const bool pre = ck + p.rs < BARY_CHUNKS;
+                if (pre) {
 #pragma unroll
-            for (int l = 0; l < 5; l++)
-                for (uint32_t r = threadIdx.x; r < rows; r += BARY_THREADS) dsm[q][l][r] = __ldg(p.invden[q] + (uint64_t)l * p.ics + row0 + r);
-        __syncthreads();
-        if (c0 < p.w) {
-            // six row-slices per step: twelve independent global loads in flight per lane, a fold per three products
-            for (uint32_t r = lane; r < rows; r += 192) {
-                uint32_t e[6][BARY_COLS], rr[6];
-#pragma unroll
-                for (int u = 0; u < 6; u++) {
-                    const uint32_t ru = r + 32 * u;
-                    rr[u] = ru < rows ? ru : r;
-#pragma unroll
-                    for (int c = 0; c < BARY_COLS; c++) e[u][c] = ru < rows ? __ldg(col[c] + row0 + ru) : 0u;   // a zero term adds nothing
+                    for (int c = 0; c < BARY_COLS; c++) nx[c] = __ldg(reinterpret_cast<const uint4*>(col[c] + t * BARY_TILE + (ck + p.rs) * 128));
                 }
 #pragma unroll
-                for (int g = 0; g < 6; g += 3) {
+                for (int q = 0; q < NP; q++) {
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        if ((uint32_t)q < p.npoints) {
+                    for (int l = 0; l < 5; l++) {
+                        const uint4 dv = *reinterpret_cast<const uint4*>(d + (q * 5 + l) * BARY_TILE + ck * 128);
 #pragma unroll
-                            for (int l = 0; l < 5; l++) {
-                                const uint32_t d0 = dsm[q][l][rr[g]], d1 = dsm[q][l][rr[g + 1]], d2 = dsm[q][l][rr[g + 2]];
-#pragma unroll
-                                for (int c = 0; c < BARY_COLS; c++)
-                                    acc[c][q][l] = lazy_fold(acc[c][q][l] + (uint64_t)e[g][c] * d0 + (uint64_t)e[g + 1][c] * d1 + (uint64_t)e[g + 2][c] * d2);
-                            }
+                        for (int c = 0; c < BARY_COLS; c++) {
+                            uint64_t a = acc[c][q][l];
+                            a = bb::madw(e[c].x, dv.x, a); a = bb::madw(e[c].y, dv.y, a); a = bb::madw(e[c].z, dv.z, a); a = bb::madw(e[c].w, dv.w, a);
+                            acc[c][q][l] = bb::lazy_fold(a);
                         }
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < BARY_COLS; c++)
+                for (int c = 0; c < BARY_COLS; c++) sum[c] += (uint64_t)e[c].x + e[c].y + e[c].z + e[c].w;
+                if (pre) {
 #pragma unroll
-                    for (int u = 0; u < 6; u++) sum[c] += e[u][c];
+                    for (int c = 0; c < BARY_COLS; c++) e[c] = nx[c];
+                }
             }
         }
+        __syncthreads();
+        buf ^= 1;
     }
-    if (c0 >= p.w) return;
+    if (!worker) return;
     // reduce to field elements, then across the warp
 #pragma unroll
     for (int c = 0; c < BARY_COLS; c++) {
         uint32_t v[BARY_OUT];
 #pragma unroll
-        for (int q = 0; q < 2; q++)
+        for (int k = 0; k < BARY_OUT; k++) v[k] = 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++)
 #pragma unroll
             for (int l = 0; l < 5; l++) v[q * 5 + l] = bb::monty_reduce64(acc[c][q][l]);
         v[10] = (uint32_t)(sum[c] % bb::P);
@@ -127,59 +155,94 @@ __global__ void __launch_bounds__(BARY_THREADS, 1) bary_kernel(BaryParams p) {
             uint32_t x = v[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x = bb::add(x, __shfl_xor_sync(0xffffffffu, x, o));
-            if (lane == 0 && c0 + c < p.w) p.partial[((uint64_t)blockIdx.x * p.w + c0 + c) * BARY_OUT + k] = x;
+            if (lane == 0 && c0 + c < p.w) p.partial[(((uint64_t)blockIdx.x * p.rs + rsl) * p.w + c0 + c) * BARY_OUT + k] = x;
         }
     }
 }
+// heights below one tile (never on the critical path): a CTA per column, plain modular arithmetic
+__global__ void __launch_bounds__(128) bary_small_kernel(BaryParams p) {
+    __shared__ uint32_t red[4][BARY_OUT];
+    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t* col = p.mat + (uint64_t)c * p.mcs + p.row_begin;
+    E5 acc[2] = {bb::e5_zero(), bb::e5_zero()};
+    uint32_t s = 0;
+    for (uint64_t r = threadIdx.x; r < p.h; r += blockDim.x) {
+        const uint32_t x = col[r];
+        s = bb::add(s, x);
+        for (uint32_t q = 0; q < p.npoints; q++) acc[q] = bb::e5_add(acc[q], bb::e5_mul_base(ld5(p.invden[q], p.ics, p.row_begin + r), x));
+    }
+    uint32_t v[BARY_OUT];
+    for (int q = 0; q < 2; q++) for (int l = 0; l < 5; l++) v[q * 5 + l] = acc[q].c[l];
+    v[10] = s;
+    for (int k = 0; k < BARY_OUT; k++) {
+        uint32_t x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x = bb::add(x, __shfl_xor_sync(0xffffffffu, x, o));
+        if (lane == 0) red[wid][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < BARY_OUT) {
+        const uint32_t k = threadIdx.x;
+        p.partial[(uint64_t)c * BARY_OUT + k] = bb::add(bb::add(red[0][k], red[1][k]), bb::add(red[2][k], red[3][k]));
+    }
+}
 
-// K9
+// K9: reduced openings.  One thread per LDE row i:
+//     U(i)   = sum_c alpha^(off + c) p_c(x_i)                       (lazy dot product, powers in the kernel parameters)
+//     ro[i] += (U - B_0) / (x_i - z_0)  +  (U * alpha^w - B_1) / (x_i - z_1),      B_q = alpha^(off_q) sum_c alpha^c p_c(z_q)
+// which is the reference's  alpha^off_q * (sum_c alpha^c p_c(x_i) - sum_c alpha^c p_c(z_q)) / (x_i - z_q)  summed over the
+// points (off_1 = off_0 + w): shifting the power table by off_0 removes one ext5 product per point from every row.
+constexpr uint32_t RO_MAXW = 96;
 struct RoParams {
     const uint32_t* mat; uint64_t mcs; uint64_t H; uint32_t w;
-    const E5* apow;                   // alpha^c, c < w
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
-    E5 sum_y[2]; E5 alpha_off[2];     // per point: sum_c alpha^c y_c and alpha^offset
+    E5 b[2]; E5 aw, aw2;              // B_q; alpha^w and 2 * alpha^w
     uint32_t* ro; uint64_t rcs;       // accumulator, limb-major, height H
     uint64_t row_begin, row_end;      // rows swept by this launch
+    uint32_t first;                   // 1: this launch also subtracts B_q (0 on the later column blocks of a matrix wider than RO_MAXW)
+    uint32_t apow[RO_MAXW][5];        // alpha^(off_0 + c)
 };
-// one thread per LDE row; sum_c alpha^c p_c(x_i) accumulated lazily (see K8), three columns per fold
-__global__ void __launch_bounds__(256) reduced_opening_kernel(RoParams p) {
-    uint64_t i = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+template <int NP>
+__global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_constant__ RoParams p) {
+    const uint64_t i = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.row_end) return;
     uint64_t a[5] = {0, 0, 0, 0, 0};
     const uint32_t* m = p.mat + i;
     uint32_t c = 0;
-    for (; c + 6 <= p.w; c += 6) {   // six loads in flight, two folds
-        uint32_t e[6];
+    for (; c + 8 <= p.w; c += 8) {   // eight loads in flight, two folds per limb
+        uint32_t e[8];
 #pragma unroll
-        for (int u = 0; u < 6; u++) e[u] = __ldg(m + (uint64_t)(c + u) * p.mcs);
+        for (int u = 0; u < 8; u++) e[u] = __ldg(m + (uint64_t)(c + u) * p.mcs);
 #pragma unroll
-        for (int g = 0; g < 6; g += 3) {
-            const E5 a0 = p.apow[c + g], a1 = p.apow[c + g + 1], a2 = p.apow[c + g + 2];
+        for (int g = 0; g < 8; g += 4)
 #pragma unroll
-            for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l] + (uint64_t)a0.c[l] * e[g] + (uint64_t)a1.c[l] * e[g + 1] + (uint64_t)a2.c[l] * e[g + 2]);
-        }
-    }
-    for (; c + 3 <= p.w; c += 3) {
-        const uint32_t e0 = __ldg(m + (uint64_t)c * p.mcs), e1 = __ldg(m + (uint64_t)(c + 1) * p.mcs), e2 = __ldg(m + (uint64_t)(c + 2) * p.mcs);
-        const E5 a0 = p.apow[c], a1 = p.apow[c + 1], a2 = p.apow[c + 2];
+            for (int l = 0; l < 5; l++) {
+                uint64_t t = a[l];
 #pragma unroll
-        for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l] + (uint64_t)a0.c[l] * e0 + (uint64_t)a1.c[l] * e1 + (uint64_t)a2.c[l] * e2);
+                for (int u = 0; u < 4; u++) t = bb::madw(e[g + u], p.apow[c + g + u][l], t);
+                a[l] = bb::lazy_fold(t);
+            }
     }
     for (; c < p.w; c++) {
         const uint32_t e0 = __ldg(m + (uint64_t)c * p.mcs);
-        const E5 a0 = p.apow[c];
 #pragma unroll
-        for (int l = 0; l < 5; l++) a[l] = lazy_fold(a[l] + (uint64_t)a0.c[l] * e0);
+        for (int l = 0; l < 5; l++) a[l] = bb::lazy_fold(bb::madw(e0, p.apow[c][l], a[l]));
     }
-    E5 red;
+    E5 U;
 #pragma unroll
-    for (int l = 0; l < 5; l++) red.c[l] = bb::monty_reduce64(a[l]);
-    E5 acc = ld5(p.ro, p.rcs, i);
-    for (uint32_t q = 0; q < p.npoints; q++) {
-        E5 t = bb::e5_mul(bb::e5_sub(red, p.sum_y[q]), ld5(p.invden[q], p.ics, i));
-        acc = bb::e5_add(acc, bb::e5_mul(t, p.alpha_off[q]));
+    for (int l = 0; l < 5; l++) U.c[l] = bb::monty_reduce64(a[l]);
+    bb::Lazy5 s; s.init();
+    {
+        const E5 w0 = p.first ? bb::e5_sub(U, p.b[0]) : U;
+        s.fma_ext(ld5(p.invden[0], p.ics, i), w0, bb::e5_dbl(w0));
     }
-    st5(p.ro, p.rcs, i, acc);
+    if (NP > 1) {
+        bb::Lazy5 t; t.init();
+        t.fma_ext(U, p.aw, p.aw2);
+        E5 w1 = t.value();
+        if (p.first) w1 = bb::e5_sub(w1, p.b[1]);
+        s.fma_ext(ld5(p.invden[1], p.ics, i), w1, bb::e5_dbl(w1));
+    }
+    st5(p.ro, p.rcs, i, bb::e5_add(ld5(p.ro, p.rcs, i), s.value()));
 }
 
 // K10: out[i] = (lo + hi)/2 + (beta/2) * g_inv^bitrev(i) * (lo - hi)  (+ add[i])
@@ -235,46 +298,67 @@ int32_t vg_inverse_denominators(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint
     return 0;
 }
 
-// p_c(z_q) for every column c and point q (q < npoints <= 2) of a committed LDE (height H = 2h).
-int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, const E5* z, const uint32_t* const* invden, std::vector<E5>* ys /* [q][c] */) {
+// Enqueue the sums behind p_c(z_q) for every column c and point q (q < npoints <= 2) of a committed LDE (height H = 2h):
+// d_out receives w * BARY_OUT words ([c][q*5 + l] = sum_i p_c(x_i) / (x_i - z_q), [c][10] = sum_i p_c(x_i)), stream-ordered, no
+// host synchronisation — open_multi_batches reads the sums of every matrix back with ONE copy.
+int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, const uint32_t* const* invden, uint32_t* d_out) {
     uint64_t H = lde->h, h = H / 2;
-    uint32_t log_H = 0; while ((1ull << log_H) < H) log_H++;
     uint32_t w = (uint32_t)lde->w;
     // split across ranks: each rank sums its contiguous range of the h rows, the per-rank sums meet in one small all-gather
     const bool split = vg_split_rows(ctx, h);
     const uint64_t rows = split ? h / ctx->comm_size : h, row_begin = split ? rows * ctx->comm_rank : 0;
-    const uint64_t ntiles = (rows + BARY_TILE - 1) / BARY_TILE;
-    unsigned by = (w + BARY_GROUP - 1) / BARY_GROUP;
-    unsigned bx = (unsigned)std::min<uint64_t>(ntiles, std::max<uint64_t>(1, 2 * (uint64_t)ctx->sm_count / by));
-    uint32_t* partial = nullptr;
-    size_t pn = (size_t)bx * w * BARY_OUT;
-    VG_TRY(vg_alloc(ctx, (void**)&partial, pn * 4));
     BaryParams p{};
     p.mat = lde->d; p.mcs = lde->col_stride; p.h = rows; p.row_begin = row_begin; p.w = w;
     p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = H; p.npoints = npoints;
-    p.partial = partial;
-    {
+    uint32_t nblocks = 1;
+    uint32_t* partial = nullptr;
+    if (rows >= BARY_TILE && rows % BARY_TILE == 0) {
+        const unsigned by = (w + 31) / 32;
+        p.cpg = 2 * (((w + by - 1) / by + 1) / 2);               // columns per CTA, even
+        p.rs = std::min<uint32_t>(BARY_CHUNKS, BARY_WARPS / (p.cpg / BARY_COLS));
+        const uint64_t ntiles = rows / BARY_TILE;
+        const unsigned bx = (unsigned)std::min<uint64_t>(ntiles, std::max<uint64_t>(1, (uint64_t)ctx->sm_count / by));
+        nblocks = bx * p.rs;
+        VG_TRY(vg_alloc(ctx, (void**)&partial, (size_t)nblocks * w * BARY_OUT * 4));
+        p.partial = partial;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VG_CUDA(ctx, cudaFuncSetAttribute(bary_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1 * 5 * BARY_TILE * 4));
+            VG_CUDA(ctx, cudaFuncSetAttribute(bary_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 5 * BARY_TILE * 4));
+            attr_set = true;
+        }
         KScope ks(ctx, KC_BARY, 4.0 * (double)rows * w);
-        bary_kernel<<<dim3(bx, by), BARY_THREADS, 0, ctx->stream>>>(p);
+        if (npoints > 1) bary_kernel<2><<<dim3(bx, by), BARY_THREADS, 2 * 2 * 5 * BARY_TILE * 4, ctx->stream>>>(p);
+        else bary_kernel<1><<<dim3(bx, by), BARY_THREADS, 2 * 1 * 5 * BARY_TILE * 4, ctx->stream>>>(p);
+    } else {
+        VG_TRY(vg_alloc(ctx, (void**)&partial, (size_t)w * BARY_OUT * 4));
+        p.partial = partial;
+        KScope ks(ctx, KC_BARY, 4.0 * (double)rows * w);
+        bary_small_kernel<<<w, 128, 0, ctx->stream>>>(p);
     }
     VG_LAUNCH_CHECK(ctx);
     const uint32_t nout = w * BARY_OUT;
-    uint32_t* reduced = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&reduced, (size_t)nout * 4 * (split ? ctx->comm_size + 1 : 1)));
-    uint32_t* mine = split ? reduced + (size_t)nout * (1 + ctx->comm_rank) : reduced;     // [total | rank 0 | rank 1 | ...]
-    bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, bx, nout, mine);
-    VG_LAUNCH_CHECK(ctx);
-    if (split) {
-        VG_TRY(vg_comm_allgather_inplace(ctx, reduced + nout, nout));
-        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(reduced + nout, (uint32_t)ctx->comm_size, nout, reduced);
+    if (!split) {
+        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, nblocks, nout, d_out);
         VG_LAUNCH_CHECK(ctx);
+    } else {
+        uint32_t* gathered = nullptr;                                                      // [rank 0 | rank 1 | ...]
+        VG_TRY(vg_alloc(ctx, (void**)&gathered, (size_t)nout * 4 * ctx->comm_size));
+        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, nblocks, nout, gathered + (size_t)nout * ctx->comm_rank);
+        VG_LAUNCH_CHECK(ctx);
+        VG_TRY(vg_comm_allgather_inplace(ctx, gathered, nout));
+        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(gathered, (uint32_t)ctx->comm_size, nout, d_out);
+        VG_LAUNCH_CHECK(ctx);
+        vg_free(ctx, gathered);
     }
-    std::vector<uint32_t> hp(nout);
-    VG_CUDA(ctx, cudaMemcpyAsync(hp.data(), reduced, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    vg_free(ctx, partial); vg_free(ctx, reduced);
-    // p(z) = -(z^h - s^h) / (h s^h) * S
-    uint32_t log_h = log_H - 1;
+    vg_free(ctx, partial);
+    return 0;
+}
+
+// host arithmetic on the sums of vg_eval_columns_enqueue:  p(z) = -(z^h - s^h) / (h s^h) * (sum_i p(x_i) + z sum_i p(x_i)/(x_i - z))
+void vg_eval_columns_finish(const uint32_t* sums, uint64_t H, uint32_t w, uint32_t npoints, const E5* z, std::vector<E5>* ys /* [q][c] */) {
+    const uint64_t h = H / 2;
+    uint32_t log_h = 0; while ((1ull << log_h) < h) log_h++;
     uint32_t s = bb::to_monty(bb::GEN_CANON), sh = s;
     for (uint32_t i = 0; i < log_h; i++) sh = bb::sqr(sh);
     uint32_t denom_inv = bb::inv(bb::mul(bb::to_monty((uint32_t)(h % bb::P)), sh));
@@ -284,30 +368,40 @@ int32_t vg_eval_columns(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, c
         E5 norm = bb::e5_neg(bb::e5_mul_base(bb::e5_sub_base(zh, sh), denom_inv));
         for (uint32_t c = 0; c < w; c++) {
             E5 D;   // sum_i p_c(x_i) / (x_i - z_q)
-            for (int l = 0; l < 5; l++) D.c[l] = hp[(size_t)c * BARY_OUT + q * 5 + l];
-            const E5 S = bb::e5_add_base(bb::e5_mul(z[q], D), hp[(size_t)c * BARY_OUT + 10]);
+            for (int l = 0; l < 5; l++) D.c[l] = sums[(size_t)c * BARY_OUT + q * 5 + l];
+            const E5 S = bb::e5_add_base(bb::e5_mul(z[q], D), sums[(size_t)c * BARY_OUT + 10]);
             (*ys)[(size_t)q * w + c] = bb::e5_mul(S, norm);
         }
     }
-    return 0;
 }
+uint32_t vg_eval_columns_words(uint32_t w) { return w * BARY_OUT; }
 
-int32_t vg_reduced_opening_accumulate(vgpu_ctx* ctx, const vgpu_dmat* lde, const E5* d_apow, uint32_t npoints, const uint32_t* const* invden,
-                                      const E5* sum_y, const E5* alpha_off, uint32_t* ro) {
-    RoParams p{};
-    p.mat = lde->d; p.mcs = lde->col_stride; p.H = lde->h; p.w = (uint32_t)lde->w; p.apow = d_apow;
-    p.npoints = npoints; p.ics = lde->h;
-    for (uint32_t q = 0; q < npoints; q++) { p.invden[q] = invden[q]; p.sum_y[q] = sum_y[q]; p.alpha_off[q] = alpha_off[q]; }
-    p.ro = ro; p.rcs = lde->h;
+// ro[i] += sum_q alpha^(off_q) * (sum_c alpha^c p_c(x_i) - sum_y[q]) / (x_i - z_q),  off_1 = off_0 + w.
+// apow_off[c] = alpha^(off_0 + c) (host, Montgomery), alpha_w = alpha^w, sum_y[q] = sum_c alpha^c p_c(z_q).
+int32_t vg_reduced_opening_accumulate(vgpu_ctx* ctx, const vgpu_dmat* lde, const E5* apow_off, const E5& alpha_w, uint32_t npoints, const uint32_t* const* invden,
+                                      const E5* sum_y, uint32_t* ro) {
+    auto p = std::make_unique<RoParams>();
+    p->mcs = lde->col_stride; p->H = lde->h;
+    p->npoints = npoints; p->ics = lde->h;
+    p->invden[0] = invden[0]; p->invden[1] = npoints > 1 ? invden[1] : invden[0];
+    p->b[0] = bb::e5_mul(apow_off[0], sum_y[0]);                                        // alpha^off_0 * sum_y_0
+    p->b[1] = npoints > 1 ? bb::e5_mul(bb::e5_mul(apow_off[0], alpha_w), sum_y[1]) : bb::e5_zero();
+    p->aw = alpha_w;
+    for (int l = 0; l < 5; l++) p->aw2.c[l] = bb::dbl(alpha_w.c[l]);
+    p->ro = ro; p->rcs = lde->h;
     // split across ranks: a rank accumulates only its range of rows; vg_reduced_openings_complete() joins the ranges
     const bool split = vg_split_rows(ctx, lde->h / 2);
     const uint64_t rows = split ? lde->h / ctx->comm_size : lde->h;
-    p.row_begin = split ? rows * ctx->comm_rank : 0; p.row_end = p.row_begin + rows;
-    {
-        KScope ks(ctx, KC_REDUCED_OPENING, (double)rows * (4.0 * lde->w + 40.0));
-        reduced_opening_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(p);
+    p->row_begin = split ? rows * ctx->comm_rank : 0; p->row_end = p->row_begin + rows;
+    for (uint64_t c0 = 0; c0 < lde->w; c0 += RO_MAXW) {         // one launch unless the matrix is wider than the parameter table
+        const uint32_t wc = (uint32_t)std::min<uint64_t>(RO_MAXW, lde->w - c0);
+        p->mat = lde->d + c0 * lde->col_stride; p->w = wc; p->first = c0 == 0;
+        for (uint32_t c = 0; c < wc; c++) for (int l = 0; l < 5; l++) p->apow[c][l] = apow_off[c0 + c].c[l];
+        KScope ks(ctx, KC_REDUCED_OPENING, (double)rows * (4.0 * wc + 40.0));
+        if (npoints > 1) reduced_opening_kernel<2><<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(*p);
+        else reduced_opening_kernel<1><<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(*p);
+        VG_LAUNCH_CHECK(ctx);
     }
-    VG_LAUNCH_CHECK(ctx);
     return 0;
 }
 

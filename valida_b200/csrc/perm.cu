@@ -31,11 +31,9 @@ __global__ void __launch_bounds__(256) perm_denominators_kernel(const DevChip* _
     if (n >= h) return;
     for (uint32_t m = 0; m < chip->n_interactions; m++) {
         const DevInteraction& it = chip->interactions[m];
-        E5 rlc = it.alpha;
-        for (uint32_t j = 0; j < it.n_fields; j++) {
-            uint32_t f = pair_col_eval(it.fields[j], main, mcs, prep, pcs, n);
-            rlc = bb::e5_add(rlc, bb::e5_mul_base(chip->betas[j], f));
-        }
+        bb::Lazy5 ra; ra.init();        // sum_j beta^j * field_j as raw 64-bit products, reduced once
+        for (uint32_t j = 0; j < it.n_fields; j++) ra.fma_base(chip->betas[j], pair_col_eval(it.fields[j], main, mcs, prep, pcs, n));
+        const E5 rlc = bb::e5_add(it.alpha, ra.value());
 #pragma unroll
         for (int l = 0; l < 5; l++) perm[(uint64_t)(5 * m + l) * qcs + n] = rlc.c[l];
     }

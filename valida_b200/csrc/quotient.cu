@@ -14,15 +14,24 @@
 // and 9x the writes; see profiles/r01_summary.md.
 // alpha-folding: acc = sum_i c_i * alpha^(N-1-i) with precomputed powers — the same value as the
 // reference's Horner recurrence acc = acc*alpha + c_i, at 5 instead of 25 multiplications for the
-// base-field constraints.
+// base-field constraints.  The sum is accumulated LAZILY (bb::Lazy5: raw 64-bit products, one IMAD.WIDE
+// per limb and constraint, a fold every fourth) and reduced once per row; the powers sit in the kernel
+// parameters (constant bank), so a base-field constraint costs ~7 instructions instead of 50.
+// The selectors need 1/((x-1)(x-g^-1)) on both rows of a pair: the product over the pair is symmetric,
+// vg_selector_inverses() inverts it for every pair of a height with the Montgomery batch trick (one
+// Fermat inversion per 8 pairs) instead of one Fermat inversion (~46 multiplications) per row.
 #include "ctx.h"
 #include "devchip.h"
 #include "airs.cuh"
+#include <cstring>
+#include <memory>
 
 namespace {
 
 using bb::E5;
 using air::F;
+
+constexpr uint32_t Q_MAX_CONSTRAINTS = 128;   // bitwise: 88 base + interactions + 3
 
 struct QParams {
     const DevChip* chip;
@@ -30,7 +39,7 @@ struct QParams {
     const uint32_t* prep; uint64_t pcs;
     const uint32_t* perm; uint64_t qcs;
     uint32_t* out; uint64_t ocs;            // h x 10 chunk matrix
-    const E5* apow;                         // apow[i] = alpha^(N-1-i)
+    const uint32_t* selinv;                 // selinv[r] = 1 / ((x-1)(x-glast)(-x-1)(-x-glast)), x = s * w^bitrev(r)
     uint32_t log_h;
     uint64_t row_begin, row_end;            // storage rows of the LDE swept by this launch (a rank's range when the sweep is split)
     uint32_t s;                             // coset shift (Montgomery)
@@ -40,17 +49,19 @@ struct QParams {
     uint32_t half;                          // 1 / 2
     E5 cumsum;
     const uint32_t* root_lo; const uint32_t* root_hi;
+    uint32_t apow[Q_MAX_CONSTRAINTS][5];    // apow[i] = alpha^(N-1-i)
 };
 
 struct DevBuilder {
     using V = air::F;
     const uint32_t* lrow; const uint32_t* nrow; uint64_t cs;   // pointers already offset to the row
     F first, last, trans;
-    const E5* apow; uint32_t idx; E5 acc;
+    const uint32_t (*apow)[5]; uint32_t idx; bb::Lazy5 acc;
     __device__ __forceinline__ F L(int c) const { return F{__ldg(lrow + (uint64_t)c * cs)}; }
     __device__ __forceinline__ F N(int c) const { return F{__ldg(nrow + (uint64_t)c * cs)}; }
-    __device__ __forceinline__ void z(F x) { acc = bb::e5_add(acc, bb::e5_mul_base(apow[idx], x.v)); idx++; }
-    __device__ __forceinline__ void z_ext(const E5& x) { acc = bb::e5_add(acc, bb::e5_mul(apow[idx], x)); idx++; }
+    __device__ __forceinline__ E5 pw() const { E5 a; for (int l = 0; l < 5; l++) a.c[l] = apow[idx][l]; return a; }
+    __device__ __forceinline__ void z(F x) { acc.fma_base(pw(), x.v); idx++; }
+    __device__ __forceinline__ void z_ext(const E5& x) { acc.fma_ext(pw(), x, bb::e5_dbl(x)); idx++; }
 };
 
 __device__ __forceinline__ uint32_t qroot_pow(const QParams& p, uint64_t e) {
@@ -73,7 +84,7 @@ __device__ __forceinline__ E5 load_e5(const uint32_t* row, uint64_t cs, uint32_t
 }
 
 template <int CHIP>
-__global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
+__global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QParams p) {
     const uint64_t h = 1ull << p.log_h, H = 2 * h;
     const uint64_t rho_raw = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
     const bool active = rho_raw < p.row_end;
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
         const uint32_t nx0 = bb::neg(x0);
         const uint32_t d0 = bb::sub(x0, bb::R1), d1 = bb::sub(x0, p.glast), d2 = bb::sub(nx0, bb::R1), d3 = bb::sub(nx0, p.glast);
         const uint32_t p01 = bb::mul(d0, d1), p23 = bb::mul(d2, d3);
-        const uint32_t all = bb::inv(bb::mul(p01, p23));
+        const uint32_t all = __ldg(p.selinv + r);
         const uint32_t i01 = bb::mul(all, p23), i23 = bb::mul(all, p01);
         inv_first = e ? bb::mul(i23, d3) : bb::mul(i01, d1);
         inv_last = e ? bb::mul(i23, d2) : bb::mul(i01, d0);
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
     b.first = F{bb::mul(zh, inv_first)};
     b.last = F{bb::mul(zh, inv_last)};
     b.trans = F{bb::sub(x, p.glast)};
-    b.apow = p.apow; b.idx = 0; b.acc = bb::e5_zero();
+    b.apow = p.apow; b.idx = 0; b.acc.init();
     air::eval_chip<CHIP>(b);
     {   // eval_permutation_constraints
         const uint32_t* ql = p.perm + rho; const uint32_t* qn = p.perm + nrow;
@@ -117,8 +128,9 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
         E5 rhs = bb::e5_zero(), phi0 = bb::e5_zero();
         for (uint32_t m = 0; m < k; m++) {
             const DevInteraction& it = chip.interactions[m];
-            E5 rlc = it.alpha;
-            for (uint32_t f = 0; f < it.n_fields; f++) rlc = bb::e5_add(rlc, bb::e5_mul_base(chip.betas[f], dev_pair_col(it.fields[f], b.lrow, p.mcs, pl, p.pcs)));
+            bb::Lazy5 ra; ra.init();
+            for (uint32_t f = 0; f < it.n_fields; f++) ra.fma_base(chip.betas[f], dev_pair_col(it.fields[f], b.lrow, p.mcs, pl, p.pcs));
+            const E5 rlc = bb::e5_add(it.alpha, ra.value());
             const E5 pm_l = load_e5(ql, p.qcs, m), pm_n = load_e5(qn, p.qcs, m);
             b.z_ext(bb::e5_sub_base(bb::e5_mul(rlc, pm_l), bb::R1));
             const uint32_t mult_l = dev_pair_col(it.count, b.lrow, p.mcs, pl, p.pcs), mult_n = dev_pair_col(it.count, b.nrow, p.mcs, pn, p.pcs);
@@ -130,7 +142,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
         b.z_ext(bb::e5_mul_base(bb::e5_sub(phi_local, phi0), b.first.v));
         b.z_ext(bb::e5_mul_base(bb::e5_sub(phi_local, p.cumsum), b.last.v));
     }
-    const E5 q = bb::e5_mul_base(b.acc, p.zinv[parity]);
+    const E5 q = bb::e5_mul_base(b.acc.value(), p.zinv[parity]);
     // decompose_and_flatten across the lane pair: even = (q(x) + q(-x))/2, odd = (q(x) - q(-x)) / (2 s g^j)
     E5 other;
 #pragma unroll
@@ -147,6 +159,38 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams p) {
         // (coalesced), which the commit's inverse transform consumes directly
 #pragma unroll
         for (int l = 0; l < 5; l++) p.out[(uint64_t)(5 * e + l) * p.ocs + r] = outv.c[l];
+    }
+}
+
+// selinv[r] = 1 / ((x0-1)(x0-glast)(-x0-1)(-x0-glast)), x0 = s * w_2h^bitrev(r), for the pairs [begin, begin + count).
+// Montgomery batch trick over SEL_BATCH pairs per thread, pairs of one thread a grid apart (coalesced).
+constexpr int SEL_BATCH = 8;
+__global__ void __launch_bounds__(256) selector_inverse_kernel(uint32_t* __restrict__ out, uint64_t begin, uint64_t count, uint32_t log_h, uint32_t s, uint32_t glast,
+                                                               const uint32_t* __restrict__ root_lo, const uint32_t* __restrict__ root_hi) {
+    const uint64_t stride = (count + SEL_BATCH - 1) / SEL_BATCH;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    uint32_t v[SEL_BATCH], pref[SEL_BATCH];
+    uint32_t acc = bb::R1;
+#pragma unroll
+    for (int i = 0; i < SEL_BATCH; i++) {
+        const uint64_t r = begin + t + (uint64_t)i * stride;
+        v[i] = bb::R1;
+        if (t + (uint64_t)i * stride < count) {
+            const uint32_t j = bb::reverse_bits((uint32_t)r, (int)log_h);
+            uint64_t e = ((uint64_t)j << (VG_LOG_NMAX - log_h - 1)) & ((1ull << VG_LOG_NMAX) - 1);
+            const uint32_t x0 = bb::mul(s, bb::mul(__ldg(root_lo + (e & (VG_POW_LO - 1))), __ldg(root_hi + (e >> VG_POW_LO_BITS))));
+            const uint32_t nx0 = bb::neg(x0);
+            v[i] = bb::mul(bb::mul(bb::sub(x0, bb::R1), bb::sub(x0, glast)), bb::mul(bb::sub(nx0, bb::R1), bb::sub(nx0, glast)));
+        }
+        pref[i] = acc;
+        acc = bb::mul(acc, v[i]);
+    }
+    uint32_t inv = bb::inv(acc);
+#pragma unroll
+    for (int i = SEL_BATCH - 1; i >= 0; i--) {
+        if (t + (uint64_t)i * stride < count) out[begin + t + (uint64_t)i * stride] = bb::mul(inv, pref[i]);
+        inv = bb::mul(inv, v[i]);
     }
 }
 
@@ -187,22 +231,20 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     VG_TRY(vg_upload_devchip(ctx, chip, perm_challenges, &dchip));
     // alpha powers for N = base + k + 3 constraints
     const uint32_t N = vg_chip_base_constraints(chip->chip_id) + chip->n_interactions + 3;
-    std::vector<E5> apow(N);
+    if (N > Q_MAX_CONSTRAINTS) { vg_free(ctx, dchip); VG_FAIL(ctx, "quotient: %u constraints exceed the parameter table (%u)", N, Q_MAX_CONSTRAINTS); }
+    auto pp = std::make_unique<QParams>();
+    QParams& p = *pp;
+    std::memset(&p, 0, sizeof p);
     E5 al; for (int i = 0; i < 5; i++) al.c[i] = bb::to_monty(alpha[i] % bb::P);
-    { E5 a = bb::e5_one(); for (uint32_t i = 0; i < N; i++) { apow[N - 1 - i] = a; a = bb::e5_mul(a, al); } }
-    E5* d_apow = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&d_apow, N * sizeof(E5)));
-    VG_CUDA(ctx, cudaMemcpyAsync(d_apow, apow.data(), N * sizeof(E5), cudaMemcpyHostToDevice, ctx->stream));
+    { E5 a = bb::e5_one(); for (uint32_t i = 0; i < N; i++) { for (int l = 0; l < 5; l++) p.apow[N - 1 - i][l] = a.c[l]; a = bb::e5_mul(a, al); } }
     vgpu_dmat* out = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, h, 10, &out));
     out->bitrev_rows = true;
-    QParams p{};
     p.chip = dchip;
     p.main = main_lde->d; p.mcs = main_lde->col_stride;
     p.prep = prep_lde ? prep_lde->d : nullptr; p.pcs = prep_lde ? prep_lde->col_stride : 0;
     p.perm = perm_lde->d; p.qcs = perm_lde->col_stride;
     p.out = out->d; p.ocs = out->col_stride;
-    p.apow = d_apow;
     p.log_h = log_degree;
     p.s = bb::to_monty(bb::GEN_CANON);
     uint32_t g_sub = bb::two_adic_generator_monty((int)log_degree);
@@ -219,7 +261,15 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     const bool split = vg_split_rows(ctx, 2 * h);
     p.row_begin = split ? (2 * h / ctx->comm_size) * ctx->comm_rank : 0;
     p.row_end = split ? p.row_begin + 2 * h / ctx->comm_size : 2 * h;
+    uint32_t* selinv = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&selinv, h * 4));
+    p.selinv = selinv;
     KScope* ks = new KScope(ctx, KC_QUOTIENT, 8.0 * (double)h * (main_lde->w + perm_lde->w + (prep_lde ? prep_lde->w : 0)) + 40.0 * (double)h);
+    {   // pairs [row_begin / 2, row_end / 2)
+        const uint64_t pb = p.row_begin / 2, pc = (p.row_end - p.row_begin) / 2, stride = (pc + SEL_BATCH - 1) / SEL_BATCH;
+        selector_inverse_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, ctx->stream>>>(selinv, pb, pc, log_degree, p.s, p.glast, p.root_lo, p.root_hi);
+        ctx->launches++;
+    }
     switch (chip->chip_id) {
         case 0: launch<0>(p, h, ctx->stream); break;   case 1: launch<1>(p, h, ctx->stream); break;
         case 2: launch<2>(p, h, ctx->stream); break;   case 3: launch<3>(p, h, ctx->stream); break;
@@ -236,8 +286,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
         for (int c = 0; c < 10; c++) VG_TRY(vg_comm_allgather_inplace(ctx, out->d + (uint64_t)c * out->col_stride, h / ctx->comm_size));
         VG_TRY(vg_comm_group_end(ctx));
     }
-    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // apow host vector / device temporaries
-    vg_free(ctx, d_apow); vg_free(ctx, dchip);
+    vg_free(ctx, selinv); vg_free(ctx, dchip);
     *out_chunks = out;
     return 0;
 }
