@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) bary_small_kernel(BaryParams p) {
 //     ro[i] += (U - B_0) / (x_i - z_0)  +  (U * alpha^w - B_1) / (x_i - z_1),      B_q = alpha^(off_q) sum_c alpha^c p_c(z_q)
 // which is the reference's  alpha^off_q * (sum_c alpha^c p_c(x_i) - sum_c alpha^c p_c(z_q)) / (x_i - z_q)  summed over the
 // points (off_1 = off_0 + w): shifting the power table by off_0 removes one ext5 product per point from every row.
-constexpr uint32_t RO_MAXW = 96;
+constexpr uint32_t RO_MAXW = 96;   // multiple of 4: the sweep reads the power table in whole groups
 struct RoParams {
     const uint32_t* mat; uint64_t mcs; uint64_t H; uint32_t w;
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
@@ -205,27 +205,35 @@ template <int NP>
 __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_constant__ RoParams p) {
     const uint64_t i = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.row_end) return;
-    uint64_t a[5] = {0, 0, 0, 0, 0};
     const uint32_t* m = p.mat + i;
-    uint32_t c = 0;
-    for (; c + 8 <= p.w; c += 8) {   // eight loads in flight, two folds per limb
-        uint32_t e[8];
+    // Columns in groups of four (one fold per group and limb), loads running two groups ahead of the arithmetic, and the
+    // row's denominators / running value requested before the sweep: ncu (r1b) had this kernel waiting on global loads
+    // (long-scoreboard stall 10 per issue, DRAM 38 %) with only the current group's loads in flight.
+    const uint32_t G = (p.w + 3) / 4;
+    auto load4 = [&](uint32_t g, uint32_t e[4]) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) e[u] = __ldg(m + (uint64_t)(c + u) * p.mcs);
+        for (int u = 0; u < 4; u++) { const uint32_t c = 4 * g + u; e[u] = c < p.w ? __ldg(m + (uint64_t)c * p.mcs) : 0u; }   // a zero term adds nothing
+    };
+    uint32_t ea[4], eb[4];
+    load4(0, ea);
+    if (G > 1) load4(1, eb); else { eb[0] = eb[1] = eb[2] = eb[3] = 0; }
+    const E5 inv0 = ld5(p.invden[0], p.ics, i);
+    E5 inv1 = inv0;
+    if (NP > 1) inv1 = ld5(p.invden[1], p.ics, i);
+    const E5 ro_old = ld5(p.ro, p.rcs, i);
+    uint64_t a[5] = {0, 0, 0, 0, 0};
+    for (uint32_t g = 0; g < G; g++) {
+        uint32_t e[4];
 #pragma unroll
-        for (int g = 0; g < 8; g += 4)
+        for (int u = 0; u < 4; u++) { e[u] = ea[u]; ea[u] = eb[u]; }
+        if (g + 2 < G) load4(g + 2, eb);
 #pragma unroll
-            for (int l = 0; l < 5; l++) {
-                uint64_t t = a[l];
+        for (int l = 0; l < 5; l++) {
+            uint64_t t = a[l];
 #pragma unroll
-                for (int u = 0; u < 4; u++) t = bb::madw(e[g + u], p.apow[c + g + u][l], t);
-                a[l] = bb::lazy_fold(t);
-            }
-    }
-    for (; c < p.w; c++) {
-        const uint32_t e0 = __ldg(m + (uint64_t)c * p.mcs);
-#pragma unroll
-        for (int l = 0; l < 5; l++) a[l] = bb::lazy_fold(bb::madw(e0, p.apow[c][l], a[l]));
+            for (int u = 0; u < 4; u++) t = bb::madw(e[u], p.apow[4 * g + u][l], t);
+            a[l] = bb::lazy_fold(t);
+        }
     }
     E5 U;
 #pragma unroll
@@ -233,16 +241,16 @@ __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_const
     bb::Lazy5 s; s.init();
     {
         const E5 w0 = p.first ? bb::e5_sub(U, p.b[0]) : U;
-        s.fma_ext(ld5(p.invden[0], p.ics, i), w0, bb::e5_dbl(w0));
+        s.fma_ext(inv0, w0, bb::e5_dbl(w0));
     }
     if (NP > 1) {
         bb::Lazy5 t; t.init();
         t.fma_ext(U, p.aw, p.aw2);
         E5 w1 = t.value();
         if (p.first) w1 = bb::e5_sub(w1, p.b[1]);
-        s.fma_ext(ld5(p.invden[1], p.ics, i), w1, bb::e5_dbl(w1));
+        s.fma_ext(inv1, w1, bb::e5_dbl(w1));
     }
-    st5(p.ro, p.rcs, i, bb::e5_add(ld5(p.ro, p.rcs, i), s.value()));
+    st5(p.ro, p.rcs, i, bb::e5_add(ro_old, s.value()));
 }
 
 // K10: out[i] = (lo + hi)/2 + (beta/2) * g_inv^bitrev(i) * (lo - hi)  (+ add[i])
@@ -279,12 +287,100 @@ __global__ void __launch_bounds__(256) gather_words_kernel(const uint32_t* const
 
 }  // namespace
 
+// 1/(x - z) without an extension-field inversion.  x is a base-field point, so the conjugates of x - z are x - frob^k(z):
+//     1/(x - z) = Q(x) / M(x),   M(x) = prod_{k=0..4} (x - frob^k z)  (minimal polynomial of z: base-field coefficients),
+//                                Q(x) = prod_{k=1..4} (x - frob^k z)  (degree 4, ext5 coefficients).
+// Per element: the powers of x, two lazy dot products (M: 6 terms, Q: 5 x 5 terms) and a share of ONE base-field Fermat
+// inversion per INVDEN_BATCH elements (Montgomery batch trick) — about 2.3x fewer instructions than forming x - z in
+// ext5 and batch-inverting there (3 ext5 products per element plus a Frobenius-norm inversion per 8).
+constexpr int INVDEN_BATCH = 16;
+struct InvdenParams {
+    uint32_t* out; uint64_t H, begin, count; uint32_t log_h, s;
+    uint32_t mc[5];          // M(x) = x^5 + sum_j mc[j] x^j
+    uint32_t qc[4][5];       // Q(x) = x^4 + sum_j qc[j] x^j   (qc[j] ext5, limb l at qc[j][l])
+    const uint32_t* lo; const uint32_t* hi;
+};
+__global__ void __launch_bounds__(128) invden_norm_kernel(const __grid_constant__ InvdenParams p) {
+    const uint64_t stride = (p.count + INVDEN_BATCH - 1) / INVDEN_BATCH;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    auto point = [&](uint64_t i) {
+        const uint32_t nat = bb::reverse_bits((uint32_t)i, (int)p.log_h);
+        return bb::mul(p.s, oroot_pow(p.lo, p.hi, (uint64_t)nat << (VG_LOG_NMAX - p.log_h)));
+    };
+    uint32_t v[INVDEN_BATCH], pref[INVDEN_BATCH];
+    uint32_t acc = bb::R1;
+#pragma unroll
+    for (int k = 0; k < INVDEN_BATCH; k++) {
+        const uint64_t j = t + (uint64_t)k * stride;
+        v[k] = bb::R1;
+        if (j < p.count) {
+            const uint32_t x = point(p.begin + j);
+            const uint32_t x2 = bb::sqr(x), x3 = bb::mul(x2, x), x4 = bb::sqr(x2), x5 = bb::mul(x4, x);
+            uint64_t m = bb::madw(p.mc[4], x4, bb::madw(p.mc[3], x3, bb::madw(p.mc[2], x2, bb::madw(p.mc[1], x, 0))));
+            m = bb::madw(x5, bb::R1, bb::madw(p.mc[0], bb::R1, bb::lazy_fold(m)));
+            v[k] = bb::monty_reduce64(m);
+        }
+        pref[k] = acc;
+        acc = bb::mul(acc, v[k]);
+    }
+    uint32_t inv = bb::inv(acc);
+#pragma unroll
+    for (int k = INVDEN_BATCH - 1; k >= 0; k--) {
+        const uint64_t j = t + (uint64_t)k * stride;
+        const uint32_t minv = bb::mul(inv, pref[k]);
+        inv = bb::mul(inv, v[k]);
+        if (j < p.count) {
+            const uint64_t i = p.begin + j;
+            const uint32_t x = point(i);
+            const uint32_t x2 = bb::sqr(x), x3 = bb::mul(x2, x), x4 = bb::sqr(x2);
+#pragma unroll
+            for (int l = 0; l < 5; l++) {
+                uint64_t q = bb::madw(p.qc[3][l], x3, bb::madw(p.qc[2][l], x2, bb::madw(p.qc[1][l], x, bb::madw(p.qc[0][l], bb::R1, 0))));
+                if (l == 0) q = bb::madw(x4, bb::R1, bb::lazy_fold(q));
+                p.out[(uint64_t)l * p.H + i] = bb::mul(bb::monty_reduce64(q), minv);
+            }
+        }
+    }
+}
+
 static int32_t inverse_denominators_range(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint32_t* out, uint64_t begin, uint64_t count) {
     uint64_t H = 1ull << log_H;
     KScope ks(ctx, KC_INVDEN, 20.0 * (double)count);
-    coset_minus_point_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, H, begin, count, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
+    if ((z.c[1] | z.c[2] | z.c[3] | z.c[4]) == 0) {
+        // z in the base field may hit a coset point: the generic path keeps a zero denominator as zero
+        coset_minus_point_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, H, begin, count, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
+        VG_LAUNCH_CHECK(ctx);
+        return vg_ext_batch_inverse(ctx, out + begin, H, count, 1);
+    }
+    InvdenParams p{};
+    p.out = out; p.H = H; p.begin = begin; p.count = count; p.log_h = log_H; p.s = bb::to_monty(bb::GEN_CANON);
+    p.lo = ctx->root_table.lo; p.hi = ctx->root_table.hi;
+    {   // poly(x) = prod (x - frob^k z): coefficients low to high, ext5 arithmetic on the host
+        uint32_t zp[5];
+        bb::e5_frob_consts(zp);
+        E5 conj[5];
+        conj[0] = z;
+        for (int k = 1; k < 5; k++) conj[k] = bb::e5_frobenius(conj[k - 1], zp);
+        auto times_x_minus = [](std::vector<E5>& poly, const E5& r) {
+            std::vector<E5> n(poly.size() + 1, bb::e5_zero());
+            for (size_t d = 0; d < poly.size(); d++) { n[d + 1] = bb::e5_add(n[d + 1], poly[d]); n[d] = bb::e5_sub(n[d], bb::e5_mul(poly[d], r)); }
+            poly.swap(n);
+        };
+        std::vector<E5> q{bb::e5_one()};
+        for (int k = 1; k < 5; k++) times_x_minus(q, conj[k]);
+        std::vector<E5> m = q;
+        times_x_minus(m, conj[0]);
+        for (int j = 0; j < 5; j++) {
+            if (m[j].c[1] | m[j].c[2] | m[j].c[3] | m[j].c[4]) VG_FAIL(ctx, "inverse denominators: the minimal polynomial left the base field");
+            p.mc[j] = m[j].c[0];
+        }
+        for (int j = 0; j < 4; j++) for (int l = 0; l < 5; l++) p.qc[j][l] = q[j].c[l];
+    }
+    const uint64_t stride = (count + INVDEN_BATCH - 1) / INVDEN_BATCH;
+    invden_norm_kernel<<<(unsigned)((stride + 127) / 128), 128, 0, ctx->stream>>>(p);
     VG_LAUNCH_CHECK(ctx);
-    return vg_ext_batch_inverse(ctx, out + begin, H, count, 1);
+    return 0;
 }
 // When the row sweeps of this height are split across ranks, a rank only ever reads 1/(x - z) on its range of the
 // reduced-opening sweep (all H rows) and on its range of the barycentric sweep (the first H/2 rows); rank 0's second

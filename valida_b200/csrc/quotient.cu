@@ -24,6 +24,7 @@
 #include "devchip.h"
 #include "airs.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 
 namespace {
@@ -34,7 +35,6 @@ using air::F;
 constexpr uint32_t Q_MAX_CONSTRAINTS = 128;   // bitwise: 88 base + interactions + 3
 
 struct QParams {
-    const DevChip* chip;
     const uint32_t* main; uint64_t mcs;
     const uint32_t* prep; uint64_t pcs;
     const uint32_t* perm; uint64_t qcs;
@@ -50,6 +50,8 @@ struct QParams {
     E5 cumsum;
     const uint32_t* root_lo; const uint32_t* root_hi;
     uint32_t apow[Q_MAX_CONSTRAINTS][5];    // apow[i] = alpha^(N-1-i)
+    DevChip chip;                           // interaction descriptors + LogUp randomness: read through the constant bank (uniform loads),
+                                            // not through dependent global loads (ncu r1b: 27-54 % of the stall samples sat on those)
 };
 
 struct DevBuilder {
@@ -83,8 +85,9 @@ __device__ __forceinline__ E5 load_e5(const uint32_t* row, uint64_t cs, uint32_t
     return r;
 }
 
-template <int CHIP>
-__global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QParams p) {
+// MINB: resident-CTA target (register cap) of the variant; 0 = ptxas' own choice (80-92 registers, 5 CTAs of 128 threads per SM)
+template <int CHIP, int MINB>
+__global__ void __launch_bounds__(128, MINB ? MINB : 1) quotient_kernel(const __grid_constant__ QParams p) {
     const uint64_t h = 1ull << p.log_h, H = 2 * h;
     const uint64_t rho_raw = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
     const bool active = rho_raw < p.row_end;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
         inv_first = e ? bb::mul(i23, d3) : bb::mul(i01, d1);
         inv_last = e ? bb::mul(i23, d2) : bb::mul(i01, d0);
     }
-    const DevChip& chip = *p.chip;
+    const DevChip& chip = p.chip;
     const uint32_t k = chip.n_interactions;
     const uint32_t parity = (uint32_t)(((uint64_t)j + (e ? h : 0)) & 1);
     const uint32_t zh = p.zh[parity];
@@ -206,7 +209,11 @@ template <int CHIP> uint32_t count_base() { CountBuilder c; air::eval_chip<CHIP>
 
 template <int CHIP> void launch(const QParams& p, uint64_t h, cudaStream_t st) {
     (void)h;
-    quotient_kernel<CHIP><<<(unsigned)((p.row_end - p.row_begin + 127) / 128), 128, 0, st>>>(p);
+    static const int minb = [] { const char* e = getenv("VGPU_QUOTIENT_MINB"); return e ? atoi(e) : 0; }();   // tuning knob (profiles/)
+    const unsigned grid = (unsigned)((p.row_end - p.row_begin + 127) / 128);
+    if (minb == 6) quotient_kernel<CHIP, 6><<<grid, 128, 0, st>>>(p);
+    else if (minb == 8) quotient_kernel<CHIP, 8><<<grid, 128, 0, st>>>(p);
+    else quotient_kernel<CHIP, 0><<<grid, 128, 0, st>>>(p);
 }
 
 }  // namespace
@@ -227,20 +234,18 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     if (main_lde->h != 2 * h || perm_lde->h != 2 * h) VG_FAIL(ctx, "quotient: LDE height must be 2 * 2^log_degree");
     if (main_lde->w != chip->width || perm_lde->w != 5 * (chip->n_interactions + 1)) VG_FAIL(ctx, "quotient: LDE width does not match the chip");
     if (chip->chip_id >= VGPU_NUM_CHIPS) VG_FAIL(ctx, "quotient: unknown chip id %u", chip->chip_id);
-    DevChip* dchip = nullptr;
-    VG_TRY(vg_upload_devchip(ctx, chip, perm_challenges, &dchip));
     // alpha powers for N = base + k + 3 constraints
     const uint32_t N = vg_chip_base_constraints(chip->chip_id) + chip->n_interactions + 3;
-    if (N > Q_MAX_CONSTRAINTS) { vg_free(ctx, dchip); VG_FAIL(ctx, "quotient: %u constraints exceed the parameter table (%u)", N, Q_MAX_CONSTRAINTS); }
+    if (N > Q_MAX_CONSTRAINTS) { VG_FAIL(ctx, "quotient: %u constraints exceed the parameter table (%u)", N, Q_MAX_CONSTRAINTS); }
     auto pp = std::make_unique<QParams>();
     QParams& p = *pp;
     std::memset(&p, 0, sizeof p);
+    VG_TRY(vg_build_devchip(ctx, chip, perm_challenges, &p.chip));
     E5 al; for (int i = 0; i < 5; i++) al.c[i] = bb::to_monty(alpha[i] % bb::P);
     { E5 a = bb::e5_one(); for (uint32_t i = 0; i < N; i++) { for (int l = 0; l < 5; l++) p.apow[N - 1 - i][l] = a.c[l]; a = bb::e5_mul(a, al); } }
     vgpu_dmat* out = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, h, 10, &out));
     out->bitrev_rows = true;
-    p.chip = dchip;
     p.main = main_lde->d; p.mcs = main_lde->col_stride;
     p.prep = prep_lde ? prep_lde->d : nullptr; p.pcs = prep_lde ? prep_lde->col_stride : 0;
     p.perm = perm_lde->d; p.qcs = perm_lde->col_stride;
@@ -286,7 +291,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
         for (int c = 0; c < 10; c++) VG_TRY(vg_comm_allgather_inplace(ctx, out->d + (uint64_t)c * out->col_stride, h / ctx->comm_size));
         VG_TRY(vg_comm_group_end(ctx));
     }
-    vg_free(ctx, selinv); vg_free(ctx, dchip);
+    vg_free(ctx, selinv);
     *out_chunks = out;
     return 0;
 }
