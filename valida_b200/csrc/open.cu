@@ -203,6 +203,11 @@ struct RoParams {
 };
 template <int NP>
 __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_constant__ RoParams p) {
+    // The power table goes from the parameters to shared memory once per CTA: an indexed constant load per product was
+    // the stall behind ncu's "long scoreboard 10 per issue" (LDC with a register index, ~20 of them per 8 columns).
+    __shared__ __align__(16) uint32_t sap[RO_MAXW * 5];
+    for (uint32_t idx = threadIdx.x; idx < ((p.w + 3) / 4) * 20; idx += blockDim.x) sap[idx] = (&p.apow[0][0])[idx];
+    __syncthreads();
     const uint64_t i = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.row_end) return;
     const uint32_t* m = p.mat + i;
@@ -227,11 +232,17 @@ __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_const
 #pragma unroll
         for (int u = 0; u < 4; u++) { e[u] = ea[u]; ea[u] = eb[u]; }
         if (g + 2 < G) load4(g + 2, eb);
+        uint32_t ap[20];                                         // alpha^(off + 4g + u) limb l at ap[5u + l]
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sap + 20 * g + 4 * k);
+            ap[4 * k] = v.x; ap[4 * k + 1] = v.y; ap[4 * k + 2] = v.z; ap[4 * k + 3] = v.w;
+        }
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             uint64_t t = a[l];
 #pragma unroll
-            for (int u = 0; u < 4; u++) t = bb::madw(e[u], p.apow[4 * g + u][l], t);
+            for (int u = 0; u < 4; u++) t = bb::madw(e[u], ap[5 * u + l], t);
             a[l] = bb::lazy_fold(t);
         }
     }
