@@ -331,24 +331,29 @@ def main():
     # Keccak trees, NCCL exchange over NVLink) — latency of one proof on N GPUs, beside the replica throughput ----
     sharded = None
     if dist is not None:
-        ctx.comm_init_from_torch()
-        for _ in range(2):
-            proof_sh = vb.prove_machine(cfg, traces, device_resident=(dm, dp))
-        assert proof_sh == proof, "split proof differs from the single-GPU proof"
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        for _ in range(args.steps):
-            vb.prove_machine(cfg, traces, device_resident=(dm, dp))
-        s1.record(stream)
-        barrier()
-        ms_sh = s0.elapsed_time(s1)
-        sh_phases = vb.last_prove_phases(ctx)
-        _, ms_sh_max = aggregate_throughput(dist, rows * args.steps, ms_sh, device="cuda")
-        ctx.set_sharding(False)
-        sharded = {"what": "ONE proof per step split across %d GPUs (strong scaling of a single proof)" % world,
-                   "ms_per_proof": ms_sh_max / args.steps, "rows_per_s": rows * args.steps / (ms_sh_max / 1e3),
-                   "proof_bytes_identical": True, "phases_ms": {k: v for k, v in sh_phases}}
+        # the split-proof figure is extra to the contract line: a failure here is reported inside `sharded`, it does not
+        # take the replica throughput (already measured above) down with it
+        try:
+            ctx.comm_init_from_torch()
+            for _ in range(2):
+                proof_sh = vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+            identical = proof_sh == proof
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for _ in range(args.steps):
+                vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+            s1.record(stream)
+            barrier()
+            ms_sh = s0.elapsed_time(s1)
+            sh_phases = vb.last_prove_phases(ctx)
+            _, ms_sh_max = aggregate_throughput(dist, rows * args.steps, ms_sh, device="cuda")
+            ctx.set_sharding(False)
+            sharded = {"what": "ONE proof per step split across %d GPUs (strong scaling of a single proof)" % world,
+                       "ms_per_proof": ms_sh_max / args.steps, "rows_per_s": rows * args.steps / (ms_sh_max / 1e3),
+                       "proof_bytes_identical": bool(identical), "phases_ms": {k: v for k, v in sh_phases}}
+        except Exception as exc:   # noqa: BLE001
+            sharded = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank != 0:
         if dist is not None:

@@ -37,8 +37,8 @@ int32_t vg_upload_devchip(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const uint3
     VG_TRY(vg_build_devchip(ctx, chip, ch, &host));
     DevChip* d = nullptr;
     VG_TRY(vg_alloc(ctx, (void**)&d, sizeof(DevChip)));
-    // pageable source: the copy is staged before the call returns, so `host` may go out of scope (no synchronisation needed)
     VG_CUDA(ctx, cudaMemcpyAsync(d, &host, sizeof(DevChip), cudaMemcpyHostToDevice, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out_device = d;
     return 0;
 }

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) bary_small_kernel(BaryParams p) {
 //     ro[i] += (U - B_0) / (x_i - z_0)  +  (U * alpha^w - B_1) / (x_i - z_1),      B_q = alpha^(off_q) sum_c alpha^c p_c(z_q)
 // which is the reference's  alpha^off_q * (sum_c alpha^c p_c(x_i) - sum_c alpha^c p_c(z_q)) / (x_i - z_q)  summed over the
 // points (off_1 = off_0 + w): shifting the power table by off_0 removes one ext5 product per point from every row.
-constexpr uint32_t RO_MAXW = 96;   // multiple of 4: the sweep reads the power table in whole groups
+constexpr uint32_t RO_MAXW = 96;
 struct RoParams {
     const uint32_t* mat; uint64_t mcs; uint64_t H; uint32_t w;
     const uint32_t* invden[2]; uint64_t ics; uint32_t npoints;
@@ -201,50 +201,33 @@ struct RoParams {
     uint32_t first;                   // 1: this launch also subtracts B_q (0 on the later column blocks of a matrix wider than RO_MAXW)
     uint32_t apow[RO_MAXW][5];        // alpha^(off_0 + c)
 };
+// (Measured alternatives that did not help, 6.5-6.8 ms per proof each: loads two column groups ahead of the arithmetic;
+// the power table in shared memory instead of indexed constant loads.  ncu r1b: issue slots 50 % busy, FMA pipe 34 %.)
 template <int NP>
 __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_constant__ RoParams p) {
-    // The power table goes from the parameters to shared memory once per CTA: an indexed constant load per product was
-    // the stall behind ncu's "long scoreboard 10 per issue" (LDC with a register index, ~20 of them per 8 columns).
-    __shared__ __align__(16) uint32_t sap[RO_MAXW * 5];
-    for (uint32_t idx = threadIdx.x; idx < ((p.w + 3) / 4) * 20; idx += blockDim.x) sap[idx] = (&p.apow[0][0])[idx];
-    __syncthreads();
     const uint64_t i = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.row_end) return;
-    const uint32_t* m = p.mat + i;
-    // Columns in groups of four (one fold per group and limb), loads running two groups ahead of the arithmetic, and the
-    // row's denominators / running value requested before the sweep: ncu (r1b) had this kernel waiting on global loads
-    // (long-scoreboard stall 10 per issue, DRAM 38 %) with only the current group's loads in flight.
-    const uint32_t G = (p.w + 3) / 4;
-    auto load4 = [&](uint32_t g, uint32_t e[4]) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t c = 4 * g + u; e[u] = c < p.w ? __ldg(m + (uint64_t)c * p.mcs) : 0u; }   // a zero term adds nothing
-    };
-    uint32_t ea[4], eb[4];
-    load4(0, ea);
-    if (G > 1) load4(1, eb); else { eb[0] = eb[1] = eb[2] = eb[3] = 0; }
-    const E5 inv0 = ld5(p.invden[0], p.ics, i);
-    E5 inv1 = inv0;
-    if (NP > 1) inv1 = ld5(p.invden[1], p.ics, i);
-    const E5 ro_old = ld5(p.ro, p.rcs, i);
     uint64_t a[5] = {0, 0, 0, 0, 0};
-    for (uint32_t g = 0; g < G; g++) {
-        uint32_t e[4];
+    const uint32_t* m = p.mat + i;
+    uint32_t c = 0;
+    for (; c + 8 <= p.w; c += 8) {   // eight loads in flight, two folds per limb
+        uint32_t e[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { e[u] = ea[u]; ea[u] = eb[u]; }
-        if (g + 2 < G) load4(g + 2, eb);
-        uint32_t ap[20];                                         // alpha^(off + 4g + u) limb l at ap[5u + l]
+        for (int u = 0; u < 8; u++) e[u] = __ldg(m + (uint64_t)(c + u) * p.mcs);
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const uint4 v = *reinterpret_cast<const uint4*>(sap + 20 * g + 4 * k);
-            ap[4 * k] = v.x; ap[4 * k + 1] = v.y; ap[4 * k + 2] = v.z; ap[4 * k + 3] = v.w;
-        }
+        for (int g = 0; g < 8; g += 4)
 #pragma unroll
-        for (int l = 0; l < 5; l++) {
-            uint64_t t = a[l];
+            for (int l = 0; l < 5; l++) {
+                uint64_t t = a[l];
 #pragma unroll
-            for (int u = 0; u < 4; u++) t = bb::madw(e[u], ap[5 * u + l], t);
-            a[l] = bb::lazy_fold(t);
-        }
+                for (int u = 0; u < 4; u++) t = bb::madw(e[g + u], p.apow[c + g + u][l], t);
+                a[l] = bb::lazy_fold(t);
+            }
+    }
+    for (; c < p.w; c++) {
+        const uint32_t e0 = __ldg(m + (uint64_t)c * p.mcs);
+#pragma unroll
+        for (int l = 0; l < 5; l++) a[l] = bb::lazy_fold(bb::madw(e0, p.apow[c][l], a[l]));
     }
     E5 U;
 #pragma unroll
@@ -252,16 +235,16 @@ __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_const
     bb::Lazy5 s; s.init();
     {
         const E5 w0 = p.first ? bb::e5_sub(U, p.b[0]) : U;
-        s.fma_ext(inv0, w0, bb::e5_dbl(w0));
+        s.fma_ext(ld5(p.invden[0], p.ics, i), w0, bb::e5_dbl(w0));
     }
     if (NP > 1) {
         bb::Lazy5 t; t.init();
         t.fma_ext(U, p.aw, p.aw2);
         E5 w1 = t.value();
         if (p.first) w1 = bb::e5_sub(w1, p.b[1]);
-        s.fma_ext(inv1, w1, bb::e5_dbl(w1));
+        s.fma_ext(ld5(p.invden[1], p.ics, i), w1, bb::e5_dbl(w1));
     }
-    st5(p.ro, p.rcs, i, bb::e5_add(ro_old, s.value()));
+    st5(p.ro, p.rcs, i, bb::e5_add(ld5(p.ro, p.rcs, i), s.value()));
 }
 
 // K10: out[i] = (lo + hi)/2 + (beta/2) * g_inv^bitrev(i) * (lo - hi)  (+ add[i])

@@ -26,13 +26,10 @@ __device__ __forceinline__ uint32_t pair_col_eval(const DevPairCol& pc, const ui
     return v;
 }
 
-// The chip descriptor is staged in shared memory by every CTA (devchip_to_shared): descriptor reads are broadcast LDS.
-__global__ void __launch_bounds__(256) perm_denominators_kernel(const DevChip* __restrict__ chip_g, const uint32_t* __restrict__ main, uint64_t mcs,
+// The chip descriptor travels in the kernel parameters (constant bank): descriptor reads are uniform constant loads.
+__global__ void __launch_bounds__(256) perm_denominators_kernel(const __grid_constant__ DevChip chip_, const uint32_t* __restrict__ main, uint64_t mcs,
                                                                const uint32_t* __restrict__ prep, uint64_t pcs, uint64_t h, uint32_t* __restrict__ perm, uint64_t qcs) {
-    __shared__ DevChip s_chip;
-    devchip_to_shared(&s_chip, chip_g);
-    __syncthreads();
-    const DevChip* chip = &s_chip;
+    const DevChip* chip = &chip_;
     uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= h) return;
     for (uint32_t m = 0; m < chip->n_interactions; m++) {
@@ -86,12 +83,9 @@ __global__ void __launch_bounds__(128) ext_batch_inverse_kernel(uint32_t* __rest
 }
 
 // term[n] = sum_m (+-) q[n][m] * count_m(n), written into the phi columns (5k..5k+4)
-__global__ void __launch_bounds__(256) perm_terms_kernel(const DevChip* __restrict__ chip_g, const uint32_t* __restrict__ main, uint64_t mcs,
+__global__ void __launch_bounds__(256) perm_terms_kernel(const __grid_constant__ DevChip chip_, const uint32_t* __restrict__ main, uint64_t mcs,
                                                         const uint32_t* __restrict__ prep, uint64_t pcs, uint64_t h, uint32_t* __restrict__ perm, uint64_t qcs) {
-    __shared__ DevChip s_chip;
-    devchip_to_shared(&s_chip, chip_g);
-    __syncthreads();
-    const DevChip* chip = &s_chip;
+    const DevChip* chip = &chip_;
     uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= h) return;
     uint32_t k = chip->n_interactions;
@@ -222,13 +216,14 @@ extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, co
     }
     VG_TRY(vg_dmat_materialize(ctx, main));
     VG_TRY(vg_dmat_materialize(ctx, prep_or_null));
-    DevChip* dchip = nullptr;
-    VG_TRY(vg_upload_devchip(ctx, chip, challenges, &dchip));
+    auto dchip_h = std::make_unique<DevChip>();
+    VG_TRY(vg_build_devchip(ctx, chip, challenges, dchip_h.get()));
+    const DevChip& dchip = *dchip_h;
     uint64_t h = main->h;
     uint32_t k = chip->n_interactions;
     vgpu_dmat* perm = nullptr;
     int32_t rc = vg_dmat_alloc(ctx, h, 5 * (k + 1), &perm);
-    if (rc) { vg_free(ctx, dchip); return rc; }
+    if (rc) return rc;
     const uint32_t* pd = prep_or_null ? prep_or_null->d : nullptr;
     uint64_t pcs = prep_or_null ? prep_or_null->col_stride : 0;
     unsigned blocks = (unsigned)((h + 255) / 256);
@@ -248,7 +243,6 @@ extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, co
         VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (int l = 0; l < 5; l++) cumulative_sum_out[l] = bb::from_monty(cs[l]);
     }
-    vg_free(ctx, dchip);
     *out_perm = perm;
     return 0;
 }

@@ -35,7 +35,6 @@ using air::F;
 constexpr uint32_t Q_MAX_CONSTRAINTS = 128;   // bitwise: 88 base + interactions + 3
 
 struct QParams {
-    const DevChip* chip;                    // device copy; staged in shared memory by every CTA
     const uint32_t* main; uint64_t mcs;
     const uint32_t* prep; uint64_t pcs;
     const uint32_t* perm; uint64_t qcs;
@@ -51,6 +50,9 @@ struct QParams {
     E5 cumsum;
     const uint32_t* root_lo; const uint32_t* root_hi;
     uint32_t apow[Q_MAX_CONSTRAINTS][5];    // apow[i] = alpha^(N-1-i)
+    DevChip chip;                           // interaction descriptors + LogUp randomness: read through the constant bank (uniform loads),
+                                            // not through dependent global loads (ncu r1b: 27-54 % of the stall samples sat on those);
+                                            // staging them in shared memory instead measured 6 % slower (9.08 vs 8.57 ms per proof)
 };
 
 struct DevBuilder {
@@ -85,12 +87,9 @@ __device__ __forceinline__ E5 load_e5(const uint32_t* row, uint64_t cs, uint32_t
 }
 
 // MINB: resident-CTA target (register cap) of the variant.  The sweep is latency bound (ncu r1b: issue slots 43-57 % busy at
-// 5 CTAs per SM), so more resident warps beat fewer spills: measured 11.4 / 8.9 / 8.6 ms per proof at 4 / 6 / 8 CTAs per SM.
+// 5 CTAs per SM), so more resident warps beat fewer spills: measured 11.4 / 8.9 / 8.6 ms per proof at 2-4 / 6 / 8 CTAs per SM.
 template <int CHIP, int MINB>
 __global__ void __launch_bounds__(128, MINB) quotient_kernel(const __grid_constant__ QParams p) {
-    __shared__ DevChip s_chip;
-    devchip_to_shared(&s_chip, p.chip);
-    __syncthreads();
     const uint64_t h = 1ull << p.log_h, H = 2 * h;
     const uint64_t rho_raw = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
     const bool active = rho_raw < p.row_end;
@@ -116,7 +115,7 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const __grid_consta
         inv_first = e ? bb::mul(i23, d3) : bb::mul(i01, d1);
         inv_last = e ? bb::mul(i23, d2) : bb::mul(i01, d0);
     }
-    const DevChip& chip = s_chip;
+    const DevChip& chip = p.chip;
     const uint32_t k = chip.n_interactions;
     const uint32_t parity = (uint32_t)(((uint64_t)j + (e ? h : 0)) & 1);
     const uint32_t zh = p.zh[parity];
@@ -215,7 +214,6 @@ template <int CHIP> void launch(const QParams& p, uint64_t h, cudaStream_t st) {
     static const int minb = [] { const char* e = getenv("VGPU_QUOTIENT_MINB"); return e ? atoi(e) : 8; }();   // tuning knob (profiles/)
     const unsigned grid = (unsigned)((p.row_end - p.row_begin + 127) / 128);
     if (minb == 6) quotient_kernel<CHIP, 6><<<grid, 128, 0, st>>>(p);
-    else if (minb == 4) quotient_kernel<CHIP, 4><<<grid, 128, 0, st>>>(p);
     else quotient_kernel<CHIP, 8><<<grid, 128, 0, st>>>(p);
 }
 
@@ -243,9 +241,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     auto pp = std::make_unique<QParams>();
     QParams& p = *pp;
     std::memset(&p, 0, sizeof p);
-    DevChip* dchip = nullptr;
-    VG_TRY(vg_upload_devchip(ctx, chip, perm_challenges, &dchip));
-    p.chip = dchip;
+    VG_TRY(vg_build_devchip(ctx, chip, perm_challenges, &p.chip));
     E5 al; for (int i = 0; i < 5; i++) al.c[i] = bb::to_monty(alpha[i] % bb::P);
     { E5 a = bb::e5_one(); for (uint32_t i = 0; i < N; i++) { for (int l = 0; l < 5; l++) p.apow[N - 1 - i][l] = a.c[l]; a = bb::e5_mul(a, al); } }
     vgpu_dmat* out = nullptr;
@@ -296,7 +292,7 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
         for (int c = 0; c < 10; c++) VG_TRY(vg_comm_allgather_inplace(ctx, out->d + (uint64_t)c * out->col_stride, h / ctx->comm_size));
         VG_TRY(vg_comm_group_end(ctx));
     }
-    vg_free(ctx, selinv); vg_free(ctx, dchip);
+    vg_free(ctx, selinv);
     *out_chunks = out;
     return 0;
 }
