@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--ref-log-rows", type=int, default=18, help="bounded sample size of the CPU reference arm")
     ap.add_argument("--cpu-baseline-log-rows", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-timeout", type=int, default=240, help="N > 1: seconds the optional split-proof section may take")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,14 +280,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed region (the same load
+    # throughout; one nvidia-smi query takes ~0.3 s, the timed region alone would see one or two samples)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         vb.prove_machine(cfg, traces, device_resident=(dm, dp))
 
     # ---- timed: device-resident, no instrumentation ----
-    sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count
     barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -327,12 +330,118 @@ def main():
     e2e_value, _ = aggregate_throughput(dist, rows * args.steps, ms_e2e, device="cuda")
     assert proof_e2e == proof
 
+    def make_line(sharded):
+
+        peak, peak_src = peaks()
+        kstats_sorted = sorted(kstats, key=lambda k: -k[2])
+        kernels = [{"kernel": k[0], "launches_per_step": k[1] / args.steps, "ms_per_step": k[2] / args.steps,
+                    "algorithmic_gb_per_step": k[3] / args.steps / 1e9, "achieved_gbs": (k[3] / 1e9) / (k[2] / 1e3) if k[2] > 0 else None} for k in kstats_sorted]
+        top = kstats_sorted[0]
+        achieved = (top[3] / 1e9) / (top[2] / 1e3)
+        roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "share_of_step": top[2] / ms_instr, "ms_per_step_instrumented": ms_instr / args.steps}
+        # The Keccak kernels are bound by the INT ALU pipe, not by HBM (profiles/r01_summary.md section 4: 122 LOP3 + 58 SHF per
+        # round at 63 lanes/clk/SM = 4.32 G Keccak-f/s on this part, 4.30 measured stand-alone): report that ceiling beside the HBM one.
+        KECCAK_PEAK_GPERM = 4.32
+        keccak = {}
+        for name, bytes_per_perm in (("compress_layer_kernel", 96.0), ("fri_leaf_hash_kernel", 72.0)):
+            kk = [k for k in kstats if k[0] == name]
+            if kk and kk[0][2] > 0:
+                g = kk[0][3] / bytes_per_perm / (kk[0][2] / 1e3) / 1e9     # >= 1 permutation per `bytes_per_perm` algorithmic bytes
+                keccak[name] = {"achieved_gperm_s": g, "frac_of_alu_ceiling": g / KECCAK_PEAK_GPERM}
+        roofline["int_alu_ceiling"] = {"unit": "G Keccak-f/s", "peak": KECCAK_PEAK_GPERM, "kernels": keccak,
+                                       "note": "lower bounds: injected layers and multi-block leaves run more permutations than counted",
+                                       "ncu": "profiles/r01_keccak_big_raw.csv: sm__inst_executed_pipe_alu 99.8 % (compress_layer_kernel, 2^24 nodes in 3.96 ms = 4.24 G/s), 92.8 % (leaf_hash_kernel)"}
+        ratio, ratio_src = ncu_traffic_ratio(top[0])
+        if ratio is not None:
+            # GB per launch, like `achieved`: the measured DRAM/algorithmic ratio of the committed capture applied to this
+            # run's average launch (ncu cannot run inside the timed region)
+            roofline["traffic"] = ratio * (top[3] / top[1]) / 1e9
+            roofline["algorithmic_gb_per_launch"] = (top[3] / top[1]) / 1e9
+            roofline["traffic_source"] = "%s: DRAM read+write = %.3f x algorithmic bytes" % (ratio_src, ratio)
+        ntt = [k for k in kstats if k[0] == "ntt_pass_kernel"]
+        if ntt:
+            a = (ntt[0][3] / 1e9) / (ntt[0][2] / 1e3)
+            roofline["ntt_pass"] = {"achieved": a, "frac": a / peak, "unit": "GB/s", "bytes": "8 B per element per pass (read+write)"}
+
+        # ---- second headline figure: BASELINE config 2 — 2^20 x 64 BabyBear NTT + inverse, device resident ----
+        ntt_line = None
+        if world == 1:
+            hh, ww = 1 << 20, 64
+            rr = np.arange(hh, dtype=np.uint64)[:, None]
+            cc = np.arange(ww, dtype=np.uint64)[None, :]
+            x = ((rr * 64 + cc) * 0x9E3779B1 % vb.BABYBEAR_P).astype(np.uint32)     # SURVEY 8(d) config 2 input
+            dft = vb.Radix2Dft(ctx)
+            dx = ctx.upload(x)
+            for _ in range(3):
+                dft.dft_batch(dx); dft.idft_batch(dx)
+            torch.cuda.synchronize()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            n0.record(stream)
+            for _ in range(reps):
+                dft.dft_batch(dx); dft.idft_batch(dx)
+            n1.record(stream)
+            torch.cuda.synchronize()
+            ms_pair = n0.elapsed_time(n1) / reps
+            roundtrip_ok = bool(np.array_equal(dx.download(), x))
+            gbs = 2 * 8.0 * hh * ww / (ms_pair / 1e3) / 1e9      # two transforms, 8 B per element each (read once + write once)
+            ntt_line = {"workload": "2^20 x 64 NTT + iNTT (natural order in/out), 256 MiB working set > L2", "ms_forward_plus_inverse": ms_pair,
+                        "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "bytes": "8*h*w per transform", "roundtrip_bit_exact": roundtrip_ok}
+            dx.free()
+
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            import oracle_binding
+
+            vbuild.build_oracle()
+            orc = oracle_binding.Oracle()
+            threads = tune_oracle_threads(orc, vb)
+            nb = fib_n_for_log_rows(args.cpu_baseline_log_rows)
+            tb = vb.run_program(vb.fib_program(nb), initial_fp=0x1000)
+            t0 = time.perf_counter()
+            ref = orc.prove(tb.main, tb.preprocessed, debug_checks=False)
+            dt = time.perf_counter() - t0
+            del ref
+            cpu_baseline = {"value": tb.main[0].shape[0] / dt, "unit": "rows/s", "cores": threads, "kind": "port",
+                            "sample": "Fibonacci n=%d (2^%d CPU rows), one full oracle prove, %.1f s, %d OpenMP threads (best of a sweep) on %d host cores"
+                                      % (nb, args.cpu_baseline_log_rows, dt, threads, os.cpu_count())}
+
+        line = {
+            "metric": "trace rows/sec proven (Fibonacci)", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (BabyBear, 31-bit modular) + ext5", "data": "synthetic",
+            "config": {"workload": workload_name(args.log_rows), "fib_n": n, "trace_bytes": trace_bytes, "proof_bytes": len(proof),
+                       "l2": "inputs (%.2f GB of traces, %.1f GB of LDEs) exceed L2" % (trace_bytes / 1e9, 4.5 * trace_bytes / 1e9),
+                       "parallelism": "independent proofs per GPU (no data-path collective)" if world > 1 else "single GPU",
+                       "host_tracegen_s": tracegen_s},
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": len(proof)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "ntt": ntt_line,
+            "cpu_baseline": cpu_baseline,
+            "phases_ms": {p[0]: p[1] for p in phases},
+            "kernels": kernels,
+            "sharded": sharded,
+        }
+        return line
+
     # ---- N > 1: the SAME single proof split across the ranks (column shares for the LDE, leaf/layer shares for the
-    # Keccak trees, NCCL exchange over NVLink) — latency of one proof on N GPUs, beside the replica throughput ----
+    # Keccak trees, NCCL exchange over NVLink) — latency of one proof on N GPUs, beside the replica throughput.
+    # The figure is extra to the contract line: a failure is reported inside `sharded`, and a watchdog gives the line out
+    # without it if the section does not finish (a hung collective must not lose the replica measurement above). ----
     sharded = None
     if dist is not None:
-        # the split-proof figure is extra to the contract line: a failure here is reported inside `sharded`, it does not
-        # take the replica throughput (already measured above) down with it
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(args.sharded_timeout):
+                if rank == 0:
+                    emit(make_line({"error": "split-proof section did not finish within %d s" % args.sharded_timeout}))
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
         try:
             ctx.comm_init_from_torch()
             for _ in range(2):
@@ -354,106 +463,14 @@ def main():
                        "proof_bytes_identical": bool(identical), "phases_ms": {k: v for k, v in sh_phases}}
         except Exception as exc:   # noqa: BLE001
             sharded = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        finally:
+            done.set()
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    peak, peak_src = peaks()
-    kstats_sorted = sorted(kstats, key=lambda k: -k[2])
-    kernels = [{"kernel": k[0], "launches_per_step": k[1] / args.steps, "ms_per_step": k[2] / args.steps,
-                "algorithmic_gb_per_step": k[3] / args.steps / 1e9, "achieved_gbs": (k[3] / 1e9) / (k[2] / 1e3) if k[2] > 0 else None} for k in kstats_sorted]
-    top = kstats_sorted[0]
-    achieved = (top[3] / 1e9) / (top[2] / 1e3)
-    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "share_of_step": top[2] / ms_instr, "ms_per_step_instrumented": ms_instr / args.steps}
-    # The Keccak kernels are bound by the INT ALU pipe, not by HBM (profiles/r01_summary.md section 4: 122 LOP3 + 58 SHF per
-    # round at 63 lanes/clk/SM = 4.32 G Keccak-f/s on this part, 4.30 measured stand-alone): report that ceiling beside the HBM one.
-    KECCAK_PEAK_GPERM = 4.32
-    keccak = {}
-    for name, bytes_per_perm in (("compress_layer_kernel", 96.0), ("fri_leaf_hash_kernel", 72.0)):
-        kk = [k for k in kstats if k[0] == name]
-        if kk and kk[0][2] > 0:
-            g = kk[0][3] / bytes_per_perm / (kk[0][2] / 1e3) / 1e9     # >= 1 permutation per `bytes_per_perm` algorithmic bytes
-            keccak[name] = {"achieved_gperm_s": g, "frac_of_alu_ceiling": g / KECCAK_PEAK_GPERM}
-    roofline["int_alu_ceiling"] = {"unit": "G Keccak-f/s", "peak": KECCAK_PEAK_GPERM, "kernels": keccak,
-                                   "note": "lower bounds: injected layers and multi-block leaves run more permutations than counted",
-                                   "ncu": "profiles/r01_keccak_big_raw.csv: sm__inst_executed_pipe_alu 99.8 % (compress_layer_kernel, 2^24 nodes in 3.96 ms = 4.24 G/s), 92.8 % (leaf_hash_kernel)"}
-    ratio, ratio_src = ncu_traffic_ratio(top[0])
-    if ratio is not None:
-        # GB per launch, like `achieved`: the measured DRAM/algorithmic ratio of the committed capture applied to this
-        # run's average launch (ncu cannot run inside the timed region)
-        roofline["traffic"] = ratio * (top[3] / top[1]) / 1e9
-        roofline["algorithmic_gb_per_launch"] = (top[3] / top[1]) / 1e9
-        roofline["traffic_source"] = "%s: DRAM read+write = %.3f x algorithmic bytes" % (ratio_src, ratio)
-    ntt = [k for k in kstats if k[0] == "ntt_pass_kernel"]
-    if ntt:
-        a = (ntt[0][3] / 1e9) / (ntt[0][2] / 1e3)
-        roofline["ntt_pass"] = {"achieved": a, "frac": a / peak, "unit": "GB/s", "bytes": "8 B per element per pass (read+write)"}
-
-    # ---- second headline figure: BASELINE config 2 — 2^20 x 64 BabyBear NTT + inverse, device resident ----
-    ntt_line = None
-    if world == 1:
-        hh, ww = 1 << 20, 64
-        rr = np.arange(hh, dtype=np.uint64)[:, None]
-        cc = np.arange(ww, dtype=np.uint64)[None, :]
-        x = ((rr * 64 + cc) * 0x9E3779B1 % vb.BABYBEAR_P).astype(np.uint32)     # SURVEY 8(d) config 2 input
-        dft = vb.Radix2Dft(ctx)
-        dx = ctx.upload(x)
-        for _ in range(3):
-            dft.dft_batch(dx); dft.idft_batch(dx)
-        torch.cuda.synchronize()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        n0.record(stream)
-        for _ in range(reps):
-            dft.dft_batch(dx); dft.idft_batch(dx)
-        n1.record(stream)
-        torch.cuda.synchronize()
-        ms_pair = n0.elapsed_time(n1) / reps
-        roundtrip_ok = bool(np.array_equal(dx.download(), x))
-        gbs = 2 * 8.0 * hh * ww / (ms_pair / 1e3) / 1e9      # two transforms, 8 B per element each (read once + write once)
-        ntt_line = {"workload": "2^20 x 64 NTT + iNTT (natural order in/out), 256 MiB working set > L2", "ms_forward_plus_inverse": ms_pair,
-                    "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "bytes": "8*h*w per transform", "roundtrip_bit_exact": roundtrip_ok}
-        dx.free()
-
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1:
-        import oracle_binding
-
-        vbuild.build_oracle()
-        orc = oracle_binding.Oracle()
-        threads = tune_oracle_threads(orc, vb)
-        nb = fib_n_for_log_rows(args.cpu_baseline_log_rows)
-        tb = vb.run_program(vb.fib_program(nb), initial_fp=0x1000)
-        t0 = time.perf_counter()
-        ref = orc.prove(tb.main, tb.preprocessed, debug_checks=False)
-        dt = time.perf_counter() - t0
-        del ref
-        cpu_baseline = {"value": tb.main[0].shape[0] / dt, "unit": "rows/s", "cores": threads, "kind": "port",
-                        "sample": "Fibonacci n=%d (2^%d CPU rows), one full oracle prove, %.1f s, %d OpenMP threads (best of a sweep) on %d host cores"
-                                  % (nb, args.cpu_baseline_log_rows, dt, threads, os.cpu_count())}
-
-    line = {
-        "metric": "trace rows/sec proven (Fibonacci)", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 (BabyBear, 31-bit modular) + ext5", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_rows), "fib_n": n, "trace_bytes": trace_bytes, "proof_bytes": len(proof),
-                   "l2": "inputs (%.2f GB of traces, %.1f GB of LDEs) exceed L2" % (trace_bytes / 1e9, 4.5 * trace_bytes / 1e9),
-                   "parallelism": "independent proofs per GPU (no data-path collective)" if world > 1 else "single GPU",
-                   "host_tracegen_s": tracegen_s},
-        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": len(proof)},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": roofline,
-        "ntt": ntt_line,
-        "cpu_baseline": cpu_baseline,
-        "phases_ms": {p[0]: p[1] for p in phases},
-        "kernels": kernels,
-        "sharded": sharded,
-    }
-    emit(line)
+    emit(make_line(sharded))
     if dist is not None:
         dist.destroy_process_group()
 
