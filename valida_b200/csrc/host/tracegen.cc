@@ -20,6 +20,10 @@
 #include <unordered_map>
 #include <algorithm>
 #include <string>
+#include <memory>
+#include <chrono>
+#include <cstdio>
+#include <omp.h>
 #include "../../../include/valida_b200.h"
 
 namespace {
@@ -40,10 +44,68 @@ struct AluRec { uint32_t a, b, c; };
 struct LtRec { uint32_t a, b, c; uint32_t opcode; };
 using BitRec = LtRec;
 
+// Memory cells of the VM: open addressing, linear probing, power-of-two table (the interpreter touches it two or three
+// times per cycle; std::unordered_map made that the slowest part of the run loop).
+struct CellMap {
+    std::vector<uint32_t> keys, vals;
+    std::vector<uint8_t> used;
+    size_t count = 0, mask = 0;
+    CellMap() { rehash(1 << 12); }
+    static size_t slot_of(uint32_t k, size_t mask) { return (size_t)((k * 0x9E3779B1u) >> 7) & mask; }
+    void rehash(size_t cap) {
+        std::vector<uint32_t> ok(std::move(keys)), ov(std::move(vals));
+        std::vector<uint8_t> ou(std::move(used));
+        keys.assign(cap, 0); vals.assign(cap, 0); used.assign(cap, 0); mask = cap - 1; count = 0;
+        for (size_t i = 0; i < ou.size(); i++) if (ou[i]) set(ok[i], ov[i]);
+    }
+    bool get(uint32_t k, uint32_t* v) const {
+        for (size_t i = slot_of(k, mask);; i = (i + 1) & mask) {
+            if (!used[i]) return false;
+            if (keys[i] == k) { *v = vals[i]; return true; }
+        }
+    }
+    void set(uint32_t k, uint32_t v) {
+        if (2 * (count + 1) > mask + 1) rehash(2 * (mask + 1));
+        for (size_t i = slot_of(k, mask);; i = (i + 1) & mask) {
+            if (!used[i]) { used[i] = 1; keys[i] = k; vals[i] = v; count++; return; }
+            if (keys[i] == k) { vals[i] = v; return; }
+        }
+    }
+};
+
+// Trace storage: zero-filled by all host threads (a 2^24 x 14 matrix is 0.9 GB; a single-threaded std::vector::assign
+// spends longer faulting its pages in than the row loop spends filling them).
+struct Buf {
+    uint32_t* p = nullptr; size_t n = 0;
+    Buf() = default;
+    Buf(const Buf&) = delete; Buf& operator=(const Buf&) = delete;
+    ~Buf() { std::free(p); }
+    uint32_t* alloc(size_t count) {                      // uninitialised
+        std::free(p);
+        n = count;
+        p = (uint32_t*)std::malloc((count ? count : 1) * sizeof(uint32_t));
+        if (!p) { n = 0; std::abort(); }
+        return p;
+    }
+    void clear_range(size_t begin, size_t end) {         // words [begin, end), all host threads
+        if (end <= begin) return;
+        const size_t count = end - begin;
+        const long chunks = (long)((count + (1 << 18) - 1) >> 18);
+#pragma omp parallel for schedule(static)
+        for (long c = 0; c < chunks; c++) {
+            const size_t b = begin + ((size_t)c << 18), e = std::min(end, b + ((size_t)1 << 18));
+            std::memset(p + b, 0, (e - b) * sizeof(uint32_t));
+        }
+    }
+    uint32_t* zeros(size_t count) { alloc(count); clear_range(0, count); return p; }
+    uint32_t* data() { return p; }
+    uint32_t& operator[](size_t i) { return p[i]; }
+};
+
 struct Vm {
     const int32_t* prog; size_t n_instr;
     uint32_t pc = 0, fp = 0, clock = 0;
-    std::unordered_map<uint32_t, uint32_t> cells;
+    CellMap cells;
     std::vector<MemOp> mem_ops;
     std::vector<CpuRec> cpu;
     std::vector<AluRec> adds, subs;
@@ -54,13 +116,11 @@ struct Vm {
     std::string err;
 
     bool read(uint32_t addr, uint32_t& v) {
-        auto it = cells.find(addr);
-        if (it == cells.end()) { err = "memory chip: read before write at " + std::to_string(addr) + " (pc=" + std::to_string(pc) + ")"; return false; }
-        v = it->second;
+        if (!cells.get(addr, &v)) { err = "memory chip: read before write at " + std::to_string(addr) + " (pc=" + std::to_string(pc) + ")"; return false; }
         mem_ops.push_back({clock, addr, v, 0});
         return true;
     }
-    void write(uint32_t addr, uint32_t v) { mem_ops.push_back({clock, addr, v, 1}); cells[addr] = v; }
+    void write(uint32_t addr, uint32_t v) { mem_ops.push_back({clock, addr, v, 1}); cells.set(addr, v); }
     void range_check(uint32_t w) { for (int i = 0; i < 4; i++) range_count[(w >> (8 * i)) & 0xff]++; }
     void push(CpuOp kind, uint32_t instr_pc, uint32_t pc_before, uint32_t fp_before, bool has_imm = false, uint32_t imm = 0) {
         cpu.push_back({pc_before, fp_before, instr_pc, kind, has_imm, imm});
@@ -148,9 +208,9 @@ struct Vm {
 struct Traces {
     vgpu_matrix main[14];
     vgpu_matrix prep[2];
-    std::vector<uint32_t> store[16];
+    Buf store[16];
     uint32_t clock = 0, n_mem_ops = 0, n_add_ops = 0, n_sub_ops = 0;
-    std::unordered_map<uint32_t, uint32_t> cells;
+    CellMap cells;
 };
 
 inline void word_be(uint32_t v, uint32_t* out) { out[0] = v >> 24; out[1] = (v >> 16) & 0xff; out[2] = (v >> 8) & 0xff; out[3] = v & 0xff; }
@@ -158,8 +218,8 @@ inline void word_be(uint32_t v, uint32_t* out) { out[0] = v >> 24; out[1] = (v >
 void build_cpu(const Vm& vm, Traces& t) {
     constexpr size_t W = 51;
     size_t n = vm.cpu.size(), h = next_pow2(n);
-    std::vector<uint32_t>& v = t.store[0];
-    v.assign(h * W, 0);
+    Buf& v = t.store[0];
+    v.zeros(h * W);
     // per-clk memory ops are contiguous in vm.mem_ops (clk non-decreasing)
     std::vector<size_t> first(n + 1, 0);
     { size_t k = 0; for (size_t clk = 0; clk <= n; clk++) { while (k < vm.mem_ops.size() && vm.mem_ops[k].clk < clk) k++; first[clk] = k; } }
@@ -209,12 +269,18 @@ void build_cpu(const Vm& vm, Traces& t) {
         for (int k = 0; k < 4; k++) { int64_t dd = (int64_t)row[32 + k] - (int64_t)row[39 + k]; dsum += (uint64_t)(dd * dd); }
         diff[i] = (uint32_t)(dsum % P);
     }
-    // diff_inv via a small cache (diff <= 4*255^2)
+    // diff_inv through a table over the possible values (diff <= 4*255^2): mark, invert the marked entries, fill
     {
-        std::unordered_map<uint32_t, uint32_t> invs;
-        for (size_t i = 0; i < n; i++) if (diff[i] && !invs.count(diff[i])) invs[diff[i]] = fpow(diff[i], P - 2);
-        for (size_t i = 0; i < n; i++) {
-            uint32_t* row = &v[i * W];
+        constexpr uint32_t DMAX = 4 * 255 * 255;
+        std::vector<uint32_t> invs(DMAX + 1, 0);
+        std::vector<uint8_t> seen(DMAX + 1, 0);
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < (long)n; i++) if (diff[i]) seen[diff[i]] = 1;     // benign race: every writer stores 1
+#pragma omp parallel for schedule(dynamic, 1024)
+        for (long d = 1; d <= (long)DMAX; d++) if (seen[d]) invs[d] = fpow((uint32_t)d, P - 2);
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < (long)n; i++) {
+            uint32_t* row = &v[(size_t)i * W];
             row[26] = diff[i];
             if (diff[i]) { row[27] = invs[diff[i]]; row[28] = 1; }
         }
@@ -223,8 +289,9 @@ void build_cpu(const Vm& vm, Traces& t) {
     if (n) {
         const uint32_t* last = &v[(n - 1) * W];
         uint32_t pc = last[1], fp = last[2], clk = last[0];
-        for (size_t i = n; i < h; i++) {
-            uint32_t* row = &v[i * W];
+#pragma omp parallel for schedule(static)
+        for (long i = (long)n; i < (long)h; i++) {
+            uint32_t* row = &v[(size_t)i * W];
             row[1] = pc; row[2] = fp; row[0] = clk + (uint32_t)(i - n) + 1;
             row[24] = 1; row[3] = OP_STOP;
             row[29 + 1] = 1; row[36 + 1] = 1;
@@ -233,30 +300,77 @@ void build_cpu(const Vm& vm, Traces& t) {
     t.main[0] = {v.data(), h, W};
 }
 
+// Stable sort of the memory log by address (memory/src/lib.rs:158 sorts by (addr, clk); the log is already in clk order, so a
+// STABLE sort on the address alone gives the same order).  LSD radix, 11 bits per pass, passes whose digit is the same for
+// every key are skipped; per-thread histograms over contiguous chunks keep each pass stable.
+// Returns the sorted log (a fresh array, or `in` itself when no pass was needed); `hold` owns whatever was allocated.
+const MemOp* sort_by_addr(const std::vector<MemOp>& in, std::unique_ptr<MemOp[]> hold[2]) {
+    const size_t n = in.size();
+    if (n < 2) return in.data();
+    uint32_t all_or = 0, all_and = 0xffffffffu;
+#pragma omp parallel for schedule(static) reduction(|: all_or) reduction(&: all_and)
+    for (long i = 0; i < (long)n; i++) { all_or |= in[i].addr; all_and &= in[i].addr; }
+    const uint32_t varying = all_or ^ all_and;
+    constexpr int BITS = 11, BUCKETS = 1 << BITS;
+    const int T = std::max(1, omp_get_max_threads());
+    std::vector<size_t> hist((size_t)T * BUCKETS);
+    const MemOp* src = in.data();
+    int next = 0;
+    for (int shift = 0; shift < 32; shift += BITS) {
+        if (((varying >> shift) & (BUCKETS - 1)) == 0) continue;
+        if (!hold[next]) hold[next].reset(new MemOp[n]);       // default-initialised: no serial zero fill of 16 n bytes
+        MemOp* dst = hold[next].get();
+        std::fill(hist.begin(), hist.end(), 0);
+#pragma omp parallel num_threads(T)
+        {
+            const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+            const size_t b = n * (size_t)tid / nt, e = n * (size_t)(tid + 1) / nt;
+            size_t* h = &hist[(size_t)tid * BUCKETS];
+            for (size_t i = b; i < e; i++) h[(src[i].addr >> shift) & (BUCKETS - 1)]++;
+#pragma omp barrier
+#pragma omp single
+            {
+                size_t run = 0;
+                for (int d = 0; d < BUCKETS; d++)
+                    for (int k = 0; k < nt; k++) { size_t c = hist[(size_t)k * BUCKETS + d]; hist[(size_t)k * BUCKETS + d] = run; run += c; }
+            }
+            for (size_t i = b; i < e; i++) dst[h[(src[i].addr >> shift) & (BUCKETS - 1)]++] = src[i];
+        }
+        src = dst;
+        next ^= 1;
+    }
+    return src;
+}
+
 void build_mem(const Vm& vm, Traces& t) {
     constexpr size_t W = 14;
-    std::vector<MemOp> ops = vm.mem_ops;
-    std::stable_sort(ops.begin(), ops.end(), [](const MemOp& x, const MemOp& y) { return x.addr != y.addr ? x.addr < y.addr : x.clk < y.clk; });
-    size_t n = ops.size(), h = next_pow2(n);
-    std::vector<uint32_t>& v = t.store[2];
-    v.assign(h * W, 0);
+    std::unique_ptr<MemOp[]> hold[2];
+    const MemOp* ops = sort_by_addr(vm.mem_ops, hold);
+    size_t n = vm.mem_ops.size(), h = next_pow2(n);
+    Buf& v = t.store[2];
+    v.alloc(h * W);
+    // every word of the n operation rows is written here and the padding rows are cleared below: no zero fill of the
+    // whole 0.9 GB matrix first
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)n; i++) {
         uint32_t* row = &v[(size_t)i * W];
         row[0] = ops[i].addr; word_be(ops[i].value, &row[1]);
         row[5] = ops[i].clk; row[6] = 0;
-        if (ops[i].is_write) row[8] = 1; else row[7] = 1;
-        row[12] = (uint32_t)i;
+        row[7] = ops[i].is_write ? 0 : 1; row[8] = ops[i].is_write ? 1 : 0;
+        row[9] = 0; row[10] = 0; row[11] = 0;
+        row[12] = (uint32_t)i; row[13] = 0;
     }
+    v.clear_range(n * W, h * W);
     t.main[2] = {v.data(), h, W};
 }
 
-void build_addsub(const std::vector<AluRec>& ops, bool is_add, std::vector<uint32_t>& v, vgpu_matrix& out) {
+void build_addsub(const std::vector<AluRec>& ops, bool is_add, Buf& v, vgpu_matrix& out) {
     constexpr size_t W = 16;
     size_t n = ops.size(), h = next_pow2(n);
-    v.assign(h * W, 0);
-    for (size_t i = 0; i < n; i++) {
-        uint32_t* row = &v[i * W];
+    v.zeros(h * W);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        uint32_t* row = &v[(size_t)i * W];
         uint32_t a[4], b[4], c[4];
         word_be(ops[i].a, a); word_be(ops[i].b, b); word_be(ops[i].c, c);
         std::memcpy(row + 0, b, 16); std::memcpy(row + 4, c, 16); std::memcpy(row + 11, a, 16);
@@ -274,12 +388,13 @@ void build_addsub(const std::vector<AluRec>& ops, bool is_add, std::vector<uint3
 }
 
 // Lt32Chip::op_to_row / set_cols (alu_u32/src/lt/mod.rs:86-160)
-void build_lt(const std::vector<LtRec>& ops, std::vector<uint32_t>& v, vgpu_matrix& out) {
+void build_lt(const std::vector<LtRec>& ops, Buf& v, vgpu_matrix& out) {
     constexpr size_t W = 45;
     size_t n = ops.size(), h = next_pow2(n);
-    v.assign(h * W, 0);
-    for (size_t i = 0; i < n; i++) {
-        uint32_t* row = &v[i * W];
+    v.zeros(h * W);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        uint32_t* row = &v[(size_t)i * W];
         uint32_t a[4], b[4], c[4];
         word_be(ops[i].a, a); word_be(ops[i].b, b); word_be(ops[i].c, c);
         std::memcpy(row + 0, b, 16); std::memcpy(row + 4, c, 16);
@@ -305,12 +420,13 @@ void build_lt(const std::vector<LtRec>& ops, std::vector<uint32_t>& v, vgpu_matr
 
 // Bitwise32Chip::op_to_row / set_cols (alu_u32/src/bitwise/mod.rs:84-131): input_1 0..3, input_2 4..7,
 // bits_1[byte][bit] 8 + 8*byte + bit, bits_2 40 + ..., output 72..75, is_and 76, is_or 77, is_xor 78
-void build_bitwise(const std::vector<BitRec>& ops, std::vector<uint32_t>& v, vgpu_matrix& out) {
+void build_bitwise(const std::vector<BitRec>& ops, Buf& v, vgpu_matrix& out) {
     constexpr size_t W = 79;
     size_t n = ops.size(), h = next_pow2(n);
-    v.assign(h * W, 0);
-    for (size_t i = 0; i < n; i++) {
-        uint32_t* row = &v[i * W];
+    v.zeros(h * W);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        uint32_t* row = &v[(size_t)i * W];
         uint32_t a[4], b[4], c[4];
         word_be(ops[i].a, a); word_be(ops[i].b, b); word_be(ops[i].c, c);
         std::memcpy(row + 0, b, 16); std::memcpy(row + 4, c, 16); std::memcpy(row + 72, a, 16);
@@ -321,7 +437,7 @@ void build_bitwise(const std::vector<BitRec>& ops, std::vector<uint32_t>& v, vgp
     out = {v.data(), h, W};
 }
 
-void zero_chip(std::vector<uint32_t>& v, vgpu_matrix& out, size_t w) { v.assign(w, 0); out = {v.data(), 1, w}; }
+void zero_chip(Buf& v, vgpu_matrix& out, size_t w) { v.zeros(w); out = {v.data(), 1, w}; }
 
 }  // namespace
 
@@ -331,9 +447,12 @@ extern "C" {
 
 int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
                    vgpu_traces** out, char* err, uint64_t err_len) {
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("VGPU_TRACEGEN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "tracegen %-12s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     Vm vm;
     vm.prog = program_words; vm.n_instr = n_instr; vm.pc = initial_pc; vm.fp = initial_fp;
     vm.prog_counts.assign(n_instr, 0);
+    vm.mem_ops.reserve(1 << 20); vm.cpu.reserve(1 << 19);
     int rc = 0;
     while ((rc = vm.step()) == 0) {
         if (vm.clock >= max_cycles) { vm.err = "cycle limit reached"; rc = -1; break; }
@@ -346,14 +465,17 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
     vgpu_traces* tr = new vgpu_traces();
     Traces& t = tr->t;
     t.clock = vm.clock; t.n_mem_ops = (uint32_t)vm.mem_ops.size(); t.n_add_ops = (uint32_t)vm.adds.size(); t.n_sub_ops = (uint32_t)vm.subs.size();
+    lap("vm run");
     build_cpu(vm, t);
+    lap("cpu");
     build_mem(vm, t);
+    lap("mem");
     {  // program: 1 main column (counts) + 7 preprocessed
         size_t h = next_pow2(n_instr);
-        t.store[1].assign(h, 0);
+        t.store[1].zeros(h);
         for (size_t i = 0; i < n_instr; i++) t.store[1][i] = vm.prog_counts[i];
         t.main[1] = {t.store[1].data(), h, 1};
-        t.store[14].assign(h * 7, 0);
+        t.store[14].zeros(h * 7);
         for (size_t i = 0; i < h; i++) {
             uint32_t* row = &t.store[14][i * 7];
             row[0] = (uint32_t)i;
@@ -363,8 +485,9 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
     }
     build_addsub(vm.adds, true, t.store[3], t.main[3]);
     build_addsub(vm.subs, false, t.store[4], t.main[4]);
+    lap("prog+addsub");
     {  // mul: 2^10 counter rows
-        t.store[5].assign(1024 * 18, 0);
+        t.store[5].zeros(1024 * 18);
         for (size_t i = 0; i < 1024; i++) t.store[5][i * 18 + 17] = (uint32_t)i + 1;
         t.main[5] = {t.store[5].data(), 1024, 18};
     }
@@ -375,13 +498,14 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
     build_bitwise(vm.bits, t.store[10], t.main[10]);   // bitwise
     zero_chip(t.store[11], t.main[11], 7);  // output
     {  // range: (mult, counter) + preprocessed counter
-        t.store[12].assign(256 * 2, 0); t.store[15].assign(256, 0);
+        t.store[12].zeros(256 * 2); t.store[15].zeros(256);
         for (uint32_t i = 0; i < 256; i++) { t.store[12][i * 2] = vm.range_count[i]; t.store[12][i * 2 + 1] = i; t.store[15][i] = i; }
         t.main[12] = {t.store[12].data(), 256, 2};
         t.prep[1] = {t.store[15].data(), 256, 1};
     }
     zero_chip(t.store[13], t.main[13], 6);  // static_data (no static data loaded)
     t.cells = std::move(vm.cells);
+    lap("rest");
     *out = tr;
     return 0;
 }
@@ -392,9 +516,7 @@ void vgpu_traces_stats(const vgpu_traces* t, uint32_t* clock, uint32_t* mem_ops,
     *clock = t->t.clock; *mem_ops = t->t.n_mem_ops; *add_ops = t->t.n_add_ops;
 }
 int vgpu_traces_mem_cell(const vgpu_traces* t, uint32_t addr, uint32_t* value) {
-    auto it = t->t.cells.find(addr);
-    if (it == t->t.cells.end()) return -1;
-    *value = it->second; return 0;
+    return t->t.cells.get(addr, value) ? 0 : -1;
 }
 void vgpu_traces_free(vgpu_traces* t) { delete t; }
 
