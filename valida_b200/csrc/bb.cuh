@@ -76,18 +76,6 @@ BB_HD uint32_t monty_reduce64(uint64_t t) {
     return umin32(u, u + P);
 }
 
-// Lazy dot-product accumulation: a 64-bit accumulator absorbs up to 4 raw products of Montgomery words
-// (each < p^2 < 2^62) before one Montgomery reduction — one IMAD.WIDE per term instead of a full modular multiply.
-struct Acc5 { uint64_t c[5]; };
-BB_HD void acc5_zero(Acc5& a) { for (int i = 0; i < 5; i++) a.c[i] = 0; }
-BB_HD void acc5_fma_base(Acc5& a, const E5& w, uint32_t x) { for (int i = 0; i < 5; i++) a.c[i] += (uint64_t)w.c[i] * x; }
-// fold the pending products into a reduced ext5 partial sum: r += reduce(a); a = 0
-BB_HD void acc5_flush(Acc5& a, E5& r) { for (int i = 0; i < 5; i++) { r.c[i] = add(r.c[i], monty_reduce64(a.c[i])); a.c[i] = 0; } }
-// keep the accumulator unreduced but small: x = lo + hi * 2^32 == lo + hi * R1 (mod p), < 2^32 + 2^60,
-// leaving room for three more products (one IMAD.WIDE, no Montgomery rescaling)
-BB_HD void acc5_fold(Acc5& a) { for (int i = 0; i < 5; i++) a.c[i] = (a.c[i] & 0xffffffffull) + (a.c[i] >> 32) * (uint64_t)R1; }
-BB_HD E5 acc5_value(const Acc5& a) { E5 r; for (int i = 0; i < 5; i++) r.c[i] = monty_reduce64(a.c[i]); return r; }
-
 #ifdef __CUDACC__
 // ---- lazy ext5 accumulation on the device ----------------------------------------------------------------------
 // a*b + c as ONE IMAD.WIDE (the C++ form `c + (uint64_t)a * b` is not reliably fused: ptxas was seen emitting a

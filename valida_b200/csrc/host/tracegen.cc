@@ -17,7 +17,6 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
-#include <unordered_map>
 #include <algorithm>
 #include <string>
 #include <memory>
@@ -447,6 +446,7 @@ extern "C" {
 
 int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
                    vgpu_traces** out, char* err, uint64_t err_len) {
+    // VGPU_TRACEGEN_TIMING=1 prints the time of each stage to stderr (development aid)
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (getenv("VGPU_TRACEGEN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "tracegen %-12s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     Vm vm;
