@@ -191,6 +191,12 @@ int32_t vgpu_verify(vgpu_ctx* ctx, const uint8_t* proof, uint64_t proof_len, con
  * program_words: n_instr x 6 int32 (opcode, a, b, c, d, e) as ProgramROM<i32> (machine/src/program.rs:165-185). */
 int32_t vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
                          vgpu_traces** out, char* err, uint64_t err_len);
+/* The same with static data preloaded: StaticDataChip::write + MachineWithStaticDataChip::initialize_memory
+ * (static_data/src/lib.rs:26-57; the reference's prove_static_data, basic/tests/test_static_data.rs:30-113).
+ * static_values[i] is the 32-bit cell at static_addrs[i] (Word bytes big-endian, as Word<u8> -> u32). */
+int32_t vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                                const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
+                                vgpu_traces** out, char* err, uint64_t err_len);
 const vgpu_matrix* vgpu_traces_main(const vgpu_traces* t, uint32_t chip);           /* canonical words */
 const vgpu_matrix* vgpu_traces_preprocessed(const vgpu_traces* t, uint32_t which);  /* 0 = program (7 cols), 1 = range (1 col) */
 void vgpu_traces_stats(const vgpu_traces* t, uint32_t* clock, uint32_t* mem_ops, uint32_t* add_ops);

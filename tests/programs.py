@@ -51,3 +51,16 @@ def config5_program(iters):
         [6, 3 * B, -4, iters, 0, 1],                          # bne loop, i, iters
         [8, 0, 0, 0, 0, 0],
     ], dtype=np.int32)
+
+
+def static_data_program():
+    """prove_static_data of the reference (basic/tests/test_static_data.rs:30-55): loops forever unless the static value is loaded.
+        _start: imm32 0(fp), 0, 0, 0, 0x10 ; load32 -4(fp), 0(fp) ; bnei _start, -4(fp), 0x25 ; stop
+    with static cells 0x10 = Word([0,0,0,0x25]), 0x14 = Word([0,0,0,0x32]) (test_static_data.rs:59-60)."""
+    prog = np.array([
+        [7, 0, 0, 0, 0, 0x10],
+        [1, -4, 0, 0, 0, 0],
+        [6, 0, -4, 0x25, 0, 1],
+        [8, 0, 0, 0, 0, 0],
+    ], dtype=np.int32)
+    return prog, {0x10: 0x25, 0x14: 0x32}

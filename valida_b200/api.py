@@ -74,6 +74,7 @@ def _load():
         "vgpu_free_bytes": (None, [C.POINTER(C.c_uint8)]),
         "vgpu_last_prove_phases": (C.c_uint32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_uint32]),
         "vgpu_machine_run": (C.c_int32, [C.POINTER(C.c_int32), u64, C.c_uint32, C.c_uint32, u64, C.POINTER(vp), C.c_char_p, u64]),
+        "vgpu_machine_run_static": (C.c_int32, [C.POINTER(C.c_int32), u64, C.c_uint32, C.c_uint32, u64, u32p, u32p, u64, C.POINTER(vp), C.c_char_p, u64]),
         "vgpu_traces_main": (C.POINTER(_Matrix), [vp, C.c_uint32]),
         "vgpu_traces_preprocessed": (C.POINTER(_Matrix), [vp, C.c_uint32]),
         "vgpu_traces_stats": (None, [vp, u32p, u32p, u32p]),
@@ -470,12 +471,17 @@ def fib_program(n):
     return np.array(list(words), dtype=np.int32).reshape(int(cnt), 6)
 
 
-def run_program(program, initial_fp=0x1000, initial_pc=0, max_cycles=1 << 30):
-    """Machine::run + generate_trace for every chip (host)."""
+def run_program(program, initial_fp=0x1000, initial_pc=0, max_cycles=1 << 30, static_data=None):
+    """Machine::run + generate_trace for every chip (host).  static_data: {address: 32-bit cell} preloaded through the
+    static-data chip (machine.static_data_mut().write(addr, Word(..)), basic/tests/test_static_data.rs:59-60)."""
     p = np.ascontiguousarray(program, dtype=np.int32)
     h = C.c_void_p()
     err = C.create_string_buffer(512)
-    rc = lib().vgpu_machine_run(p.ctypes.data_as(C.POINTER(C.c_int32)), p.shape[0], initial_pc, initial_fp, max_cycles, C.byref(h), err, 512)
+    sa = np.array(sorted((static_data or {}).keys()), dtype=np.uint32)
+    sv = np.array([(static_data or {})[int(a)] for a in sa], dtype=np.uint32)
+    u32ptr = C.POINTER(C.c_uint32)
+    rc = lib().vgpu_machine_run_static(p.ctypes.data_as(C.POINTER(C.c_int32)), p.shape[0], initial_pc, initial_fp, max_cycles,
+                                       sa.ctypes.data_as(u32ptr), sv.ctypes.data_as(u32ptr), len(sa), C.byref(h), err, 512)
     if rc != 0:
         raise VgpuError(err.value.decode())
     return MachineTraces(h)

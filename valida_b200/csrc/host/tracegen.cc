@@ -10,6 +10,8 @@
 //   add/sub rows                   alu_u32/src/add/mod.rs:38-129, alu_u32/src/sub/mod.rs
 //   mul floor (2^10 counter rows)  alu_u32/src/mul/mod.rs:38-64
 //   range / program rows           range/src/lib.rs:32-72, program/src/lib.rs:38-81, program/src/stark.rs:22-40
+//   static data                    static_data/src/lib.rs:26-79 (chip rows), memory/src/lib.rs:132-135, 163-169, 265-283
+//                                  (write_static, the static rows that open the memory trace); basic/src/lib.rs:131
 // Output: 14 row-major matrices of canonical BabyBear words in chip order
 // (cpu, program, mem, add, sub, mul, div, shift, lt, com, bitwise, output, range, static_data)
 // plus the two preprocessed traces.
@@ -105,6 +107,7 @@ struct Vm {
     const int32_t* prog; size_t n_instr;
     uint32_t pc = 0, fp = 0, clock = 0;
     CellMap cells;
+    std::vector<std::pair<uint32_t, uint32_t>> static_cells;   // (addr, value), ascending addr (the reference keeps a BTreeMap)
     std::vector<MemOp> mem_ops;
     std::vector<CpuRec> cpu;
     std::vector<AluRec> adds, subs;
@@ -345,21 +348,29 @@ void build_mem(const Vm& vm, Traces& t) {
     constexpr size_t W = 14;
     std::unique_ptr<MemOp[]> hold[2];
     const MemOp* ops = sort_by_addr(vm.mem_ops, hold);
-    size_t n = vm.mem_ops.size(), h = next_pow2(n);
+    // the static cells open the trace (memory/src/lib.rs:163-169): is_static_initial = 1, clk = 0, is_write = 1, counter = n
+    const size_t n0 = vm.static_cells.size();
+    size_t n = vm.mem_ops.size(), h = next_pow2(n0 + n);
     Buf& v = t.store[2];
     v.alloc(h * W);
+    for (size_t i = 0; i < n0; i++) {
+        uint32_t* row = &v[i * W];
+        std::memset(row, 0, W * sizeof(uint32_t));
+        row[0] = vm.static_cells[i].first; word_be(vm.static_cells[i].second, &row[1]);
+        row[6] = 1; row[8] = 1; row[12] = (uint32_t)i;
+    }
     // every word of the n operation rows is written here and the padding rows are cleared below: no zero fill of the
     // whole 0.9 GB matrix first
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)n; i++) {
-        uint32_t* row = &v[(size_t)i * W];
+        uint32_t* row = &v[(n0 + (size_t)i) * W];
         row[0] = ops[i].addr; word_be(ops[i].value, &row[1]);
         row[5] = ops[i].clk; row[6] = 0;
         row[7] = ops[i].is_write ? 0 : 1; row[8] = ops[i].is_write ? 1 : 0;
         row[9] = 0; row[10] = 0; row[11] = 0;
-        row[12] = (uint32_t)i; row[13] = 0;
+        row[12] = (uint32_t)(n0 + (size_t)i); row[13] = 0;
     }
-    v.clear_range(n * W, h * W);
+    v.clear_range((n0 + n) * W, h * W);
     t.main[2] = {v.data(), h, W};
 }
 
@@ -444,8 +455,9 @@ struct vgpu_traces { Traces t; };
 
 extern "C" {
 
-int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
-                   vgpu_traces** out, char* err, uint64_t err_len) {
+int vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                          const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
+                          vgpu_traces** out, char* err, uint64_t err_len) {
     // VGPU_TRACEGEN_TIMING=1 prints the time of each stage to stderr (development aid)
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (getenv("VGPU_TRACEGEN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "tracegen %-12s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
@@ -453,6 +465,16 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
     vm.prog = program_words; vm.n_instr = n_instr; vm.pc = initial_pc; vm.fp = initial_fp;
     vm.prog_counts.assign(n_instr, 0);
     vm.mem_ops.reserve(1 << 20); vm.cpu.reserve(1 << 19);
+    {   // MachineWithStaticDataChip::initialize_memory (static_data/src/lib.rs:26-30): cells are preloaded, nothing is logged
+        std::vector<std::pair<uint32_t, uint32_t>> sc;
+        for (uint64_t i = 0; i < n_static; i++) sc.push_back({static_addrs[i], static_values[i]});
+        std::stable_sort(sc.begin(), sc.end(), [](const std::pair<uint32_t, uint32_t>& x, const std::pair<uint32_t, uint32_t>& y) { return x.first < y.first; });
+        for (auto& c : sc) {            // a repeated address keeps the LAST value, as BTreeMap::insert does
+            if (!vm.static_cells.empty() && vm.static_cells.back().first == c.first) vm.static_cells.back().second = c.second;
+            else vm.static_cells.push_back(c);
+        }
+        for (auto& c : vm.static_cells) vm.cells.set(c.first, c.second);
+    }
     int rc = 0;
     while ((rc = vm.step()) == 0) {
         if (vm.clock >= max_cycles) { vm.err = "cycle limit reached"; rc = -1; break; }
@@ -503,11 +525,24 @@ int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t in
         t.main[12] = {t.store[12].data(), 256, 2};
         t.prep[1] = {t.store[15].data(), 256, 1};
     }
-    zero_chip(t.store[13], t.main[13], 6);  // static_data (no static data loaded)
+    {   // static_data: (addr, value[4], is_real) per cell in address order, padded to a power of two (one zero row when empty)
+        const size_t n0 = vm.static_cells.size(), h = next_pow2(n0 ? n0 : 1);
+        t.store[13].zeros(h * 6);
+        for (size_t i = 0; i < n0; i++) {
+            uint32_t* row = &t.store[13][i * 6];
+            row[0] = vm.static_cells[i].first; word_be(vm.static_cells[i].second, &row[1]); row[5] = 1;
+        }
+        t.main[13] = {t.store[13].data(), h, 6};
+    }
     t.cells = std::move(vm.cells);
     lap("rest");
     *out = tr;
     return 0;
+}
+
+int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                   vgpu_traces** out, char* err, uint64_t err_len) {
+    return vgpu_machine_run_static(program_words, n_instr, initial_pc, initial_fp, max_cycles, nullptr, nullptr, 0, out, err, err_len);
 }
 
 const vgpu_matrix* vgpu_traces_main(const vgpu_traces* t, uint32_t chip) { return chip < 14 ? &t->t.main[chip] : nullptr; }
