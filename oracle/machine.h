@@ -10,6 +10,9 @@
 // Inputs are the 14 main traces (row-major, canonical u32) and the two preprocessed traces
 // (program: 7 columns, range: 1 column) — trace generation is outside this file.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "field.h"
 #include "air.h"
 #include "pcs.h"
@@ -225,6 +228,9 @@ static inline MachineProof machine_prove(const MachineInput& in, const Poseidon1
     const auto& cd = chips();
     Pcs pcs;
     Challenger ch(&perm16);
+    // ORACLE_TIMING=1: wall time of each phase on stderr (where the CPU baseline spends its time)
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("ORACLE_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "oracle %-18s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     // preprocessed commit (derive:299-311)
     PcsData prep_data = pcs.commit_batches({in.program_prep, in.range_prep});
     Digest prep_commit = prep_data.tree.root();
@@ -235,6 +241,7 @@ static inline MachineProof machine_prove(const MachineInput& in, const Poseidon1
     PcsData main_data = pcs.commit_batches(in.main_traces);
     Digest main_commit = main_data.tree.root();
     ch.observe_digest(main_commit.data());
+    lap("commit main");
     Ext5 rnd[3];
     for (int i = 0; i < 3; i++) rnd[i] = ch.sample_ext();
     // permutation traces (339-358)
@@ -246,7 +253,9 @@ static inline MachineProof machine_prove(const MachineInput& in, const Poseidon1
         cumulative_sums[i] = perm_traces[i].v.back();
         perm_flat[i] = perm_traces[i].flatten_to_base();
     }
+    lap("perm traces");
     PcsData perm_data = pcs.commit_batches(perm_flat);
+    lap("commit perm");
     Digest perm_commit = perm_data.tree.root();
     ch.observe_digest(perm_commit.data());
     Ext5 alpha = ch.sample_ext();
@@ -259,10 +268,12 @@ static inline MachineProof machine_prove(const MachineInput& in, const Poseidon1
         const Matrix* plde = cd[i].prep_width ? &prep_data.tree.leaves[prep_idx++] : nullptr;
         quotients[i] = quotient(cd[i], log_degrees[i], plde, main_data.tree.leaves[i], perm_data.tree.leaves[i], cumulative_sums[i], rnd, alpha);
     }
+    lap("quotient");
     std::vector<uint32_t> coset_shifts(NUM_CHIPS, exp_pow2(pcs.coset_shift(), LOG_QUOTIENT_DEGREE));
     PcsData quot_data = pcs.commit_shifted_batches(quotients, coset_shifts);
     Digest quot_commit = quot_data.tree.root();
     ch.observe_digest(quot_commit.data());
+    lap("commit quotient");
     Ext5 zeta = ch.sample_ext();
     // openings (379-392): preprocessed NOT opened (TODO in the reference)
     Points zeta_and_next(NUM_CHIPS), zeta_exp(NUM_CHIPS);
@@ -273,6 +284,7 @@ static inline MachineProof machine_prove(const MachineInput& in, const Poseidon1
     }
     std::vector<Pcs::Round> rounds = {{&main_data, zeta_and_next}, {&perm_data, zeta_and_next}, {&quot_data, zeta_exp}};
     auto opened = pcs.open_multi_batches(rounds, ch);
+    lap("open");
     MachineProof proof;
     proof.main_trace = main_commit; proof.perm_trace = perm_commit; proof.quotient_chunks = quot_commit;
     proof.opening_proof = std::move(opened.second);
