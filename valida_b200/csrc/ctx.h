@@ -53,6 +53,7 @@ struct vgpu_ctx {
     int comm_rank = 0, comm_size = 1;
     bool sharding = false;                                       // commit / FRI-commit work split across ranks
     cudaStream_t copy_stream = nullptr;                         // H2D copies of a pipelined vgpu_prove (staging.cu)
+    bool ntt_attrs_set = false, bary_attrs_set = false;          // cudaFuncSetAttribute is per device: tracked per context, not per process
     bool ktiming = false;
     std::vector<KTimer> ktimers;
     std::vector<cudaEvent_t> event_pool;

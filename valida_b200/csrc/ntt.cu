@@ -545,8 +545,7 @@ int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
                                          ntt_pass_kernel<6>, ntt_pass_kernel<7>, ntt_pass_kernel<8>, ntt_pass_kernel<9>, ntt_pass_kernel<10>, ntt_pass_kernel<11>,
                                          ntt_pass_kernel<12>, ntt_pass_kernel<13>, ntt_pass_kernel<14>};
     if (p.log_len > 14) VG_FAIL(ctx, "ntt: sub-transform 2^%u exceeds the shared-memory tile", p.log_len);
-    static bool attr_set = false;
-    if (!attr_set) { for (auto k : kernels) VG_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    if (!ctx->ntt_attrs_set) { for (auto k : kernels) VG_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); ctx->ntt_attrs_set = true; }
     if (p.post_mode == 2) {   // step of the store phase's running product (see the kernel): base^(k_stride * post_k)
         uint32_t log_nt = 0; while ((1u << log_nt) < threads) log_nt++;
         uint32_t log_t = 0; while ((1u << log_t) < p.tile) log_t++;

@@ -419,11 +419,10 @@ int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t np
         nblocks = bx * p.rs;
         VG_TRY(vg_alloc(ctx, (void**)&partial, (size_t)nblocks * w * BARY_OUT * 4));
         p.partial = partial;
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->bary_attrs_set) {
             VG_CUDA(ctx, cudaFuncSetAttribute(bary_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1 * 5 * BARY_TILE * 4));
             VG_CUDA(ctx, cudaFuncSetAttribute(bary_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 5 * BARY_TILE * 4));
-            attr_set = true;
+            ctx->bary_attrs_set = true;
         }
         KScope ks(ctx, KC_BARY, 4.0 * (double)rows * w);
         if (npoints > 1) bary_kernel<2><<<dim3(bx, by), BARY_THREADS, 2 * 2 * 5 * BARY_TILE * 4, ctx->stream>>>(p);
