@@ -25,13 +25,31 @@ def two_adic_generator(bits):
 def e_scale(a, k): return [x * k % P for x in a]
 
 
+class X:
+    """An element of F_p[X]/(X^5 - 2) with int-like operators (ints embed as constants): lets one AIR text serve the prover
+    folder (base-field cells: plain ints) and the verifier folder (cells opened at zeta: extension values)."""
+    __slots__ = ("c",)
+
+    def __init__(self, c): self.c = [int(v) % P for v in c]
+    @staticmethod
+    def of(v): return v if isinstance(v, X) else X([v, 0, 0, 0, 0])
+    def __add__(self, o): return X(e_add(self.c, X.of(o).c))
+    __radd__ = __add__
+    def __sub__(self, o): return X(e_sub(self.c, X.of(o).c))
+    def __rsub__(self, o): return X(e_sub(X.of(o).c, self.c))
+    def __mul__(self, o): return X(e_mul(self.c, X.of(o).c))
+    __rmul__ = __mul__
+    def __mod__(self, m): return self                  # the int-flavoured AIR text reduces with "% P": a no-op here
+    def __eq__(self, o): return self.c == X.of(o).c
+    def inv(self): return X(e_inv(self.c))
+
+
 # ---- AIRs: each returns the list of base-field constraint values in eval() order ---------------------------------------------
 def air_add(loc, nxt, sel):
     """Add32Chip::eval (alu_u32/src/add/stark.rs:21-55): input_1 0-3, input_2 4-7, carry 8-10, output 11-14."""
     i1, i2, carry, out = loc[0:4], loc[4:8], loc[8:11], loc[11:15]
     base = 1 << 8
-    ov = [(i1[3] + i2[3] - out[3]) % P, (i1[2] + i2[2] - out[2] + carry[0]) % P,
-          (i1[1] + i2[1] - out[1] + carry[1]) % P, (i1[0] + i2[0] - out[0] + carry[2]) % P]
+    ov = [i1[3] + i2[3] - out[3], i1[2] + i2[2] - out[2] + carry[0], i1[1] + i2[1] - out[1] + carry[1], i1[0] + i2[0] - out[0] + carry[2]]
     cons = [o * (o - base) % P for o in ov]
     cons += [(ov[k] * (carry[k] - 1) + (ov[k] - base) * carry[k]) % P for k in range(3)]
     cons += [c * (c - 1) % P for c in carry]        # assert_bool
@@ -41,8 +59,8 @@ def air_add(loc, nxt, sel):
 def air_static_data(loc, nxt, sel):
     """StaticDataChip::eval_main (static_data/src/stark.rs:25-37): when_transition().when(local.is_real * next.is_real)
     .assert_eq(next.addr, local.addr + 4); addr 0, is_real 5."""
-    cond = loc[5] * nxt[5] % P
-    return [sel["transition"] * cond % P * ((nxt[0] - (loc[0] + 4)) % P) % P]
+    cond = loc[5] * nxt[5]
+    return [sel["transition"] * cond * (nxt[0] - (loc[0] + 4)) % P]
 
 
 def air_cpu(loc, nxt, sel):
@@ -62,11 +80,11 @@ def air_cpu(loc, nxt, sel):
     clk_or_zero = loc[50]
     npc, nfp, nclk = nxt[1], nxt[2], nxt[0]
     base = [1 << 24, 1 << 16, 1 << 8, 1]
-    reduce = lambda word: sum(b * x for b, x in zip(base, word)) % P
-    sqdiff = lambda u, v: sum((a - b) * (a - b) for a, b in zip(u, v)) % P
+    reduce = lambda word: sum(b * x for b, x in zip(base, word))
+    sqdiff = lambda u, v: sum((a - b) * (a - b) for a, b in zip(u, v))
     B = 24                                            # BYTES_PER_INSTR
     cons = []
-    z = lambda *factors: cons.append(__import__("functools").reduce(lambda a, b: a * b % P, [f % P for f in factors], 1))
+    z = _z(cons)
     # eval_pc (stark.rs:206-251)
     should_inc = is_imm32 + is_loadfp + is_bus_op + is_advice
     inc_pc = pc + 1
@@ -132,9 +150,14 @@ def _z(cons):
     def z(*factors):
         v = 1
         for f in factors:
-            v = v * (f % P) % P
-        cons.append(v)
+            v = v * f
+        cons.append(v % P)
     return z
+
+
+def bits_value(bits):
+    """sum_k bit_k * 2^k without shifting (cells may be extension values)"""
+    return sum(b * (1 << k) for k, b in enumerate(bits))
 
 
 def air_sub(loc, nxt, sel):
@@ -155,8 +178,8 @@ def air_mul(loc, nxt, sel):
     """Mul32Chip::eval (alu_u32/src/mul/stark.rs:23-82): input_1 0-3, input_2 4-7, output 8-11, r 12, s 13, counter 17."""
     i1, i2, out, r, s_, counter, ncounter = loc[0:4], loc[4:8], loc[8:12], loc[12], loc[13], loc[17], nxt[17]
     base_m = [1, 1 << 8, 1 << 16, 1 << 24]
-    pi_m = lambda N: sum(base_m[i + j] * i1[3 - i] * i2[3 - j] for i in range(N) for j in range(N) if i + j < N) % P
-    sigma_m = lambda N: sum(base_m[i] * x for i, x in enumerate(list(reversed(out))[:N])) % P
+    pi_m = lambda N: sum(base_m[i + j] * i1[3 - i] * i2[3 - j] for i in range(N) for j in range(N) if i + j < N)
+    sigma_m = lambda N: sum(base_m[i] * x for i, x in enumerate(list(reversed(out))[:N]))
     cons = []
     z = _z(cons)
     z(pi_m(4) - sigma_m(4) - r * 2)
@@ -173,7 +196,7 @@ def air_shift(loc, nxt, sel):
     i2, bits, temp_1, pw2, shl, shr, sra = loc[4:8], loc[12:20], loc[20], loc[21:25], loc[25], loc[26], loc[27]
     cons = []
     z = _z(cons)
-    z(i2[3] - sum(b << k for k, b in enumerate(bits)))
+    z(i2[3] - bits_value(bits))
     for b in bits:
         z(b, b - 1)
     z(temp_1 - (bits[0] * 2) * (bits[1] * 4) * (bits[2] * 16))
@@ -195,8 +218,8 @@ def air_lt(loc, nxt, sel):
     tb1, tb2, dsig = loc[28:36], loc[36:44], loc[44]
     cons = []
     z = _z(cons)
-    bit_comp = sum(b << k for k, b in enumerate(bits)) % P
-    flag_sum = sum(bf) % P
+    bit_comp = bits_value(bits)
+    flag_sum = sum(bf)
     z(flag_sum, flag_sum - 1)
     z(bf[0] - 1, i1[0] - i2[0])
     z(bf[0] + bf[1] - 1, i1[1] - i2[1])
@@ -207,8 +230,8 @@ def air_lt(loc, nxt, sel):
         z(bf[i], 256 + i1[i] - i2[i] - bit_comp)
         z(bf[i], (i1[i] - i2[i]) * diff_inv - 1)
         z(bf[i], bf[i] - 1)
-    z(sum(b << k for k, b in enumerate(tb1)) - i1[0])
-    z(sum(b << k for k, b in enumerate(tb2)) - i2[0])
+    z(bits_value(tb1) - i1[0])
+    z(bits_value(tb2) - i2[0])
     is_signed = is_slt + is_sle
     is_unsigned, same_sign, are_equal = 1 - is_signed, 1 - dsig, 1 - flag_sum
     z(is_unsigned, dsig)
@@ -251,10 +274,10 @@ def air_bitwise(loc, nxt, sel):
     z = _z(cons)
     for i in range(4):
         b1, b2 = loc[8 + 8 * i:16 + 8 * i], loc[40 + 8 * i:48 + 8 * i]
-        byte_1, byte_2 = sum(b << k for k, b in enumerate(b1)) % P, sum(b << k for k, b in enumerate(b2)) % P
+        byte_1, byte_2 = bits_value(b1), bits_value(b2)
         z(i1[i] - byte_1)
         z(i2[i] - byte_2)
-        b_and = sum(x * y % P << k for k, (x, y) in enumerate(zip(b1, b2))) % P
+        b_and = sum(x * y * (1 << k) for k, (x, y) in enumerate(zip(b1, b2)))
         z(is_and, b_and - out[i])
         z(is_or, byte_1 + byte_2 - b_and - out[i])
         z(is_xor, byte_1 + byte_2 - 2 * b_and - out[i])
@@ -355,3 +378,84 @@ def test_python_quotient_matches_oracle_on_random_traces(built, oracle, chip):
     want = quotient_py(chip, log_degree, nat(main), nat(perm), [int(v) for v in cs], ch, [int(v) for v in alpha])
     got = oracle.quotient(chip, log_degree, rev(prep) if pw else None, rev(main), rev(perm), cs, ch, alpha)
     assert np.array_equal(got, want)
+
+
+# ---- verify_constraints (machine/src/verify.rs:11-107) on the opened values of a real proof -------------------------------------
+def verify_constraints_py(chip, log_degree, trace_local, trace_next, perm_local, perm_next, quotient_chunks, cumsum, zeta, alpha, ch15):
+    """Every argument is a list of ext5 coefficient lists, as they sit in OpenedValues.  Returns (folded constraints, z_h * quotient)."""
+    n = 1 << log_degree
+    g_inv = pow(two_adic_generator(log_degree), P - 2, P)
+    zeta = X(zeta)
+    zeta_n = zeta
+    for _ in range(log_degree):
+        zeta_n = zeta_n * zeta_n
+    z_h = zeta_n - 1
+    sel = {"first": z_h * (zeta - 1).inv(), "last": z_h * (zeta - g_inv).inv(), "transition": zeta - g_inv}
+    monomial = lambda k: X([1 if i == k else 0 for i in range(5)])
+    unflatten = lambda v: [sum(X(v[5 * m + k]) * monomial(k) for k in range(5)) for m in range(len(v) // 5)]   # sum_k x_k * X^k
+    loc, nxt = [X(v) for v in trace_local], [X(v) for v in trace_next]
+    pl, pn = unflatten(perm_local), unflatten(perm_next)
+    parts = unflatten(quotient_chunks)
+    alpha_x, folded = X(alpha), X.of(0)
+    r1, r2 = X(ch15[5:10]), X(ch15[10:15])
+    alphas_global, acc = [], X.of(1)
+    for _ in range(4):
+        acc = acc * r1
+        alphas_global.append(acc)
+
+    def assert_zero(c):
+        nonlocal folded
+        folded = folded * alpha_x + c
+
+    if AIRS[chip]:
+        for c in AIRS[chip](loc, nxt, sel):
+            assert_zero(c)
+    inter = CHIPS[chip]
+    k = len(inter)
+    field = lambda col, row: (row[col[1]] if col[0] == "main" else X.of(col[1]) if col[0] == "const"
+                              else sum(row[c] * w for c, w in col[1]) if col[0] == "weighted" else sum(row[c] for c in col[1]))
+    lhs, rhs, phi0 = pn[k] - pl[k], X.of(0), X.of(0)
+    for m, (sign, bus, fields, count) in enumerate(inter):
+        rlc, beta = X.of(0), X.of(1)
+        for f in fields:
+            rlc = rlc + beta * field(f, loc)
+            beta = beta * r2
+        rlc = rlc + alphas_global[bus]
+        assert_zero(rlc * pl[m] - 1)
+        t_loc, t_nxt = pl[m] * field(count, loc), pn[m] * field(count, nxt)
+        if sign == SEND:
+            phi0, rhs = phi0 + t_loc, rhs + t_nxt
+        else:
+            phi0, rhs = phi0 - t_loc, rhs - t_nxt
+    assert_zero((lhs - rhs) * sel["transition"])
+    assert_zero((pl[k] - phi0) * sel["first"])
+    assert_zero((pl[k] - X(cumsum)) * sel["last"])
+    # reverse_slice_index_bits(&mut quotient_parts) is the identity on two parts; quotient = sum_i zeta^i * part_i
+    quotient = parts[0] + zeta * parts[1]
+    assert len(parts) == 2
+    return folded, z_h * quotient
+
+
+@pytest.mark.parametrize("workload", ["fib3", "static_data", "config5"])
+def test_in_repo_verifier_identity_holds_on_oracle_proofs(built, oracle, workload):
+    """folded_constraints(zeta) == Z_H(zeta) * quotient(zeta) for every chip of a real proof, with the constraints evaluated by the
+    Python transcriptions on the OPENED values (VerifierConstraintFolder semantics) and the quotient recombined as verify.rs does."""
+    import programs
+    import valida_b200 as vb
+
+    if workload == "fib3":
+        t = vb.run_program(vb.fib_program(3), initial_fp=0x1000)
+    elif workload == "static_data":
+        prog, cells = programs.static_data_program()
+        t = vb.run_program(prog, initial_fp=0x1000, static_data=cells)
+    else:
+        t = vb.run_program(programs.config5_program(6), initial_fp=0x1000)
+    pr = oracle.prove(t.main, t.preprocessed, debug_checks=False)
+    tr = pr.transcript()
+    rows = lambda a: [[int(v) for v in r] for r in a]
+    for chip in range(14):
+        log_degree = t.main[chip].shape[0].bit_length() - 1
+        ov = [rows(pr.opened(chip, w)) for w in range(5)]
+        folded, rhs = verify_constraints_py(chip, log_degree, ov[0], ov[1], ov[2], ov[3], ov[4], [int(v) for v in pr.cumulative_sum(chip)],
+                                            [int(v) for v in tr["zeta"]], [int(v) for v in tr["alpha"]], [int(v) for v in tr["perm_challenges"]])
+        assert folded == rhs, (workload, chip)
