@@ -459,3 +459,33 @@ def test_in_repo_verifier_identity_holds_on_oracle_proofs(built, oracle, workloa
         folded, rhs = verify_constraints_py(chip, log_degree, ov[0], ov[1], ov[2], ov[3], ov[4], [int(v) for v in pr.cumulative_sum(chip)],
                                             [int(v) for v in tr["zeta"]], [int(v) for v in tr["alpha"]], [int(v) for v in tr["perm_challenges"]])
         assert folded == rhs, (workload, chip)
+
+
+# ---- get_log_quotient_degree (machine/src/symbolic/symbolic_builder.rs:17-43, symbolic_expression.rs:41-61) ------------------------
+class Deg:
+    """degree_multiple of a symbolic expression: variables 1, is_first_row / is_last_row 1, is_transition 0, constants 0; a sum takes
+    the maximum, a product the sum."""
+    __slots__ = ("d",)
+
+    def __init__(self, d): self.d = d
+    @staticmethod
+    def of(v): return v if isinstance(v, Deg) else Deg(0)
+    def __add__(self, o): return Deg(max(self.d, Deg.of(o).d))
+    __radd__ = __sub__ = __rsub__ = __add__
+    def __mul__(self, o): return Deg(self.d + Deg.of(o).d)
+    __rmul__ = __mul__
+    def __mod__(self, m): return self
+
+
+def test_every_air_has_constraint_degree_at_most_three_so_the_quotient_has_two_chunks(built, oracle):
+    """log_quotient_degree = log2_ceil(max(max_constraint_degree, 3) - 1); only Air::eval counts (the permutation constraints are not
+    part of get_symbolic_constraints).  Degree <= 3 on every chip => 1 => two quotient chunks, as the oracle and the kernels assume."""
+    sel = {"first": Deg(1), "last": Deg(1), "transition": Deg(0)}
+    for chip, air in AIRS.items():
+        if air is None:
+            continue
+        w = oracle.chip_width(chip)
+        degs = [Deg.of(c).d for c in air([Deg(1)] * w, [Deg(1)] * w, sel)]
+        constraint_degree = max(max(degs), 3)
+        assert (constraint_degree - 1 - 1).bit_length() == 1, (chip, max(degs))        # log2_ceil(constraint_degree - 1)
+        assert max(degs) <= 3, (chip, degs)
