@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <string>
 #include <memory>
+#include <new>
+#include <exception>
 #include <chrono>
 #include <cstdio>
 #include <omp.h>
@@ -85,7 +87,7 @@ struct Buf {
         std::free(p);
         n = count;
         p = (uint32_t*)std::malloc((count ? count : 1) * sizeof(uint32_t));
-        if (!p) { n = 0; std::abort(); }
+        if (!p) { n = 0; throw std::bad_alloc(); }         // caught at the C boundary (vgpu_machine_run_static)
         return p;
     }
     void clear_range(size_t begin, size_t end) {         // words [begin, end), all host threads
@@ -455,9 +457,9 @@ struct vgpu_traces { Traces t; };
 
 extern "C" {
 
-int vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
-                          const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
-                          vgpu_traces** out, char* err, uint64_t err_len) {
+static int machine_run_impl(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                            const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
+                            vgpu_traces** out, char* err, uint64_t err_len) {
     // VGPU_TRACEGEN_TIMING=1 prints the time of each stage to stderr (development aid)
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (getenv("VGPU_TRACEGEN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "tracegen %-12s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
@@ -484,7 +486,7 @@ int vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint
     size_t padded = next_pow2(vm.clock);
     vm.prog_counts[vm.pc] += (uint32_t)(padded - vm.clock);
 
-    vgpu_traces* tr = new vgpu_traces();
+    std::unique_ptr<vgpu_traces> tr(new vgpu_traces());      // released to the caller at the end; freed if an allocation below throws
     Traces& t = tr->t;
     t.clock = vm.clock; t.n_mem_ops = (uint32_t)vm.mem_ops.size(); t.n_add_ops = (uint32_t)vm.adds.size(); t.n_sub_ops = (uint32_t)vm.subs.size();
     lap("vm run");
@@ -536,8 +538,19 @@ int vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint
     }
     t.cells = std::move(vm.cells);
     lap("rest");
-    *out = tr;
+    *out = tr.release();
     return 0;
+}
+
+int vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                          const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
+                          vgpu_traces** out, char* err, uint64_t err_len) {
+    try {   // no exception crosses the C boundary: host allocation failures (traces are gigabytes) come back as an error string
+        return machine_run_impl(program_words, n_instr, initial_pc, initial_fp, max_cycles, static_addrs, static_values, n_static, out, err, err_len);
+    } catch (const std::exception& e) {
+        if (err && err_len) { std::snprintf(err, err_len, "host witness generation failed: %s", e.what()); }
+        return -1;
+    }
 }
 
 int vgpu_machine_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
