@@ -47,6 +47,30 @@ struct AluRec { uint32_t a, b, c; };
 struct LtRec { uint32_t a, b, c; uint32_t opcode; };
 using BitRec = LtRec;
 
+// Append-only log of trivially copyable records.  Growth goes through realloc(), which glibc serves with mremap() for large
+// blocks — no copy of the 150 MB memory log at every doubling (std::vector growth cost 0.2-0.3 s of a 0.5 s run loop).
+template <class T> struct PodVec {
+    T* p = nullptr; size_t n = 0, cap = 0;
+    PodVec() = default;
+    PodVec(const PodVec&) = delete; PodVec& operator=(const PodVec&) = delete;
+    ~PodVec() { std::free(p); }
+    void push_back(const T& v) {
+        if (n == cap) {
+            const size_t nc = cap ? 2 * cap : 4096;
+            T* q = (T*)std::realloc(p, nc * sizeof(T));
+            if (!q) throw std::bad_alloc();
+            p = q; cap = nc;
+        }
+        p[n++] = v;
+    }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    const T* data() const { return p; }
+    const T& operator[](size_t i) const { return p[i]; }
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+};
+
 // Memory cells of the VM: open addressing, linear probing, power-of-two table (the interpreter touches it two or three
 // times per cycle; std::unordered_map made that the slowest part of the run loop).
 struct CellMap {
@@ -110,11 +134,11 @@ struct Vm {
     uint32_t pc = 0, fp = 0, clock = 0;
     CellMap cells;
     std::vector<std::pair<uint32_t, uint32_t>> static_cells;   // (addr, value), ascending addr (the reference keeps a BTreeMap)
-    std::vector<MemOp> mem_ops;
-    std::vector<CpuRec> cpu;
-    std::vector<AluRec> adds, subs;
-    std::vector<LtRec> lts;
-    std::vector<BitRec> bits;
+    PodVec<MemOp> mem_ops;
+    PodVec<CpuRec> cpu;
+    PodVec<AluRec> adds, subs;
+    PodVec<LtRec> lts;
+    PodVec<BitRec> bits;
     std::vector<uint32_t> prog_counts;
     uint32_t range_count[256] = {0};
     std::string err;
@@ -308,7 +332,7 @@ void build_cpu(const Vm& vm, Traces& t) {
 // STABLE sort on the address alone gives the same order).  LSD radix, 11 bits per pass, passes whose digit is the same for
 // every key are skipped; per-thread histograms over contiguous chunks keep each pass stable.
 // Returns the sorted log (a fresh array, or `in` itself when no pass was needed); `hold` owns whatever was allocated.
-const MemOp* sort_by_addr(const std::vector<MemOp>& in, std::unique_ptr<MemOp[]> hold[2]) {
+const MemOp* sort_by_addr(const PodVec<MemOp>& in, std::unique_ptr<MemOp[]> hold[2]) {
     const size_t n = in.size();
     if (n < 2) return in.data();
     uint32_t all_or = 0, all_and = 0xffffffffu;
@@ -376,7 +400,7 @@ void build_mem(const Vm& vm, Traces& t) {
     t.main[2] = {v.data(), h, W};
 }
 
-void build_addsub(const std::vector<AluRec>& ops, bool is_add, Buf& v, vgpu_matrix& out) {
+void build_addsub(const PodVec<AluRec>& ops, bool is_add, Buf& v, vgpu_matrix& out) {
     constexpr size_t W = 16;
     size_t n = ops.size(), h = next_pow2(n);
     v.zeros(h * W);
@@ -400,7 +424,7 @@ void build_addsub(const std::vector<AluRec>& ops, bool is_add, Buf& v, vgpu_matr
 }
 
 // Lt32Chip::op_to_row / set_cols (alu_u32/src/lt/mod.rs:86-160)
-void build_lt(const std::vector<LtRec>& ops, Buf& v, vgpu_matrix& out) {
+void build_lt(const PodVec<LtRec>& ops, Buf& v, vgpu_matrix& out) {
     constexpr size_t W = 45;
     size_t n = ops.size(), h = next_pow2(n);
     v.zeros(h * W);
@@ -432,7 +456,7 @@ void build_lt(const std::vector<LtRec>& ops, Buf& v, vgpu_matrix& out) {
 
 // Bitwise32Chip::op_to_row / set_cols (alu_u32/src/bitwise/mod.rs:84-131): input_1 0..3, input_2 4..7,
 // bits_1[byte][bit] 8 + 8*byte + bit, bits_2 40 + ..., output 72..75, is_and 76, is_or 77, is_xor 78
-void build_bitwise(const std::vector<BitRec>& ops, Buf& v, vgpu_matrix& out) {
+void build_bitwise(const PodVec<BitRec>& ops, Buf& v, vgpu_matrix& out) {
     constexpr size_t W = 79;
     size_t n = ops.size(), h = next_pow2(n);
     v.zeros(h * W);
@@ -466,7 +490,6 @@ static int machine_run_impl(const int32_t* program_words, uint64_t n_instr, uint
     Vm vm;
     vm.prog = program_words; vm.n_instr = n_instr; vm.pc = initial_pc; vm.fp = initial_fp;
     vm.prog_counts.assign(n_instr, 0);
-    vm.mem_ops.reserve(1 << 20); vm.cpu.reserve(1 << 19);
     {   // MachineWithStaticDataChip::initialize_memory (static_data/src/lib.rs:26-30): cells are preloaded, nothing is logged
         std::vector<std::pair<uint32_t, uint32_t>> sc;
         for (uint64_t i = 0; i < n_static; i++) sc.push_back({static_addrs[i], static_values[i]});
