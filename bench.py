@@ -389,6 +389,31 @@ def main():
             ntt_line = {"workload": "2^20 x 64 NTT + iNTT (natural order in/out), 256 MiB working set > L2", "ms_forward_plus_inverse": ms_pair,
                         "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "bytes": "8*h*w per transform", "roundtrip_bit_exact": roundtrip_ok}
             dx.free()
+            # SURVEY 8(d) config 2 also asks for the one-column and the CPU-chip-width shapes; they are extras to the line:
+            # any failure is recorded here and changes nothing above
+            try:
+                others = {}
+                for w2 in (51, 1):
+                    x2 = np.ascontiguousarray(x[:, :w2])
+                    d2 = ctx.upload(x2)
+                    for _ in range(3):
+                        dft.dft_batch(d2); dft.idft_batch(d2)
+                    torch.cuda.synchronize()
+                    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    m0.record(stream)
+                    for _ in range(reps):
+                        dft.dft_batch(d2); dft.idft_batch(d2)
+                    m1.record(stream)
+                    torch.cuda.synchronize()
+                    ms2 = m0.elapsed_time(m1) / reps
+                    ok2 = bool(np.array_equal(d2.download(), x2))
+                    d2.free()
+                    g2 = 2 * 8.0 * hh * w2 / (ms2 / 1e3) / 1e9
+                    others["2^20 x %d" % w2] = {"ms_forward_plus_inverse": ms2, "achieved": g2, "unit": "GB/s", "frac": g2 / peak, "roundtrip_bit_exact": ok2,
+                                               "l2": "working set %d MiB %s L2" % (hh * w2 * 4 >> 20, ">" if hh * w2 * 4 > 126 << 20 else "fits in")}
+                ntt_line["other_widths"] = others
+            except Exception as exc:   # noqa: BLE001
+                ntt_line["other_widths"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
