@@ -40,6 +40,21 @@ static inline uint32_t exp_pow2(uint32_t a, int k) { while (k-- > 0) a = mul(a, 
 // TwoAdicField::two_adic_generator(bits)  [P3-UNVERIFIED; SURVEY App. A item 2]
 static inline uint32_t two_adic_generator(int bits) { assert(bits <= TWO_ADICITY); return exp_pow2(TWO_ADIC_ROOT_27, TWO_ADICITY - bits); }
 
+// out[i] = start * base^i for i < n, on all host threads (each chunk restarts from start * base^chunk_begin): replaces the serial
+// running products that made up most of the prover's non-parallel time.
+static inline std::vector<uint32_t> geometric(uint32_t start, uint32_t base, size_t n) {
+    std::vector<uint32_t> out(n);
+    const size_t CH = 1 << 14;
+    const long nch = (long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static) if (n > 4 * CH)
+    for (long c = 0; c < nch; c++) {
+        const size_t a = (size_t)c * CH, b = std::min(n, a + CH);
+        uint32_t x = mul(start, pw(base, a));
+        for (size_t i = a; i < b; i++) { out[i] = x; x = mul(x, base); }
+    }
+    return out;
+}
+
 static inline uint32_t reverse_bits_len(uint32_t x, int bits) {
     uint32_t r = 0;
     for (int i = 0; i < bits; i++) { r = (r << 1) | ((x >> i) & 1); }
@@ -65,16 +80,26 @@ static inline Ext5 operator+(const Ext5& a, const Ext5& b) { Ext5 r; for (int i 
 static inline Ext5 operator-(const Ext5& a, const Ext5& b) { Ext5 r; for (int i = 0; i < 5; i++) r.c[i] = sub(a.c[i], b.c[i]); return r; }
 static inline Ext5 operator-(const Ext5& a) { Ext5 r; for (int i = 0; i < 5; i++) r.c[i] = neg(a.c[i]); return r; }
 static inline Ext5 operator*(const Ext5& a, const Ext5& b) {
-    // schoolbook product reduced with X^5 = 2; accumulate in u64 (each term < 2^62, <= 9 terms... reduce per term)
-    uint64_t t[9] = {0};
-    for (int i = 0; i < 5; i++)
-        for (int j = 0; j < 5; j++) t[i + j] += ((uint64_t)a.c[i] * b.c[j]) % P;
+    // schoolbook product reduced with X^5 = 2.  Canonical factors are < p < 2^31, so a raw product is < 2^62 and FOUR of them
+    // fit in a u64 (4 p^2 < 2^64): every diagonal is summed raw, at most four terms at a time, and reduced once or twice —
+    // 11 reductions instead of one per term (same values: reduction is exact).
+    const uint32_t* x = a.c; const uint32_t* y = b.c;
+    auto pr = [&](int i, int j) { return (uint64_t)x[i] * y[j]; };
+    const uint64_t t0 = pr(0, 0) % P;
+    const uint64_t t1 = (pr(0, 1) + pr(1, 0)) % P;
+    const uint64_t t2 = (pr(0, 2) + pr(1, 1) + pr(2, 0)) % P;
+    const uint64_t t3 = (pr(0, 3) + pr(1, 2) + pr(2, 1) + pr(3, 0)) % P;
+    const uint64_t t4 = ((pr(0, 4) + pr(1, 3) + pr(2, 2) + pr(3, 1)) % P + pr(4, 0)) % P;
+    const uint64_t t5 = (pr(1, 4) + pr(2, 3) + pr(3, 2) + pr(4, 1)) % P;
+    const uint64_t t6 = (pr(2, 4) + pr(3, 3) + pr(4, 2)) % P;
+    const uint64_t t7 = (pr(3, 4) + pr(4, 3)) % P;
+    const uint64_t t8 = pr(4, 4) % P;
     Ext5 r;
-    for (int k = 0; k < 5; k++) {
-        uint64_t v = t[k] % P;
-        if (k + 5 < 9) v += (t[k + 5] % P) * EXT_W;
-        r.c[k] = (uint32_t)(v % P);
-    }
+    r.c[0] = (uint32_t)((t0 + EXT_W * t5) % P);
+    r.c[1] = (uint32_t)((t1 + EXT_W * t6) % P);
+    r.c[2] = (uint32_t)((t2 + EXT_W * t7) % P);
+    r.c[3] = (uint32_t)((t3 + EXT_W * t8) % P);
+    r.c[4] = (uint32_t)t4;
     return r;
 }
 static inline Ext5 operator*(const Ext5& a, uint32_t s) { Ext5 r; for (int i = 0; i < 5; i++) r.c[i] = mul(a.c[i], s); return r; }
@@ -158,20 +183,44 @@ static inline std::vector<Ext5> batch_inverse(const std::vector<Ext5>& v) {
     return out;
 }
 // valida util::batch_multiplicative_inverse_allowing_zero (util/src/lib.rs:21-43): zeros stay zero.
+// Chunked like batch_inverse, zeros skipped in place (no serial gather / scatter of the non-zero entries).
 static inline std::vector<Ext5> batch_inverse_allowing_zero(const std::vector<Ext5>& v) {
-    std::vector<Ext5> nz; std::vector<size_t> idx;
-    for (size_t i = 0; i < v.size(); i++) if (!v[i].is_zero()) { nz.push_back(v[i]); idx.push_back(i); }
-    std::vector<Ext5> inz = batch_inverse(nz);
-    std::vector<Ext5> out = v;
-    for (size_t k = 0; k < idx.size(); k++) out[idx[k]] = inz[k];
+    size_t n = v.size();
+    std::vector<Ext5> out(n);
+    const size_t CH = 4096;
+    long nch = (long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static) if (n > 4 * CH)
+    for (long c = 0; c < nch; c++) {
+        size_t a = (size_t)c * CH, b = std::min(n, a + CH);
+        std::vector<Ext5> pref(b - a);
+        Ext5 acc = Ext5::one();
+        bool any = false;
+        for (size_t i = a; i < b; i++) { pref[i - a] = acc; if (!v[i].is_zero()) { acc = acc * v[i]; any = true; } }
+        Ext5 ia = any ? ext_inv(acc) : Ext5::one();
+        for (size_t i = b; i-- > a;) {
+            if (v[i].is_zero()) { out[i] = Ext5::zero(); continue; }
+            out[i] = ia * pref[i - a]; ia = ia * v[i];
+        }
+    }
     return out;
 }
 static inline std::vector<uint32_t> batch_inverse_allowing_zero(const std::vector<uint32_t>& v) {
-    std::vector<uint32_t> nz; std::vector<size_t> idx;
-    for (size_t i = 0; i < v.size(); i++) if (v[i]) { nz.push_back(v[i]); idx.push_back(i); }
-    std::vector<uint32_t> inz = batch_inverse(nz);
-    std::vector<uint32_t> out = v;
-    for (size_t k = 0; k < idx.size(); k++) out[idx[k]] = inz[k];
+    size_t n = v.size();
+    std::vector<uint32_t> out(n);
+    const size_t CH = 8192;
+    long nch = (long)((n + CH - 1) / CH);
+#pragma omp parallel for schedule(static) if (n > 4 * CH)
+    for (long c = 0; c < nch; c++) {
+        size_t a = (size_t)c * CH, b = std::min(n, a + CH);
+        std::vector<uint32_t> pref(b - a);
+        uint32_t acc = 1;
+        for (size_t i = a; i < b; i++) { pref[i - a] = acc; if (v[i]) acc = mul(acc, v[i]); }
+        uint32_t ia = inv(acc);
+        for (size_t i = b; i-- > a;) {
+            if (!v[i]) { out[i] = 0; continue; }
+            out[i] = mul(ia, pref[i - a]); ia = mul(ia, v[i]);
+        }
+    }
     return out;
 }
 

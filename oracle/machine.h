@@ -25,7 +25,8 @@ struct ExtMatrix {  // RowMajorMatrix<Challenge>
     size_t height() const { return width ? v.size() / width : 0; }
     Matrix flatten_to_base() const {
         Matrix m(height(), width * 5);
-        for (size_t i = 0; i < v.size(); i++) std::memcpy(&m.v[i * 5], v[i].c, 20);
+#pragma omp parallel for schedule(static) if (v.size() > 8192)
+        for (long i = 0; i < (long)v.size(); i++) std::memcpy(&m.v[(size_t)i * 5], v[i].c, 20);
         return m;
     }
 };
@@ -63,18 +64,22 @@ static inline ExtMatrix generate_permutation_trace(const ChipDef& chip, const Ma
     }
     // batch_multiplicative_inverse_allowing_zero over the whole matrix (the phi column is still zero)
     perm.v = batch_inverse_allowing_zero(perm.v);
-    Ext5 phi = Ext5::zero();
-    for (size_t n = 0; n < h; n++) {
+    // the row terms on all host threads, then the running sum itself (additions only) in row order, as the reference's loop
+#pragma omp parallel for schedule(static) firstprivate(mrow, prow) if (h > 1024)
+    for (long n = 0; n < (long)h; n++) {
         for (size_t c = 0; c < main.width; c++) mrow[c] = Fp(main.at(n, c));
         if (prep) for (size_t c = 0; c < prep->width; c++) prow[c] = Fp(prep->at(n, c));
+        Ext5 term = Ext5::zero();
         for (size_t m = 0; m < k; m++) {
             const Interaction& it = chip.interactions[m];
             uint32_t mult = it.count.apply<Fp>(prow.data(), mrow.data()).v;
             Ext5 t = perm.v[n * pw_ + m] * mult;
-            if (it.is_send) phi += t; else phi -= t;
+            if (it.is_send) term += t; else term -= t;
         }
-        perm.v[n * pw_ + k] = phi;
+        perm.v[n * pw_ + k] = term;
     }
+    Ext5 phi = Ext5::zero();
+    for (size_t n = 0; n < h; n++) { phi += perm.v[n * pw_ + k]; perm.v[n * pw_ + k] = phi; }
     return perm;
 }
 
@@ -149,10 +154,10 @@ static inline Matrix quotient(const ChipDef& chip, int log_degree, const Matrix*
     // ZerofierOnCoset: Z_H(s g_ext^i) = s^n * v^(i mod rate) - 1, v = rate-th root of unity
     uint32_t zevals[2] = {sub(s_pow_n, 1), sub(mul(s_pow_n, two_adic_generator(lqd)), 1)};
     uint32_t zinv[2] = {inv(zevals[0]), inv(zevals[1])};
-    std::vector<uint32_t> coset(qs);
-    { uint32_t x = s; for (size_t i = 0; i < qs; i++) { coset[i] = x; x = mul(x, g_ext); } }
+    std::vector<uint32_t> coset = geometric(s, g_ext, qs);
     std::vector<uint32_t> den_first(qs), den_last(qs);
-    for (size_t i = 0; i < qs; i++) { den_first[i] = sub(coset[i], 1); den_last[i] = sub(coset[i], subgroup_last); }  // g_h^(n-1) = g_h^-1
+#pragma omp parallel for schedule(static) if (qs > 8192)
+    for (long i = 0; i < (long)qs; i++) { den_first[i] = sub(coset[i], 1); den_last[i] = sub(coset[i], subgroup_last); }  // g_h^(n-1) = g_h^-1
     std::vector<uint32_t> inv_first = batch_inverse(den_first), inv_last = batch_inverse(den_last);
     size_t w = main_lde.width, pwb = perm_lde.width, pwe = pwb / 5, wp = prep_lde ? prep_lde->width : 0;
     std::vector<Ext5> q(qs);
@@ -181,13 +186,13 @@ static inline Matrix quotient(const ChipDef& chip, int log_degree, const Matrix*
     // decompose_and_flatten(q, shift = s, log_chunks = 1): even/odd halves over the coset s^2 H
     Matrix out(n, 10);
     uint32_t g_inv = inv(g_ext), one_half = inv(2);
-    uint32_t gp = mul(inv(s), one_half);
-    for (size_t i = 0; i < n; i++) {
+    std::vector<uint32_t> gps = geometric(mul(inv(s), one_half), g_inv, n);
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (long i = 0; i < (long)n; i++) {
         Ext5 even = (q[i] + q[i + n]) * one_half;
-        Ext5 odd = (q[i] - q[i + n]) * gp;
+        Ext5 odd = (q[i] - q[i + n]) * gps[i];
         std::memcpy(out.row(i), even.c, 20);
         std::memcpy(out.row(i) + 5, odd.c, 20);
-        gp = mul(gp, g_inv);
     }
     return out;
 }

@@ -32,9 +32,7 @@ static inline void dft_rows(Matrix& m, bool inverse) {
     for (int s = 1; s <= lg; s++) {
         size_t half = 1ull << (s - 1), len = half * 2;
         uint32_t wm = exp_pow2(root, lg - s);
-        std::vector<uint32_t> tw(half);
-        tw[0] = 1;
-        for (size_t k = 1; k < half; k++) tw[k] = mul(tw[k - 1], wm);
+        std::vector<uint32_t> tw = geometric(1, wm, half);
         long nb = (long)(h / len);
 #pragma omp parallel for schedule(static) if (h * w > (1u << 16))
         for (long b = 0; b < nb * (long)half; b++) {
@@ -64,8 +62,7 @@ static inline Matrix coset_lde_batch(const Matrix& in, int added_bits, uint32_t 
     Matrix coeffs = idft_batch(in);
     size_t h = in.height(), w = in.width, H = h << added_bits;
     Matrix out(H, w);
-    std::vector<uint32_t> sp(h);
-    { uint32_t s = 1; for (size_t i = 0; i < h; i++) { sp[i] = s; s = mul(s, shift); } }
+    std::vector<uint32_t> sp = geometric(1, shift, h);
 #pragma omp parallel for schedule(static) if (h * w > (1u << 16))
     for (long i = 0; i < (long)h; i++)
         for (size_t c = 0; c < w; c++) out.v[i * w + c] = mul(coeffs.v[i * w + c], sp[i]);

@@ -37,7 +37,8 @@ using Points = std::vector<std::vector<Ext5>>;  // [matrix][point]
 // ExtensionMmcs: an ext-field matrix of width 2 is committed as its base flattening (width 10).
 static inline Matrix flatten_ext_pairs(const std::vector<Ext5>& v) {
     Matrix m(v.size() / 2, 10);
-    for (size_t i = 0; i < v.size(); i++) std::memcpy(&m.v[i * 5], v[i].c, 20);
+#pragma omp parallel for schedule(static) if (v.size() > 8192)
+    for (long i = 0; i < (long)v.size(); i++) std::memcpy(&m.v[(size_t)i * 5], v[i].c, 20);
     return m;
 }
 
@@ -50,9 +51,7 @@ static inline std::vector<Ext5> fold_even_odd(const std::vector<Ext5>& poly, con
     Ext5 half_beta = beta * one_half;
     std::vector<Ext5> powers(half);
     {
-        std::vector<uint32_t> gp(half);
-        uint32_t a = 1;
-        for (size_t i = 0; i < half; i++) { gp[i] = a; a = mul(a, g_inv); }
+        std::vector<uint32_t> gp = geometric(1, g_inv, half);
 #pragma omp parallel for schedule(static) if (half > 4096)
         for (long i = 0; i < (long)half; i++) powers[reverse_bits_len((uint32_t)i, log_half)] = half_beta * gp[i];
     }
@@ -96,8 +95,7 @@ struct Pcs {
         size_t h = lde.height() >> fri.log_blowup, w = lde.width;
         int lg = log2_strict(h);
         uint32_t s = GEN, om = two_adic_generator(lg);
-        std::vector<uint32_t> xs(h);
-        { uint32_t x = s; for (size_t i = 0; i < h; i++) { xs[i] = x; x = mul(x, om); } }
+        std::vector<uint32_t> xs = geometric(s, om, h);
         std::vector<Ext5> den(h);
 #pragma omp parallel for schedule(static) if (h > 4096)
         for (long i = 0; i < (long)h; i++) den[i] = z - xs[i];
@@ -139,8 +137,9 @@ struct Pcs {
                 all.back().emplace_back();
                 // x for storage row i: g * omega^{bitrev(i)}
                 std::vector<uint32_t> xs(H);
-                { uint32_t om = two_adic_generator(lh), x = GEN; std::vector<uint32_t> nat(H); for (size_t i = 0; i < H; i++) { nat[i] = x; x = mul(x, om); }
-                  for (size_t i = 0; i < H; i++) xs[i] = nat[reverse_bits_len((uint32_t)i, lh)]; }
+                { std::vector<uint32_t> nat = geometric(GEN, two_adic_generator(lh), H);
+#pragma omp parallel for schedule(static) if (H > 8192)
+                  for (long i = 0; i < (long)H; i++) xs[i] = nat[reverse_bits_len((uint32_t)i, lh)]; }
                 std::vector<Ext5> apow(w);
                 { Ext5 a = Ext5::one(); for (size_t c = 0; c < w; c++) { apow[c] = a; a = a * alpha; } }
                 for (const Ext5& z : rd.points[mi]) {
@@ -180,7 +179,11 @@ struct Pcs {
             layer_trees.push_back(std::move(t));
             Ext5 beta = ch.sample_ext();
             current = fold_even_odd(current, beta);
-            if (!ro[lfh].empty()) for (size_t i = 0; i < current.size(); i++) current[i] += ro[lfh][i];
+            if (!ro[lfh].empty()) {
+                const std::vector<Ext5>& add = ro[lfh];
+#pragma omp parallel for schedule(static) if (current.size() > 8192)
+                for (long i = 0; i < (long)current.size(); i++) current[i] += add[i];
+            }
         }
         assert(current.size() == (1u << fri.log_blowup));
         for (auto& x : current) { assert(x == current[0]); (void)x; }
