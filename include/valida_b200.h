@@ -58,8 +58,15 @@ int32_t vgpu_set_challenger(vgpu_ctx* ctx, const uint32_t round_constants[480], 
 
 /* ---- device matrices (K12 staging: H2D + row-major -> column-major + repr conversion) ---------- */
 int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out);
+/* Split proof (multi-GPU section below): of a trace tall enough to be split a rank keeps ITS contiguous run of rows only;
+ * every rank passes the same host matrix.  Shorter traces, and any trace on a lone GPU, are uploaded whole. */
+int32_t vgpu_dmat_upload_rows(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out);
+/* Writes the rows this rank holds at their place in the caller's height x width row-major buffer. */
 int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint32_t* host_row_major_out);
+/* Logical dimensions (of the whole matrix, also for a shard). */
 int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width);
+/* The rows held here; returns 0 = whole matrix, 1 = row shard, 2 = column share. */
+int32_t vgpu_dmat_local_rows(const vgpu_dmat* m, uint64_t* row0, uint64_t* rows);
 void vgpu_dmat_free(vgpu_dmat* m);
 
 /* ---- p3-dft: TwoAdicSubgroupDft::dft_batch / idft_batch / coset_lde_batch ------------------------
@@ -154,19 +161,28 @@ void vgpu_free_bytes(uint8_t* p);
 /* Per-phase device time of the last vgpu_prove* call: names[i] (static strings) / ms[i]; returns the count. */
 uint32_t vgpu_last_prove_phases(const vgpu_ctx* ctx, const char** names, float* ms, uint32_t cap);
 
-/* ---- multi-GPU: one rank (process) per GPU of one box, NCCL over NVLink -----------------
- * After vgpu_comm_init every rank of the communicator must make the SAME sequence of library calls with
- * the SAME (replicated) inputs.  With sharding on (the default after init), vgpu_commit_batches* and the
- * FRI commit phase inside vgpu_prove* split their work: rank r transforms a contiguous share of every
- * matrix's columns (coset LDE), the shares are exchanged (broadcast per share, one NCCL group), each rank
- * hashes a contiguous 1/nranks range of the leaves and compresses the tree layers above that range, and one
- * grouped all-gather leaves every rank with all digest layers; the top log2(nranks) layers are computed
- * by every rank.  Results (roots, prover data, proof bytes) are identical on all ranks and identical to
- * the single-GPU ones.  nranks must be a power of two. */
+/* ---- multi-GPU: ONE proof split across the GPUs of one box ------------------------------------
+ * One rank per GPU, either a process per rank (vgpu_comm_init: NCCL for the small all-gathers, CUDA IPC for the peer
+ * pointers; what a torchrun launch uses) or a thread per rank inside one process (vgpu_comm_init_local; what a Rust host
+ * with a worker thread per GPU uses; several ranks may share a device).  After either, every rank must make the SAME
+ * sequence of library calls with the same arguments, each rank from its own thread / process.
+ * Data path with sharding on (the default after init): a trace tall enough (LDE height >= 4096 * nranks) is held as
+ * contiguous ROW shards (vgpu_dmat_upload_rows, vgpu_prove); a commit (1) hands every column to the rank that extends it,
+ * (2) extends the column shares (coset LDE) and stores each rank's contiguous run of the committed (bit-reversed) rows into
+ * that rank's shard — kernels storing through peer pointers over NVLink, the ONE bulk exchange of a commit — and (3) hashes
+ * leaves and builds the sub-tree of its own rows; the nranks x 32-byte sub-roots are all-gathered and the top log2(nranks)
+ * layers computed by every rank.  LogUp traces, the quotient sweep (its "next" rows are one peer's shard, read over
+ * NVLink), inverse denominators, reduced openings and the FRI folds / layer trees work on a rank's own rows; what crosses
+ * ranks afterwards are per-rank partial sums, sub-roots and the 40 opened rows.  Shorter matrices are computed whole by
+ * every rank.  Roots and proof bytes are identical on all ranks and identical to the single-GPU ones.
+ * nranks must be a power of two (<= 16). */
 #define VGPU_COMM_ID_BYTES 128
 int32_t vgpu_comm_unique_id(uint8_t out[VGPU_COMM_ID_BYTES]);                 /* rank 0 creates, the caller distributes */
 int32_t vgpu_comm_init(vgpu_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t unique_id[VGPU_COMM_ID_BYTES]);
+int32_t vgpu_comm_init_local(vgpu_ctx* const* ctxs, int32_t nranks);          /* ctxs[i] becomes rank i; call once, before the rank threads start */
 int32_t vgpu_comm_set_sharding(vgpu_ctx* ctx, int32_t on);                    /* 0: behave as a lone GPU (independent replicas) */
+/* Collectives since the last reset: [0] barriers, [1] all-gathers, [2] peer-store exchanges (calls; bytes sent to peers). */
+void vgpu_comm_stats(vgpu_ctx* ctx, uint32_t calls[3], double bytes[3], int32_t reset);
 void vgpu_shard_range(uint64_t total, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* end);   /* the split used for columns */
 void vgpu_tree_share(uint64_t len, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* count, int32_t* split); /* ... for tree layers */
 

@@ -25,6 +25,8 @@ from .api import (  # noqa: F401
     lib_path,
     run_program,
     comm_unique_id,
+    comm_init_local,
+    run_ranks,
     shard_range,
     tree_share,
 )

@@ -45,6 +45,8 @@ def _load():
         "vgpu_ctx_set_kernel_timing": (C.c_int32, [vp, C.c_int32]),
         "vgpu_ctx_kernel_stats": (C.c_uint32, [vp, C.POINTER(C.c_char_p), u32p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_uint32]),
         "vgpu_dmat_upload": (C.c_int32, [vp, C.POINTER(_Matrix), C.c_int32, C.POINTER(vp)]),
+        "vgpu_dmat_upload_rows": (C.c_int32, [vp, C.POINTER(_Matrix), C.c_int32, C.POINTER(vp)]),
+        "vgpu_dmat_local_rows": (C.c_int32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "vgpu_dmat_download": (C.c_int32, [vp, vp, C.c_int32, u32p]),
         "vgpu_dmat_dims": (C.c_int32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "vgpu_dmat_free": (None, [vp]),
@@ -64,6 +66,8 @@ def _load():
         "vgpu_challenger_sample_ext": (C.c_int32, [vp, u32p]),
         "vgpu_comm_unique_id": (C.c_int32, [C.c_char_p]),
         "vgpu_comm_init": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_char_p]),
+        "vgpu_comm_init_local": (C.c_int32, [C.POINTER(vp), C.c_int32]),
+        "vgpu_comm_stats": (None, [vp, u32p, C.POINTER(C.c_double), C.c_int32]),
         "vgpu_comm_set_sharding": (C.c_int32, [vp, C.c_int32]),
         "vgpu_shard_range": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
         "vgpu_tree_share": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_int32)]),
@@ -155,8 +159,22 @@ class Context:
         self.comm_init(dist.get_rank(), dist.get_world_size(), ids[0])
 
     def set_sharding(self, on):
-        """False: this rank works alone (independent replicas); True: commits are split across the ranks."""
+        """False: this rank works alone (independent replicas); True: ONE proof is split across the ranks."""
         self.check(lib().vgpu_comm_set_sharding(self._h, 1 if on else 0))
+
+    def comm_stats(self, reset=True):
+        """Collectives since the last reset: {name: (calls, bytes sent to peers)} for barriers, all-gathers, peer-store exchanges."""
+        calls = (C.c_uint32 * 3)(); by = (C.c_double * 3)()
+        lib().vgpu_comm_stats(self._h, calls, by, 1 if reset else 0)
+        return {n: (int(calls[i]), float(by[i])) for i, n in enumerate(("barrier", "allgather", "exchange"))}
+
+    def upload_rows(self, row_major, repr=REPR_CANONICAL):
+        """Split proof: of a trace tall enough to be split, keep this rank's run of rows only (otherwise like upload)."""
+        a = _as_u32(row_major)
+        m = _mat(a)
+        out = C.c_void_p()
+        self.check(lib().vgpu_dmat_upload_rows(self._h, C.byref(m), repr, C.byref(out)))
+        return DeviceMatrix(self, out)
 
     def upload(self, row_major, repr=REPR_CANONICAL):
         """RowMajorMatrix<Val> (numpy h x w uint32) -> DeviceMatrix."""
@@ -370,6 +388,42 @@ def prove_machine(config, traces, device_resident=None):
 
 
 COMM_ID_BYTES = 128
+
+
+def comm_init_local(contexts):
+    """One process, one worker THREAD per context (a Rust host with a thread per GPU): contexts[i] becomes rank i of a
+    split proof.  Afterwards every rank's calls must come from its own thread — the collectives wait for all ranks.
+    Several contexts may share a device (how the split-proof tests run on a one-GPU box)."""
+    n = len(contexts)
+    arr = (C.c_void_p * n)(*[c._h for c in contexts])
+    rc = lib().vgpu_comm_init_local(arr, n)
+    if rc != 0:
+        raise VgpuError(lib().vgpu_last_error(contexts[0]._h).decode())
+    for i, c in enumerate(contexts):
+        c.rank, c.world_size = i, n
+
+
+def run_ranks(fn, contexts):
+    """Run fn(rank, ctx) on one thread per context and return the results in rank order (re-raises the first failure)."""
+    import threading
+
+    out, err = [None] * len(contexts), [None] * len(contexts)
+
+    def work(i):
+        try:
+            out[i] = fn(i, contexts[i])
+        except BaseException as e:   # noqa: BLE001
+            err[i] = e
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(contexts))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 def comm_unique_id():

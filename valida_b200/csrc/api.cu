@@ -44,7 +44,27 @@ int32_t vg_dmat_alloc(vgpu_ctx* ctx, uint64_t h, uint64_t w, vgpu_dmat** out) {
     vgpu_dmat* m = new (std::nothrow) vgpu_dmat();
     if (!m) VG_FAIL(ctx, "out of host memory");
     m->ctx = ctx; m->h = h; m->w = w; m->col_stride = h; m->owns = true;
+    m->gh = h; m->gw = w;
     int32_t rc = vg_alloc(ctx, (void**)&m->d, h * w * 4);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return 0;
+}
+
+// The local part of a gh x gw matrix: VG_FULL = all of it; VG_ROWS = this rank's run of gh / comm_size stored rows;
+// VG_COLS = this rank's column share (vg_shard_range of gw).  symm: taken from the symmetric heap (peers store into it).
+int32_t vg_dmat_alloc_dist(vgpu_ctx* ctx, int dist, uint64_t gh, uint64_t gw, bool symm, vgpu_dmat** out) {
+    vgpu_dmat* m = new (std::nothrow) vgpu_dmat();
+    if (!m) VG_FAIL(ctx, "out of host memory");
+    const uint64_t G = (uint64_t)ctx->comm_size, r = (uint64_t)ctx->comm_rank;
+    m->ctx = ctx; m->gh = gh; m->gw = gw; m->dist = dist; m->owns = true; m->symm = symm;
+    m->h = gh; m->w = gw;
+    if (dist == VG_ROWS) { m->h = gh / G; m->row0 = r * m->h; }
+    else if (dist == VG_COLS) { uint64_t a, b; vg_shard_range(gw, (int)G, (int)r, &a, &b); m->col0 = a; m->w = b - a; }
+    m->col_stride = m->h;
+    size_t words = m->h * m->w;
+    if (dist == VG_COLS) words = m->h * ((gw + G - 1) / G);       // the same size on every rank
+    int32_t rc = symm ? vg_symm_alloc(ctx, (void**)&m->d, words * 4) : vg_alloc(ctx, (void**)&m->d, words * 4);
     if (rc) { delete m; return rc; }
     *out = m;
     return 0;
@@ -83,6 +103,14 @@ int32_t vg_get_shift_table(vgpu_ctx* ctx, uint32_t shift_canonical, uint32_t sca
 }
 
 void vg_host_state_free(vgpu_ctx* ctx);
+
+// Every entry point runs on the context's device whatever the calling thread's current device is (a thread per GPU in
+// one process, or torch having switched devices).
+int32_t vg_enter(vgpu_ctx* ctx) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) VG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return 0;
+}
 
 extern "C" {
 
@@ -140,7 +168,7 @@ uint64_t vgpu_ctx_launch_count(const vgpu_ctx* ctx) { return ctx->launches; }
 
 int32_t vgpu_ctx_set_kernel_timing(vgpu_ctx* ctx, int32_t on) { ctx->ktiming = on != 0; return 0; }
 static const char* KCLASS_NAMES[KC_COUNT] = {"ntt_pass_kernel", "leaf_hash_kernel", "compress_layer_kernel", "fri_leaf_hash_kernel", "transpose (rm<->cm)",
-                                             "perm trace kernels", "quotient_kernel", "inverse denominators", "bary_kernel", "reduced_opening_kernel", "fri_fold_kernel", "other"};
+                                             "perm trace kernels", "quotient_kernel", "inverse denominators", "bary_kernel", "reduced_opening_kernel", "fri_fold_kernel", "peer-store exchange", "other"};
 uint32_t vgpu_ctx_kernel_stats(vgpu_ctx* ctx, const char** names, uint32_t* launches, float* ms, double* bytes, uint32_t cap) {
     cudaStreamSynchronize(ctx->stream);
     uint32_t n[KC_COUNT] = {0}; float t[KC_COUNT] = {0}; double b[KC_COUNT] = {0};
@@ -158,6 +186,7 @@ uint32_t vgpu_ctx_kernel_stats(vgpu_ctx* ctx, const char** names, uint32_t* laun
 // ---- device matrices -----------------------------------------------------------------------------
 int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out) {
     if (!host || !out) VG_FAIL(ctx, "dmat_upload: null argument");
+    VG_TRY(vg_enter(ctx));
     vgpu_dmat* m = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, host->height, host->width, &m));
     int32_t rc = vg_upload_rowmajor(ctx, host->data, host->height, host->width, repr, m);
@@ -165,9 +194,27 @@ int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, v
     *out = m;
     return 0;
 }
+// Split proof: a rank keeps only ITS run of rows of a trace tall enough to be split (every rank passes the same host
+// matrix, or at least its own rows of it); shorter traces are uploaded whole.  The handle reports the logical dimensions.
+int32_t vgpu_dmat_upload_rows(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out) {
+    if (!host || !out) VG_FAIL(ctx, "dmat_upload_rows: null argument");
+    if (!vg_split_rows(ctx, 2 * host->height)) return vgpu_dmat_upload(ctx, host, repr, out);
+    VG_TRY(vg_enter(ctx));
+    vgpu_dmat* m = nullptr;
+    VG_TRY(vg_dmat_alloc_dist(ctx, VG_ROWS, host->height, host->width, false, &m));
+    int32_t rc = vg_upload_rowmajor(ctx, host->data + m->row0 * host->width, m->h, m->w, repr, m);
+    if (rc) { vgpu_dmat_free(m); return rc; }
+    *out = m;
+    return 0;
+}
+// Writes the rows this rank holds (all of them unless the matrix is a row shard) at their place in the caller's
+// gh x gw row-major buffer.
 int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint32_t* host_row_major_out) {
+    VG_TRY(vg_enter(ctx));
     VG_TRY(vg_dmat_materialize(ctx, m));
-    VG_TRY(vg_download_rowmajor(ctx, m, repr, host_row_major_out));
+    if (m->dist == VG_COLS) VG_FAIL(ctx, "dmat_download: column shares are internal to a commit");
+    if (m->dist == VG_ROWS && m->bitrev_rows) VG_FAIL(ctx, "dmat_download: a bit-reversed row shard has no contiguous natural-order image");
+    VG_TRY(vg_download_rowmajor(ctx, m, repr, host_row_major_out + m->row0 * m->gw));
     if (m->bitrev_rows && m->h > 1) {   // present the logical (natural) row order to the caller
         int lg = 0; while ((1ull << lg) < m->h) lg++;
         std::vector<uint32_t> tmp(m->w);
@@ -181,7 +228,8 @@ int32_t vgpu_dmat_download(vgpu_ctx* ctx, const vgpu_dmat* m, int32_t repr, uint
     }
     return 0;
 }
-int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width) { *height = m->h; *width = m->w; return 0; }
+int32_t vgpu_dmat_dims(const vgpu_dmat* m, uint64_t* height, uint64_t* width) { *height = m->gh; *width = m->gw; return 0; }
+int32_t vgpu_dmat_local_rows(const vgpu_dmat* m, uint64_t* row0, uint64_t* rows) { *row0 = m->row0; *rows = m->h; return m->dist; }
 void vgpu_dmat_free(vgpu_dmat* m) {
     if (!m) return;
     if (m->pend_stage) {   // an upload that was never consumed: let the copy finish, then release
@@ -189,12 +237,14 @@ void vgpu_dmat_free(vgpu_dmat* m) {
         vg_free(m->ctx, m->pend_stage);
         m->ctx->event_pool.push_back(m->pend_ev);
     }
-    if (m->owns) vg_free(m->ctx, m->d);
+    if (m->owns) { if (m->symm) vg_symm_free(m->ctx, m->d); else vg_free(m->ctx, m->d); }
     delete m;
 }
 
 // ---- NTT / LDE -------------------------------------------------------------------------------------
 int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
+    VG_TRY(vg_enter(ctx));
+    if (m->dist != VG_FULL) VG_FAIL(ctx, "ntt_batch: the matrix is a shard of a split proof");
     int log_n = 0;
     while ((1ull << log_n) < m->h) log_n++;
     if ((1ull << log_n) != m->h) VG_FAIL(ctx, "ntt_batch: height %llu is not a power of two", (unsigned long long)m->h);
@@ -211,6 +261,8 @@ int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
 
 int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_blowup, uint32_t shift_canonical, int32_t bit_reversed, vgpu_dmat** out) {
     if (log_blowup != 1) VG_FAIL(ctx, "coset_lde: only log_blowup = 1 (FriConfig of basic/src/bin/valida.rs:385-390) is built");
+    VG_TRY(vg_enter(ctx));
+    if (in->dist != VG_FULL) VG_FAIL(ctx, "coset_lde: the matrix is a shard of a split proof");
     VG_TRY(vg_dmat_materialize(ctx, in));
     vgpu_dmat* o = nullptr;
     VG_TRY(vg_dmat_alloc(ctx, in->h * 2, in->w, &o));
@@ -231,53 +283,86 @@ int32_t vgpu_ntt_batch_host(vgpu_ctx* ctx, uint32_t* row_major, uint64_t height,
 }
 
 // ---- commit ------------------------------------------------------------------------------------------
+// TwoAdicFriPcs::commit_shifted_batches per matrix: shift = generator / coset_shift_i; LDE; bit-reversed rows.
+static uint32_t lde_shift_of(const uint32_t* coset_shifts_or_null, uint32_t i) {
+    const uint32_t cs = coset_shifts_or_null ? coset_shifts_or_null[i] : 1;
+    return bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
+}
+
+// Split proof: the tall matrices of a commit.  (1) a matrix that arrives as row shards is handed to the ranks that extend
+// its columns; (2) every rank extends its column share and stores, through peer pointers, each rank's run of the committed
+// rows into that rank's shard.  After the closing barrier pd->ldes[i] holds rows [rank * H/G, (rank+1) * H/G) of all columns.
+static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat* const* mats, const std::vector<size_t>& tall, const uint32_t* coset_shifts_or_null) {
+    const uint64_t G = (uint64_t)ctx->comm_size;
+    size_t need = 0;
+    for (size_t i : tall) {
+        need += vg_symm_round((2 * mats[i]->gh / G) * mats[i]->gw * 4);
+        if (mats[i]->dist == VG_ROWS) need += vg_symm_round(mats[i]->gh * ((mats[i]->gw + G - 1) / G) * 4);
+    }
+    VG_TRY(vg_symm_reserve(ctx, need));
+    std::vector<vgpu_dmat*> cols(mats ? tall.size() : 0, nullptr);
+    struct Guard { std::vector<vgpu_dmat*>& v; ~Guard() { for (auto* m : v) vgpu_dmat_free(m); } } guard{cols};
+    bool moved = false;
+    for (size_t k = 0; k < tall.size(); k++) {
+        const vgpu_dmat* m = mats[tall[k]];
+        VG_TRY(vg_dmat_materialize(ctx, m));
+        if (m->dist != VG_ROWS) continue;
+        VG_TRY(vg_dmat_alloc_dist(ctx, VG_COLS, m->gh, m->gw, true, &cols[k]));
+        VG_TRY(vg_exchange_rows_to_cols(ctx, m, cols[k]->d, (m->gw + G - 1) / G));
+        moved = true;
+    }
+    if (moved) VG_TRY(vg_comm_barrier(ctx));
+    for (size_t k = 0; k < tall.size(); k++) {
+        const size_t i = tall[k];
+        const vgpu_dmat* m = mats[i];
+        const uint64_t h = m->gh, H = 2 * h;
+        uint64_t c0, c1;
+        vg_shard_range(m->gw, (int)G, ctx->comm_rank, &c0, &c1);
+        VG_TRY(vg_dmat_alloc_dist(ctx, VG_ROWS, H, m->gw, true, &pd->ldes[i]));
+        pd->ldes[i]->bitrev_rows = false;        // committed order IS the stored order of an LDE (rows at reverse_bits)
+        if (c1 > c0) {
+            const uint32_t* src; uint64_t scs;
+            if (m->dist == VG_ROWS) { src = cols[k]->d; scs = h; }
+            else if (m->dist == VG_COLS) { src = m->d; scs = m->col_stride; }
+            else { src = m->d + c0 * m->col_stride; scs = m->col_stride; }
+            uint32_t* ext = nullptr;
+            VG_TRY(vg_alloc(ctx, (void**)&ext, H * (c1 - c0) * 4));
+            int32_t rc = vg_coset_lde(ctx, src, scs, h, c1 - c0, lde_shift_of(coset_shifts_or_null, (uint32_t)i), ext, H, true, m->bitrev_rows);
+            if (rc == 0) rc = vg_exchange_cols_to_rows(ctx, ext, H, c0, c1, pd->ldes[i]);
+            vg_free(ctx, ext);
+            if (rc) return rc;
+        }
+    }
+    return vg_comm_barrier(ctx);   // also orders the release of the column buffers (guard) behind every peer's stores
+}
+
 int32_t vgpu_commit_batches(vgpu_ctx* ctx, const vgpu_dmat* const* mats, uint32_t n, const uint32_t* coset_shifts_or_null,
                             uint32_t digest_out[8], vgpu_prover_data** out) {
+    VG_TRY(vg_enter(ctx));
     vgpu_prover_data* pd = new (std::nothrow) vgpu_prover_data();
     if (!pd) VG_FAIL(ctx, "out of host memory");
     pd->ctx = ctx;
-    const bool sharded = vg_sharded(ctx);
     pd->ldes.assign(n, nullptr);
     std::vector<uint64_t> heights(n);
+    std::vector<size_t> tall;
     for (uint32_t i = 0; i < n; i++) {
         if (!mats[i]) { vgpu_prover_data_free(pd); VG_FAIL(ctx, "commit: matrix %u is null", i); }
-        heights[i] = mats[i]->h * 2;
+        heights[i] = mats[i]->gh * 2;
+        if (vg_split_rows(ctx, heights[i])) tall.push_back(i);
+        else if (mats[i]->dist != VG_FULL) { vgpu_prover_data_free(pd); VG_FAIL(ctx, "commit: matrix %u is a shard but too short to be split", i); }
     }
-    // One height group at a time, when the tree reaches that height: TwoAdicFriPcs::commit_shifted_batches for the group
-    // (shift = generator / coset_shift_i; LDE; bit-reversed rows).  A matrix whose upload is still in flight is waited
-    // for here, not earlier.
+    int32_t rc = tall.empty() ? 0 : extend_split(ctx, pd, mats, tall, coset_shifts_or_null);
+    // The other matrices one height group at a time, when the tree reaches that height; a matrix whose upload is still in
+    // flight is waited for here, not earlier.  (Split proof: short matrices are extended, whole, by every rank.)
     auto extend_group = [&](const std::vector<size_t>& group) -> int32_t {
         for (size_t i : group) {
+            if (pd->ldes[i]) continue;
             VG_TRY(vg_dmat_materialize(ctx, mats[i]));
-            uint32_t cs = coset_shifts_or_null ? coset_shifts_or_null[i] : 1;
-            uint32_t shift = bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
-            if (!sharded) {
-                VG_TRY(vgpu_coset_lde_batch(ctx, mats[i], 1, shift, 1, &pd->ldes[i]));
-            } else {
-                // this rank extends only its share of the columns; the other shares arrive in the exchange below
-                uint64_t c0, c1;
-                vg_shard_range(mats[i]->w, ctx->comm_size, ctx->comm_rank, &c0, &c1);
-                VG_TRY(vg_dmat_alloc(ctx, mats[i]->h * 2, mats[i]->w, &pd->ldes[i]));
-                if (c1 > c0)
-                    VG_TRY(vg_coset_lde(ctx, mats[i]->d + c0 * mats[i]->col_stride, mats[i]->col_stride, mats[i]->h, c1 - c0, shift,
-                                        pd->ldes[i]->d + c0 * pd->ldes[i]->col_stride, pd->ldes[i]->col_stride, true, mats[i]->bitrev_rows));
-            }
-        }
-        if (sharded) {
-            // exchange of the column shares: one NCCL group per height group, a broadcast per (matrix, owner) — shares
-            // are contiguous runs of whole columns in the column-major LDE
-            VG_TRY(vg_comm_group_begin(ctx));
-            for (size_t i : group)
-                for (int r = 0; r < ctx->comm_size; r++) {
-                    uint64_t c0, c1;
-                    vg_shard_range(pd->ldes[i]->w, ctx->comm_size, r, &c0, &c1);
-                    VG_TRY(vg_comm_bcast(ctx, pd->ldes[i]->d + c0 * pd->ldes[i]->col_stride, (c1 - c0) * pd->ldes[i]->col_stride, r));
-                }
-            VG_TRY(vg_comm_group_end(ctx));
+            VG_TRY(vgpu_coset_lde_batch(ctx, mats[i], 1, lde_shift_of(coset_shifts_or_null, (uint32_t)i), 1, &pd->ldes[i]));
         }
         return 0;
     };
-    int32_t rc = vg_merkle_build(ctx, pd, heights, extend_group);
+    if (rc == 0) rc = vg_merkle_build(ctx, pd, heights, extend_group);
     if (rc) { vgpu_prover_data_free(pd); return rc; }
     if (digest_out) std::memcpy(digest_out, pd->root, 32);
     *out = pd;
@@ -288,7 +373,7 @@ int32_t vgpu_commit_batches_host(vgpu_ctx* ctx, const vgpu_matrix* mats, uint32_
                                  uint32_t digest_out[8], vgpu_prover_data** out) {
     std::vector<vgpu_dmat*> dm(n, nullptr);
     int32_t rc = 0;
-    for (uint32_t i = 0; i < n && rc == 0; i++) rc = vgpu_dmat_upload(ctx, &mats[i], repr, &dm[i]);
+    for (uint32_t i = 0; i < n && rc == 0; i++) rc = vgpu_dmat_upload_rows(ctx, &mats[i], repr, &dm[i]);   // a split proof uploads each rank's rows only
     if (rc == 0) rc = vgpu_commit_batches(ctx, dm.data(), n, coset_shifts_or_null, digest_out, out);
     for (auto* m : dm) vgpu_dmat_free(m);
     return rc;
@@ -302,7 +387,7 @@ int32_t vgpu_prover_data_lde(const vgpu_prover_data* pd, uint32_t i, const vgpu_
 void vgpu_prover_data_free(vgpu_prover_data* pd) {
     if (!pd) return;
     for (auto* m : pd->ldes) vgpu_dmat_free(m);
-    vg_free(pd->ctx, pd->digests);
+    vg_tree_free(pd->ctx, &pd->tree);
     delete pd;
 }
 

@@ -37,12 +37,24 @@ struct OpeningH {
 };
 struct OpenRound { const vgpu_prover_data* pd; std::vector<std::vector<E5>> points; };
 
-struct FriLayer {
-    uint32_t* values = nullptr;   // limb-major ext5 vector of length n
-    uint64_t n = 0;
-    uint32_t* digests = nullptr;
-    std::vector<uint32_t*> layer_ptr; std::vector<uint64_t> layer_len;
+// An ext5 vector over the rows of one LDE height (reduced openings, inverse denominators, FRI layers): limb-major.
+// Split proof: a vector of a height whose matrices are row shards holds this rank's run [begin, begin + count) only.
+struct RowVec {
+    uint32_t* d = nullptr;
+    uint64_t n = 0, begin = 0, count = 0;      // whole length; stored run (limb stride = count)
+    bool shard() const { return count != n; }
+    const uint32_t* at(const vgpu_ctx* ctx, int limb, uint64_t i) const {   // null: another rank reports this element (see VgTree::node)
+        if (!shard()) return ctx->comm_rank == 0 || !vg_sharded(ctx) ? d + (uint64_t)limb * count + i : nullptr;
+        return i >= begin && i < begin + count ? d + (uint64_t)limb * count + (i - begin) : nullptr;
+    }
 };
+int32_t rowvec_alloc(vgpu_ctx* ctx, uint64_t n, RowVec* v) {
+    v->n = n;
+    if (vg_split_rows(ctx, n)) { v->count = n / ctx->comm_size; v->begin = v->count * ctx->comm_rank; } else { v->count = n; v->begin = 0; }
+    return vg_alloc(ctx, (void**)&v->d, 5 * v->count * 4);
+}
+
+struct FriLayer { RowVec values; VgTree tree; };
 
 struct PointKey {
     uint32_t log_H; uint32_t c[5];
@@ -51,23 +63,34 @@ struct PointKey {
 
 int log2u(uint64_t n) { int l = 0; while ((1ull << l) < n) l++; return l; }
 
+// Device buffers of open_multi_batches, released on every exit path.
+struct OpenScratch {
+    vgpu_ctx* ctx;
+    std::map<PointKey, uint32_t*> invden;       // (height, point) -> 1/(x - z) over this rank's rows of the coset
+    RowVec ro[32];
+    uint32_t* d_sums = nullptr;
+    RowVec current;
+    std::vector<FriLayer> layers;
+    explicit OpenScratch(vgpu_ctx* c) : ctx(c) {}
+    void drop_invden() { for (auto& kv : invden) vg_free(ctx, kv.second); invden.clear(); vg_free(ctx, d_sums); d_sums = nullptr; }
+    ~OpenScratch() {
+        drop_invden();
+        for (auto& r : ro) vg_free(ctx, r.d);
+        vg_free(ctx, current.d);
+        for (auto& L : layers) { vg_free(ctx, L.values.d); vg_tree_free(ctx, &L.tree); }
+    }
+};
+
 int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, vgh::Challenger& ch, OpeningH* out) {
     const E5 alpha = ch.sample_ext();
     // alpha^c table (host; the reduced-opening kernel takes its powers through the kernel parameters)
     uint32_t max_w = 1;
-    for (auto& r : rounds) for (auto* m : r.pd->ldes) max_w = std::max<uint32_t>(max_w, (uint32_t)m->w);
+    for (auto& r : rounds) for (auto* m : r.pd->ldes) max_w = std::max<uint32_t>(max_w, (uint32_t)m->gw);
     std::vector<E5> apow(max_w + 1);
     { E5 a = bb::e5_one(); for (uint32_t c = 0; c <= max_w; c++) { apow[c] = a; a = bb::e5_mul(a, alpha); } }
 
-    std::map<PointKey, uint32_t*> invden;       // (height, point) -> 1/(x - z) over the whole coset
-    uint32_t* ro[32] = {nullptr};
+    OpenScratch S(ctx);
     uint64_t num_reduced[32] = {0};
-    uint32_t* d_sums = nullptr;
-    auto cleanup = [&]() {
-        for (auto& kv : invden) vg_free(ctx, kv.second);
-        invden.clear();
-        vg_free(ctx, d_sums); d_sums = nullptr;
-    };
     // Pass 1 — enqueue, for every matrix, the inverse denominators of its points and the column sums behind p_c(z_q); nothing
     // here waits for the device.  One copy brings the sums of all matrices back.
     struct Job { const vgpu_dmat* lde; uint32_t log_H, w; const std::vector<E5>* pts; const uint32_t* dens[2]; size_t sums_at; };
@@ -76,32 +99,34 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
     for (const OpenRound& rd : rounds)
         for (size_t mi = 0; mi < rd.pd->ldes.size(); mi++) {
             Job j{};
-            j.lde = rd.pd->ldes[mi]; j.log_H = (uint32_t)log2u(j.lde->h); j.w = (uint32_t)j.lde->w; j.pts = &rd.points[mi];
+            j.lde = rd.pd->ldes[mi]; j.log_H = (uint32_t)log2u(j.lde->gh); j.w = (uint32_t)j.lde->gw; j.pts = &rd.points[mi];
             if (j.pts->empty() || j.pts->size() > 2) VG_FAIL(ctx, "open: 1 or 2 points per matrix are supported");
+            if ((j.lde->dist == VG_ROWS) != vg_split_rows(ctx, j.lde->gh)) VG_FAIL(ctx, "open: a committed matrix is not distributed as its height demands");
             j.sums_at = sums_words; sums_words += vg_eval_columns_words(j.w);
             jobs.push_back(j);
         }
-    VG_TRY(vg_alloc(ctx, (void**)&d_sums, sums_words * 4));
+    VG_TRY(vg_alloc(ctx, (void**)&S.d_sums, sums_words * 4));
     for (Job& j : jobs) {
-        if (!ro[j.log_H]) {
-            VG_TRY(vg_alloc(ctx, (void**)&ro[j.log_H], 5 * j.lde->h * 4));
-            VG_CUDA(ctx, cudaMemsetAsync(ro[j.log_H], 0, 5 * j.lde->h * 4, ctx->stream));
+        RowVec& R = S.ro[j.log_H];
+        if (!R.d) {
+            VG_TRY(rowvec_alloc(ctx, j.lde->gh, &R));
+            VG_CUDA(ctx, cudaMemsetAsync(R.d, 0, 5 * R.count * 4, ctx->stream));
         }
         for (size_t q = 0; q < j.pts->size(); q++) {
             PointKey key; key.log_H = j.log_H; std::memcpy(key.c, (*j.pts)[q].c, 20);
-            auto it = invden.find(key);
-            if (it == invden.end()) {
+            auto it = S.invden.find(key);
+            if (it == S.invden.end()) {
                 uint32_t* buf = nullptr;
-                VG_TRY(vg_alloc(ctx, (void**)&buf, 5 * j.lde->h * 4));
-                VG_TRY(vg_inverse_denominators(ctx, j.log_H, (*j.pts)[q], buf));
-                it = invden.emplace(key, buf).first;
+                VG_TRY(vg_alloc(ctx, (void**)&buf, 5 * R.count * 4));
+                it = S.invden.emplace(key, buf).first;
+                VG_TRY(vg_inverse_denominators(ctx, j.log_H, (*j.pts)[q], R.begin, R.count, buf));
             }
             j.dens[q] = it->second;
         }
-        VG_TRY(vg_eval_columns_enqueue(ctx, j.lde, (uint32_t)j.pts->size(), j.dens, d_sums + j.sums_at));
+        VG_TRY(vg_eval_columns_enqueue(ctx, j.lde, (uint32_t)j.pts->size(), j.dens, R.count, S.d_sums + j.sums_at));
     }
     std::vector<uint32_t> sums(sums_words);
-    VG_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_sums, sums_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VG_CUDA(ctx, cudaMemcpyAsync(sums.data(), S.d_sums, sums_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // Pass 2 — opened values on the host, then the reduced openings of every matrix (again without waiting)
     out->values.clear();
@@ -114,7 +139,7 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
                 const Job& j = jobs[ji];
                 const uint32_t w = j.w, np = (uint32_t)j.pts->size();
                 std::vector<E5> ys;
-                vg_eval_columns_finish(sums.data() + j.sums_at, j.lde->h, w, np, j.pts->data(), &ys);
+                vg_eval_columns_finish(sums.data() + j.sums_at, j.lde->gh, w, np, j.pts->data(), &ys);
                 E5 sum_y[2];
                 out->values.back().emplace_back();
                 for (uint32_t q = 0; q < np; q++) {
@@ -128,73 +153,82 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
                 const E5 a_off = bb::e5_pow(alpha, num_reduced[j.log_H]);
                 num_reduced[j.log_H] += (uint64_t)w * np;
                 for (uint32_t c = 0; c < w; c++) apow_off[c] = bb::e5_mul(a_off, apow[c]);
-                VG_TRY(vg_reduced_opening_accumulate(ctx, j.lde, apow_off.data(), apow[w], np, j.dens, sum_y, ro[j.log_H]));
+                VG_TRY(vg_reduced_opening_accumulate(ctx, j.lde, apow_off.data(), apow[w], np, j.dens, S.ro[j.log_H].count, sum_y, S.ro[j.log_H].d));
             }
         }
     }
-    cleanup();
+    S.drop_invden();
 
     // ---- p3-fri prove: commit phase --------------------------------------------------------------
+    // Split proof: while a layer is long enough it stays in row shards — a fold pairs neighbours (2i, 2i+1), so a rank folds its
+    // own run, hashes its own leaves and sub-tree, and only the sub-roots meet; the first layer too short to split is
+    // all-gathered once and folded by every rank from there on.
     int log_max = 31;
-    while (log_max >= 0 && !ro[log_max]) log_max--;
+    while (log_max >= 0 && !S.ro[log_max].d) log_max--;
     if (log_max < LOG_BLOWUP) VG_FAIL(ctx, "open: nothing to open");
-    for (int lg = 0; lg <= log_max; lg++) if (ro[lg]) VG_TRY(vg_reduced_openings_complete(ctx, ro[lg], 1ull << lg));
-    std::vector<FriLayer> layers;
-    uint32_t* current = ro[log_max];
-    uint64_t cur_n = 1ull << log_max;
-    ro[log_max] = nullptr;
+    S.current = S.ro[log_max];
+    S.ro[log_max] = RowVec();
     for (int lfh = log_max - 1; lfh >= LOG_BLOWUP; lfh--) {
-        FriLayer L;
-        L.values = current; L.n = cur_n;
-        uint64_t npairs = cur_n / 2;
-        VG_TRY(vg_alloc(ctx, (void**)&L.digests, 2 * npairs * 32));
+        S.layers.emplace_back();
+        FriLayer& L = S.layers.back();
+        L.values = S.current; S.current = RowVec();
+        const RowVec& cur = L.values;
+        const uint64_t npairs = cur.n / 2;
         Digest root;
-        VG_TRY(vg_fri_layer_commit(ctx, current, cur_n, npairs, L.digests, &L.layer_ptr, &L.layer_len, root.data()));
+        VG_TRY(vg_fri_layer_commit(ctx, cur.d, cur.count, npairs, cur.shard(), &L.tree, root.data()));
         ch.observe_digest_canonical(root.data());
         out->fri.commit_phase_commits.push_back(root);
         E5 beta = ch.sample_ext();
-        uint32_t* next = nullptr;
-        VG_TRY(vg_alloc(ctx, (void**)&next, 5 * npairs * 4));
-        VG_TRY(vg_fri_fold(ctx, current, cur_n, beta, ro[lfh], next));
-        if (ro[lfh]) { vg_free(ctx, ro[lfh]); ro[lfh] = nullptr; }
-        layers.push_back(std::move(L));
-        current = next; cur_n = npairs;
+        RowVec next;
+        VG_TRY(rowvec_alloc(ctx, npairs, &next));
+        S.current = next;
+        const RowVec& add = S.ro[lfh];
+        if (add.d && add.shard() != next.shard()) VG_FAIL(ctx, "open: reduced openings and FRI layer of height 2^%d are distributed differently", lfh);
+        const uint64_t i0 = cur.shard() ? cur.begin / 2 : 0, cnt = cur.count / 2;      // outputs folded here
+        VG_TRY(vg_fri_fold(ctx, cur.d, cur.count, cur.n, i0, cnt, beta, add.d ? add.d - add.begin : nullptr, add.count, next.d - next.begin, next.count));
+        if (cur.shard() && !next.shard()) {   // every rank folded its run into the whole-length buffer: complete it
+            VG_TRY(vg_comm_group_begin(ctx));
+            for (int l = 0; l < 5; l++) VG_TRY(vg_comm_allgather_inplace(ctx, next.d + (uint64_t)l * next.count, cnt));
+            VG_TRY(vg_comm_group_end(ctx));
+        }
+        if (S.ro[lfh].d) { vg_free(ctx, S.ro[lfh].d); S.ro[lfh] = RowVec(); }
     }
-    for (int i = 0; i < 32; i++) if (ro[i]) { vg_free(ctx, ro[i]); ro[i] = nullptr; }
     {
-        std::vector<uint32_t> fin(5 * cur_n);
-        VG_CUDA(ctx, cudaMemcpyAsync(fin.data(), current, fin.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        const RowVec& cur = S.current;
+        if (cur.shard()) VG_FAIL(ctx, "open: the final FRI layer is still distributed");
+        std::vector<uint32_t> fin(5 * cur.n);
+        VG_CUDA(ctx, cudaMemcpyAsync(fin.data(), cur.d, fin.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
         VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        vg_free(ctx, current);
         E5 f0;
-        for (int l = 0; l < 5; l++) f0.c[l] = fin[l * cur_n];
-        for (uint64_t i = 1; i < cur_n; i++)
+        for (int l = 0; l < 5; l++) f0.c[l] = fin[l * cur.n];
+        for (uint64_t i = 1; i < cur.n; i++)
             for (int l = 0; l < 5; l++)
-                if (fin[l * cur_n + i] != f0.c[l]) VG_FAIL(ctx, "FRI: final layer is not constant (the committed functions are not low degree)");
+                if (fin[l * cur.n + i] != f0.c[l]) VG_FAIL(ctx, "FRI: final layer is not constant (the committed functions are not low degree)");
         out->fri.final_poly = canon(f0);
     }
     out->fri.pow_witness = bb::from_monty(ch.grind(POW_BITS));
     std::vector<uint64_t> indices;
     for (int q = 0; q < NUM_QUERIES; q++) indices.push_back(ch.sample_bits(log_max));
 
-    // ---- query phase: one gather for every word the proof needs -----------------------------------
+    // ---- query phase: one gather for every word the proof needs (split proof: every rank reports the words it holds) ------
     std::vector<const uint32_t*> ptrs;
-    auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) ptrs.push_back(d + k); };
+    auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) ptrs.push_back(d ? d + k : nullptr); };
     for (uint64_t index : indices) {
-        for (size_t i = 0; i < layers.size(); i++) {
-            const FriLayer& L = layers[i];
+        for (size_t i = 0; i < S.layers.size(); i++) {
+            const FriLayer& L = S.layers[i];
             uint64_t index_i = index >> i, sib = index_i ^ 1, pair = index_i >> 1;
-            for (int l = 0; l < 5; l++) ptrs.push_back(L.values + (uint64_t)l * L.n + sib);
-            for (size_t lvl = 0; lvl + 1 < L.layer_ptr.size(); lvl++) push_digest(L.layer_ptr[lvl] + ((pair >> lvl) ^ 1) * 8);
+            for (int l = 0; l < 5; l++) ptrs.push_back(L.values.at(ctx, l, sib));
+            for (size_t lvl = 0; lvl + 1 < L.tree.layer_ptr.size(); lvl++) push_digest(L.tree.node(ctx, lvl, (pair >> lvl) ^ 1));
         }
         for (const OpenRound& rd : rounds) {
             int lg = log2u(rd.pd->max_height);
             uint64_t bidx = index >> (log_max - lg);
             for (auto* m : rd.pd->ldes) {
-                uint64_t row = bidx >> (lg - log2u(m->h));
-                for (uint64_t c = 0; c < m->w; c++) ptrs.push_back(m->d + c * m->col_stride + row);
+                const uint64_t row = bidx >> (lg - log2u(m->gh));
+                const bool mine = m->dist == VG_ROWS ? (row >= m->row0 && row < m->row0 + m->h) : (ctx->comm_rank == 0 || !vg_sharded(ctx));
+                for (uint64_t c = 0; c < m->w; c++) ptrs.push_back(mine ? m->d + c * m->col_stride + (row - m->row0) : nullptr);
             }
-            for (int lvl = 0; lvl < lg; lvl++) push_digest(rd.pd->layer_ptr[lvl] + ((bidx >> lvl) ^ 1) * 8);
+            for (int lvl = 0; lvl < lg; lvl++) push_digest(rd.pd->tree.node(ctx, lvl, (bidx >> lvl) ^ 1));
         }
     }
     std::vector<uint32_t> words;
@@ -203,10 +237,10 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
     auto take_digest = [&]() { Digest d; for (int k = 0; k < 8; k++) d[k] = words[pos++]; return d; };
     for (size_t qi = 0; qi < indices.size(); qi++) {
         QueryProofH qp;
-        for (size_t i = 0; i < layers.size(); i++) {
+        for (size_t i = 0; i < S.layers.size(); i++) {
             CommitPhaseStepH st;
             for (int l = 0; l < 5; l++) st.sibling_value.c[l] = bb::from_monty(words[pos++]);
-            for (size_t lvl = 0; lvl + 1 < layers[i].layer_ptr.size(); lvl++) st.opening_proof.push_back(take_digest());
+            for (size_t lvl = 0; lvl + 1 < S.layers[i].tree.layer_ptr.size(); lvl++) st.opening_proof.push_back(take_digest());
             qp.steps.push_back(std::move(st));
         }
         out->fri.query_proofs.push_back(std::move(qp));
@@ -223,7 +257,6 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
             out->query_openings.back().push_back(std::move(bo));
         }
     }
-    for (auto& L : layers) { vg_free(ctx, L.values); vg_free(ctx, L.digests); }
     return 0;
 }
 
@@ -272,11 +305,29 @@ void write_opening_proof(Cbor& w, const OpeningH& op) {
     }
 }
 
+// Device time of a phase: an event pair on the context's stream, read back by vgpu_last_prove_phases — no host
+// synchronisation inside the proof.
 struct Phase {
-    vgpu_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
-    Phase(vgpu_ctx* c, const char* n) : ctx(c), name(n) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
-    ~Phase() { cudaStreamSynchronize(ctx->stream); ctx->phases.push_back({name, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count()}); }
+    vgpu_ctx* ctx;
+    static cudaEvent_t ev(vgpu_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e);
+        return e;
+    }
+    Phase(vgpu_ctx* c, const char* n) : ctx(c) {
+        vgpu_ctx::PhaseMark m; m.name = n; m.a = ev(c); m.b = ev(c);
+        cudaEventRecord(m.a, c->stream);
+        c->phase_marks.push_back(m);
+        idx = c->phase_marks.size() - 1;
+    }
+    ~Phase() { cudaEventRecord(ctx->phase_marks[idx].b, ctx->stream); }
+    size_t idx;
 };
+void phases_reset(vgpu_ctx* ctx) {
+    for (auto& m : ctx->phase_marks) { ctx->event_pool.push_back(m.a); ctx->event_pool.push_back(m.b); }
+    ctx->phase_marks.clear();
+    ctx->phases.clear();
+}
 
 vgh::Poseidon16* poseidon_of(vgpu_ctx* ctx) {
     if (!ctx->poseidon) {
@@ -288,6 +339,7 @@ vgh::Poseidon16* poseidon_of(vgpu_ctx* ctx) {
 }
 
 struct PdGuard { vgpu_prover_data* p = nullptr; ~PdGuard() { if (p) vgpu_prover_data_free(p); } };
+struct BufGuard { vgpu_ctx* ctx; void* p = nullptr; explicit BufGuard(vgpu_ctx* c) : ctx(c) {} ~BufGuard() { vg_free(ctx, p); } };
 struct MatGuard { std::vector<vgpu_dmat*> v; ~MatGuard() { for (auto* m : v) vgpu_dmat_free(m); } };
 
 }  // namespace
@@ -359,14 +411,15 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
                           uint8_t** proof_out, uint64_t* proof_len) {
     if (!ctx->challenger_set) VG_FAIL(ctx, "prove: vgpu_set_challenger has not been called");
     if (!proof_out || !proof_len) VG_FAIL(ctx, "prove: null output");
-    ctx->phases.clear();
+    VG_TRY(vg_enter(ctx));
+    if (!ctx->in_host_prove) phases_reset(ctx);
     const vgpu_chip_desc* chips[VGPU_NUM_CHIPS];
     int log_degrees[VGPU_NUM_CHIPS];
     for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
         chips[i] = vgpu_basic_machine_chip(i);
-        if (!main[i] || main[i]->w != chips[i]->width) VG_FAIL(ctx, "prove: chip %d trace has width %llu, expected %u", i, main[i] ? (unsigned long long)main[i]->w : 0ull, chips[i]->width);
-        log_degrees[i] = log2u(main[i]->h);
-        if ((1ull << log_degrees[i]) != main[i]->h) VG_FAIL(ctx, "prove: chip %d trace height is not a power of two", i);
+        if (!main[i] || main[i]->gw != chips[i]->width) VG_FAIL(ctx, "prove: chip %d trace has width %llu, expected %u", i, main[i] ? (unsigned long long)main[i]->gw : 0ull, chips[i]->width);
+        log_degrees[i] = log2u(main[i]->gh);
+        if ((1ull << log_degrees[i]) != main[i]->gh) VG_FAIL(ctx, "prove: chip %d trace height is not a power of two", i);
     }
     vgh::Challenger ch;
     { delete (vgh::Poseidon16*)ctx->poseidon; ctx->poseidon = nullptr; }
@@ -392,12 +445,26 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
         MatGuard perms;
         {
             Phase ph(ctx, "permutation traces");
+            // the cumulative sums of all chips come back with ONE copy: per chip the per-rank sums of its running sum
+            const uint32_t slots = vg_perm_totals_ranks(ctx);
+            BufGuard tot(ctx);
+            VG_TRY(vg_alloc(ctx, (void**)&tot.p, (size_t)VGPU_NUM_CHIPS * slots * 5 * 4));
+            uint32_t nt[VGPU_NUM_CHIPS];
             for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
                 const vgpu_dmat* p = i == 1 ? prep[0] : i == 12 ? prep[1] : nullptr;
                 vgpu_dmat* pm = nullptr;
-                VG_TRY(vgpu_perm_trace(ctx, chips[i], main[i], p, perm_challenges, &pm, cumsum[i]));
+                VG_TRY(vg_perm_trace_enqueue(ctx, chips[i], main[i], p, perm_challenges, &pm, (uint32_t*)tot.p + (size_t)i * slots * 5, &nt[i]));
                 perms.v.push_back(pm);
             }
+            std::vector<uint32_t> ht((size_t)VGPU_NUM_CHIPS * slots * 5);
+            VG_CUDA(ctx, cudaMemcpyAsync(ht.data(), tot.p, ht.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < VGPU_NUM_CHIPS; i++)
+                for (int l = 0; l < 5; l++) {
+                    uint32_t a = 0;
+                    for (uint32_t r = 0; r < nt[i]; r++) a = bb::add(a, ht[((size_t)i * slots + r) * 5 + l]);
+                    cumsum[i][l] = bb::from_monty(a);
+                }
         }
         Phase ph(ctx, "commit permutation");
         VG_TRY(vgpu_commit_batches(ctx, perms.v.data(), VGPU_NUM_CHIPS, nullptr, perm_commit.data(), &perm_pd.p));
@@ -477,26 +544,43 @@ int32_t vgpu_prove(vgpu_ctx* ctx, const vgpu_matrix main[VGPU_NUM_CHIPS], const 
     // then main traces tallest first — the Merkle tree hashes the tallest LDEs first and extends the shorter matrices
     // only when a tree layer of their height is reached), each transpose is deferred to the matrix's first use, so
     // copies of later matrices overlap the LDE / Keccak kernels of earlier ones.
+    // Split proof: of a trace tall enough to be split a rank uploads ITS run of rows only (1 / comm_size of the bytes).
+    VG_TRY(vg_enter(ctx));
     MatGuard dm, dp;
-    ctx->phases.clear();
+    phases_reset(ctx);
     auto t0 = std::chrono::steady_clock::now();
     dm.v.assign(VGPU_NUM_CHIPS, nullptr); dp.v.assign(2, nullptr);
-    for (int i = 0; i < 2; i++) VG_TRY(vg_dmat_alloc(ctx, prep[i].height, prep[i].width, &dp.v[i]));
-    for (int i = 0; i < VGPU_NUM_CHIPS; i++) VG_TRY(vg_dmat_alloc(ctx, main[i].height, main[i].width, &dm.v[i]));
-    for (int i = 0; i < 2; i++) VG_TRY(vg_upload_begin(ctx, prep[i].data, prep[i].height, prep[i].width, repr, dp.v[i]));
+    auto alloc_for = [&](const vgpu_matrix& hm, vgpu_dmat** out) {
+        return vg_split_rows(ctx, 2 * hm.height) ? vg_dmat_alloc_dist(ctx, VG_ROWS, hm.height, hm.width, false, out) : vg_dmat_alloc(ctx, hm.height, hm.width, out);
+    };
+    auto begin_upload = [&](const vgpu_matrix& hm, vgpu_dmat* m) { return vg_upload_begin(ctx, hm.data + m->row0 * hm.width, m->h, m->w, repr, m); };
+    for (int i = 0; i < 2; i++) VG_TRY(alloc_for(prep[i], &dp.v[i]));
+    for (int i = 0; i < VGPU_NUM_CHIPS; i++) VG_TRY(alloc_for(main[i], &dm.v[i]));
+    for (int i = 0; i < 2; i++) VG_TRY(begin_upload(prep[i], dp.v[i]));
     std::vector<int> order(VGPU_NUM_CHIPS);
     for (int i = 0; i < VGPU_NUM_CHIPS; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return main[a].height > main[b].height; });
-    for (int i : order) VG_TRY(vg_upload_begin(ctx, main[i].data, main[i].height, main[i].width, repr, dm.v[i]));
+    for (int i : order) VG_TRY(begin_upload(main[i], dm.v[i]));
     float up = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->phases.push_back({"upload traces (H2D enqueue; copies overlap the commits)", up});
+    ctx->in_host_prove = true;
     int32_t rc = vgpu_prove_device(ctx, dm.v.data(), dp.v.data(), proof_out, proof_len);
-    ctx->phases.insert(ctx->phases.begin(), {"upload traces (H2D enqueue; copies overlap the commits)", up});
+    ctx->in_host_prove = false;
     return rc;
 }
 
 void vgpu_free_bytes(uint8_t* p) { std::free(p); }
 
-uint32_t vgpu_last_prove_phases(const vgpu_ctx* ctx, const char** names, float* ms, uint32_t cap) {
+uint32_t vgpu_last_prove_phases(const vgpu_ctx* cctx, const char** names, float* ms, uint32_t cap) {
+    vgpu_ctx* ctx = const_cast<vgpu_ctx*>(cctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& m : ctx->phase_marks) {          // drain the event pairs of the last prove into (name, milliseconds)
+        float e = 0;
+        if (cudaEventElapsedTime(&e, m.a, m.b) != cudaSuccess) { cudaGetLastError(); e = -1.f; }
+        ctx->phases.push_back({m.name, e});
+        ctx->event_pool.push_back(m.a); ctx->event_pool.push_back(m.b);
+    }
+    ctx->phase_marks.clear();
     uint32_t n = (uint32_t)ctx->phases.size();
     for (uint32_t i = 0; i < n && i < cap; i++) { names[i] = ctx->phases[i].first; ms[i] = ctx->phases[i].second; }
     return n;

@@ -92,23 +92,6 @@ __global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __r
     w[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint64_t row0, uint64_t nrows, uint32_t* digests) {
-    std::vector<const uint32_t*> cols;
-    for (auto* m : mats) for (uint64_t c = 0; c < m->w; c++) cols.push_back(m->d + c * m->col_stride);
-    const uint32_t** dcols = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&dcols, cols.size() * sizeof(void*)));
-    VG_CUDA(ctx, cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    // the host vector must outlive the async copy from pageable memory: cudaMemcpyAsync from pageable memory
-    // stages synchronously, so it is safe to let `cols` go once the call returns.
-    {
-        KScope ks(ctx, KC_LEAF_HASH, (double)nrows * (4.0 * cols.size() + 32.0));
-        leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), row0, nrows, digests);
-    }
-    VG_LAUNCH_CHECK(ctx);
-    vg_free(ctx, dcols);
-    return 0;
-}
-
 // FRI commit-phase leaf: the pair (v[2i], v[2i+1]) of ext5 values flattened to 10 base words
 // (ExtensionMmcs over a width-2 matrix); v is limb-major: limb l of element e at v[l * cs + e].
 __global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __restrict__ v, uint64_t cs, uint64_t i0, uint64_t npairs, uint32_t* __restrict__ digests) {
@@ -130,57 +113,95 @@ __global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __re
 
 }  // namespace
 
-// Tree layers split across the ranks of the communicator: a layer of `len` nodes with len >= comm_size is cut into
-// comm_size contiguous shares; a rank derives its share of every such layer from its own share of the layer below
-// (parents [k*len/G, (k+1)*len/G) need exactly children [k*2len/G, (k+1)*2len/G)), so no exchange is needed on the
-// way up.  One grouped all-gather then completes every layer on every rank, and the layers shorter than comm_size
-// are computed by all ranks.  Unsplit (single GPU / sharding off): share = the whole layer.
-struct Share { uint64_t begin, count; bool split; };
-static Share share_of(const vgpu_ctx* ctx, uint64_t len) {
-    Share s; int32_t split = 0;
-    vgpu_tree_share(len, vg_sharded(ctx) ? ctx->comm_size : 1, ctx->comm_rank, &s.begin, &s.count, &split);
-    s.split = split != 0;
-    return s;
+// ---- host side: layer plan, launches --------------------------------------------------------------------------
+// Layer plan of a tree over `leaves` leaves (merkle.h): which run of every layer this rank computes and which it keeps.
+struct LayerPlan { uint64_t len, cbegin, ccount, sbegin, scount; bool gather; };
+static std::vector<LayerPlan> plan_tree(const vgpu_ctx* ctx, uint64_t leaves, bool split) {
+    const uint64_t G = split ? (uint64_t)ctx->comm_size : 1, r = split ? (uint64_t)ctx->comm_rank : 0;
+    std::vector<LayerPlan> plan;
+    for (uint64_t len = leaves; len >= 1; len >>= 1) {
+        LayerPlan p{};
+        p.len = len;
+        if (G > 1 && len >= G) { p.ccount = len / G; p.cbegin = r * p.ccount; } else { p.cbegin = 0; p.ccount = len; }
+        if (G > 1 && len > G) { p.sbegin = p.cbegin; p.scount = p.ccount; } else { p.sbegin = 0; p.scount = len; }
+        p.gather = G > 1 && len == G;          // the sub-roots: one node per rank, completed by the all-gather
+        plan.push_back(p);
+        if (len == 1) break;
+    }
+    return plan;
 }
-// complete the split layers [first, last) of a tree whose layer i starts at layer_ptr[i] and has layer_len[i] nodes
-static int32_t gather_split_layers(vgpu_ctx* ctx, const std::vector<uint32_t*>& layer_ptr, const std::vector<uint64_t>& layer_len, size_t first, size_t last) {
-    if (first >= last) return 0;
-    VG_TRY(vg_comm_group_begin(ctx));
-    for (size_t i = first; i < last; i++) VG_TRY(vg_comm_allgather_inplace(ctx, layer_ptr[i], layer_len[i] / (uint64_t)ctx->comm_size * 8));
-    return vg_comm_group_end(ctx);
+static int32_t alloc_tree(vgpu_ctx* ctx, const std::vector<LayerPlan>& plan, VgTree* t) {
+    uint64_t total = 0;
+    for (auto& p : plan) total += p.scount;
+    VG_TRY(vg_alloc(ctx, (void**)&t->digests, total * 32));
+    t->layer_ptr.clear(); t->layer_len.clear(); t->layer_begin.clear(); t->layer_count.clear();
+    uint32_t* at = t->digests;
+    for (auto& p : plan) { t->layer_ptr.push_back(at); t->layer_len.push_back(p.len); t->layer_begin.push_back(p.sbegin); t->layer_count.push_back(p.scount); at += p.scount * 8; }
+    return 0;
 }
+void vg_tree_free(vgpu_ctx* ctx, VgTree* t) { vg_free(ctx, t->digests); t->digests = nullptr; }
 
-// Single-matrix tree over ext5 pairs (p3-fri commit phase): digests = [leaf layer | ... | root].
-int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint64_t npairs, uint32_t* digests,
-                            std::vector<uint32_t*>* layer_ptr, std::vector<uint64_t>* layer_len, uint32_t root_out[8]) {
-    Share sh = share_of(ctx, npairs);
+// digest of rows [row0, row0 + nrows) of the concatenated matrices, written to digests_v[row * 8] (digests_v is a VIRTUAL
+// base: the stored run starts at its first row).  A row shard contributes its local rows through a base shifted likewise.
+static int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mats, uint64_t row0, uint64_t nrows, uint32_t* digests_v) {
+    std::vector<const uint32_t*> cols;
+    for (auto* m : mats) {
+        if (m->dist == VG_ROWS && (row0 < m->row0 || row0 + nrows > m->row0 + m->h)) VG_FAIL(ctx, "commit: rows [%llu, +%llu) are not in this rank's shard", (unsigned long long)row0, (unsigned long long)nrows);
+        for (uint64_t c = 0; c < m->w; c++) cols.push_back(m->d + c * m->col_stride - m->row0);
+    }
+    const uint32_t** dcols = nullptr;
+    VG_TRY(vg_alloc(ctx, (void**)&dcols, cols.size() * sizeof(void*)));
+    // cudaMemcpyAsync from pageable memory stages synchronously: `cols` may go once the call returns
+    VG_CUDA(ctx, cudaMemcpyAsync(dcols, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     {
-        KScope ks(ctx, KC_FRI_LEAF, (double)sh.count * 72.0);
-        fri_leaf_hash_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, ctx->stream>>>(v, cs, sh.begin, sh.count, digests);
+        KScope ks(ctx, KC_LEAF_HASH, (double)nrows * (4.0 * cols.size() + 32.0));
+        leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(dcols, (uint32_t)cols.size(), row0, nrows, digests_v);
     }
     VG_LAUNCH_CHECK(ctx);
-    uint32_t* layer = digests;
-    uint64_t len = npairs;
-    layer_ptr->clear(); layer_len->clear();
-    layer_ptr->push_back(layer); layer_len->push_back(len);
-    size_t n_split = sh.split ? 1 : 0;
-    bool gathered = !sh.split;
-    while (len > 1) {
-        uint64_t next_len = len / 2;
-        uint32_t* next = layer + len * 8;
-        sh = share_of(ctx, next_len);
-        if (!sh.split && !gathered) { VG_TRY(gather_split_layers(ctx, *layer_ptr, *layer_len, 0, n_split)); gathered = true; }
+    vg_free(ctx, dcols);
+    return 0;
+}
+
+// layers 1.. of a planned tree whose leaf layer is already hashed; inject(lvl, plan, inj_v) fills the digests of the rows a
+// shorter matrix group contributes at layer lvl (returns false when there is none)
+template <class Inject>
+static int32_t build_upper_layers(vgpu_ctx* ctx, const std::vector<LayerPlan>& plan, VgTree* t, uint32_t* inject_buf, Inject inject) {
+    if (plan[0].gather) VG_TRY(vg_comm_allgather_inplace(ctx, t->layer_ptr[0], 8));
+    for (size_t lvl = 1; lvl < plan.size(); lvl++) {
+        const LayerPlan& p = plan[lvl];
+        const uint32_t* prev_v = t->layer_ptr[lvl - 1] - plan[lvl - 1].sbegin * 8;
+        uint32_t* next_v = t->layer_ptr[lvl] - p.sbegin * 8;
+        const uint32_t* inj_v = nullptr;
+        if (inject_buf) {
+            uint32_t* buf_v = inject_buf - p.cbegin * 8;
+            bool have = false;
+            VG_TRY(inject(lvl, p, buf_v, &have));
+            if (have) inj_v = buf_v;
+        }
         {
-            KScope ks(ctx, KC_COMPRESS, (double)sh.count * 96.0);
-            compress_layer_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, ctx->stream>>>(layer, nullptr, sh.begin, sh.count, next);
+            KScope ks(ctx, KC_COMPRESS, (double)p.ccount * (inj_v ? 128.0 : 96.0));
+            compress_layer_kernel<<<(unsigned)((p.ccount + 127) / 128), 128, 0, ctx->stream>>>(prev_v, inj_v, p.cbegin, p.ccount, next_v);
         }
         VG_LAUNCH_CHECK(ctx);
-        layer_ptr->push_back(next); layer_len->push_back(next_len);
-        if (sh.split) n_split++;
-        layer = next; len = next_len;
+        if (p.gather) VG_TRY(vg_comm_allgather_inplace(ctx, t->layer_ptr[lvl], 8));
     }
-    if (!gathered) VG_TRY(gather_split_layers(ctx, *layer_ptr, *layer_len, 0, n_split));
-    VG_CUDA(ctx, cudaMemcpyAsync(root_out, layer, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// Single-matrix tree over ext5 pairs (p3-fri commit phase).
+int32_t vg_fri_layer_commit(vgpu_ctx* ctx, const uint32_t* v, uint64_t cs, uint64_t npairs, bool v_is_shard, VgTree* tree, uint32_t root_out[8]) {
+    const std::vector<LayerPlan> plan = plan_tree(ctx, npairs, v_is_shard);
+    VG_TRY(alloc_tree(ctx, plan, tree));
+    const LayerPlan& l0 = plan[0];
+    {
+        // v holds the pairs of this rank's run when it is a shard (the run IS the computed run), all pairs otherwise
+        const uint32_t* v_v = v_is_shard ? v - 2 * l0.cbegin : v;
+        KScope ks(ctx, KC_FRI_LEAF, (double)l0.ccount * 72.0);
+        fri_leaf_hash_kernel<<<(unsigned)((l0.ccount + 127) / 128), 128, 0, ctx->stream>>>(v_v, cs, l0.cbegin, l0.ccount, tree->layer_ptr[0] - l0.sbegin * 8);
+    }
+    VG_LAUNCH_CHECK(ctx);
+    VG_TRY(build_upper_layers(ctx, plan, tree, nullptr, [](size_t, const LayerPlan&, uint32_t*, bool*) { return 0; }));
+    VG_CUDA(ctx, cudaMemcpyAsync(root_out, tree->layer_ptr.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -196,8 +217,8 @@ int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd, const std::vector<u
     uint64_t max_h = heights[order[0]];
     if (max_h & (max_h - 1)) VG_FAIL(ctx, "commit: heights must be powers of two");
     pd->max_height = max_h;
-    // all layers in one allocation: max_h + max_h/2 + ... + 1 = 2*max_h - 1 digests
-    VG_TRY(vg_alloc(ctx, (void**)&pd->digests, (2 * max_h) * 32));
+    const std::vector<LayerPlan> plan = plan_tree(ctx, max_h, vg_split_rows(ctx, max_h));
+    VG_TRY(alloc_tree(ctx, plan, &pd->tree));
     size_t pos = 0;
     std::vector<size_t> idx;
     std::vector<const vgpu_dmat*> group;
@@ -207,46 +228,25 @@ int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd, const std::vector<u
         if (idx.empty()) return 0;
         if (need) VG_TRY(need(idx));
         for (size_t i : idx) {
-            if (!pd->ldes[i] || pd->ldes[i]->h != height) VG_FAIL(ctx, "commit: matrix %zu was not extended to height %llu", i, (unsigned long long)height);
+            if (!pd->ldes[i] || pd->ldes[i]->gh != height) VG_FAIL(ctx, "commit: matrix %zu was not extended to height %llu", i, (unsigned long long)height);
             group.push_back(pd->ldes[i]);
         }
         return 0;
     };
     VG_TRY(take(max_h));
-    uint32_t* layer = pd->digests;
-    pd->layer_ptr.clear(); pd->layer_len.clear();
-    pd->layer_ptr.push_back(layer); pd->layer_len.push_back(max_h);
-    Share sh = share_of(ctx, max_h);
-    VG_TRY(hash_rows(ctx, group, sh.begin, sh.count, layer));
-    size_t n_split = sh.split ? 1 : 0;
-    bool gathered = !sh.split;
+    VG_TRY(hash_rows(ctx, group, plan[0].cbegin, plan[0].ccount, pd->tree.layer_ptr[0] - plan[0].sbegin * 8));
     uint32_t* inject_buf = nullptr;
-    uint64_t len = max_h;
-    while (len > 1) {
-        uint64_t next_len = len / 2;
-        sh = share_of(ctx, next_len);
-        if (!sh.split && !gathered) { VG_TRY(gather_split_layers(ctx, pd->layer_ptr, pd->layer_len, 0, n_split)); gathered = true; }
-        VG_TRY(take(next_len));
-        const uint32_t* inj = nullptr;
-        if (!group.empty()) {
-            if (!inject_buf) VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (max_h / 2) * 32));
-            VG_TRY(hash_rows(ctx, group, sh.begin, sh.count, inject_buf));
-            inj = inject_buf;
-        }
-        uint32_t* next = layer + len * 8;
-        {
-            KScope ks(ctx, KC_COMPRESS, (double)sh.count * (inj ? 128.0 : 96.0));
-            compress_layer_kernel<<<(unsigned)((sh.count + 127) / 128), 128, 0, ctx->stream>>>(layer, inj, sh.begin, sh.count, next);
-        }
-        VG_LAUNCH_CHECK(ctx);
-        pd->layer_ptr.push_back(next); pd->layer_len.push_back(next_len);
-        if (sh.split) n_split++;
-        layer = next; len = next_len;
-    }
-    if (!gathered) VG_TRY(gather_split_layers(ctx, pd->layer_ptr, pd->layer_len, 0, n_split));
+    if (pos < n) VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (plan.size() > 1 ? plan[1].ccount : 1) * 32));
+    int32_t rc = build_upper_layers(ctx, plan, &pd->tree, inject_buf, [&](size_t, const LayerPlan& p, uint32_t* buf_v, bool* have) -> int32_t {
+        VG_TRY(take(p.len));
+        *have = !group.empty();
+        if (*have) VG_TRY(hash_rows(ctx, group, p.cbegin, p.ccount, buf_v));
+        return 0;
+    });
     if (inject_buf) vg_free(ctx, inject_buf);
+    if (rc) return rc;
     if (pos != n) VG_FAIL(ctx, "commit: a matrix height does not match any tree layer");
-    VG_CUDA(ctx, cudaMemcpyAsync(pd->root, layer, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    VG_CUDA(ctx, cudaMemcpyAsync(pd->root, pd->tree.layer_ptr.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -33,7 +33,7 @@ __device__ __forceinline__ void st5(uint32_t* v, uint64_t cs, uint64_t i, const 
 }
 
 // out[i] = x_i - z,  x_i = s * w_H^bitrev(i)   (storage order of a committed LDE of height H = 2^log_h)
-__global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out, uint64_t H, uint64_t begin, uint64_t count, uint32_t log_h, uint32_t s, E5 z, const uint32_t* lo, const uint32_t* hi) {
+__global__ void __launch_bounds__(256) coset_minus_point_kernel(uint32_t* out /* virtual base: + global row */, uint64_t H /* limb stride */, uint64_t begin, uint64_t count, uint32_t log_h, uint32_t s, E5 z, const uint32_t* lo, const uint32_t* hi) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     i += begin;
@@ -248,14 +248,16 @@ __global__ void __launch_bounds__(256) reduced_opening_kernel(const __grid_const
     st5(p.ro, p.rcs, i, bb::e5_add(ld5(p.ro, p.rcs, i), s.value()));
 }
 
-// K10: out[i] = (lo + hi)/2 + (beta/2) * g_inv^bitrev(i) * (lo - hi)  (+ add[i])
-__global__ void __launch_bounds__(256) fri_fold_kernel(const uint32_t* cur, uint64_t ccs, uint64_t half, uint32_t log_half, E5 half_beta, uint32_t one_half,
+// K10: out[i] = (lo + hi)/2 + (beta/2) * g_inv^bitrev(i) * (lo - hi)  (+ add[i]) for the `count` outputs starting at i0; `cur` holds
+// the pairs of exactly those outputs (a rank's run, or everything with i0 = 0); out / add are virtual bases (+ global i)
+__global__ void __launch_bounds__(256) fri_fold_kernel(const uint32_t* cur, uint64_t ccs, uint64_t i0, uint64_t count, uint32_t log_half, E5 half_beta, uint32_t one_half,
                                                       const uint32_t* add, uint64_t acs, uint32_t* out, uint64_t ocs, const uint32_t* lo, const uint32_t* hi) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= half) return;
+    const uint64_t il = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= count) return;
+    const uint64_t i = i0 + il;
     E5 a, b;
 #pragma unroll
-    for (int l = 0; l < 5; l++) { uint2 t = *reinterpret_cast<const uint2*>(cur + (uint64_t)l * ccs + 2 * i); a.c[l] = t.x; b.c[l] = t.y; }
+    for (int l = 0; l < 5; l++) { uint2 t = *reinterpret_cast<const uint2*>(cur + (uint64_t)l * ccs + 2 * il); a.c[l] = t.x; b.c[l] = t.y; }
     uint32_t nat = bb::reverse_bits((uint32_t)i, (int)log_half);
     // g_inv^nat, g = two_adic_generator(log_half + 1)
     uint64_t e = (uint64_t)nat << (VG_LOG_NMAX - log_half - 1);
@@ -275,9 +277,17 @@ __global__ void __launch_bounds__(256) bary_reduce_kernel(const uint32_t* __rest
     out[i] = acc;
 }
 
+// a null pointer is a word another rank reports (split proof): it contributes 0 to the sum over the ranks
 __global__ void __launch_bounds__(256) gather_words_kernel(const uint32_t* const* ptrs, uint64_t n, uint32_t* out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = *ptrs[i];
+    if (i < n) { const uint32_t* q = ptrs[i]; out[i] = q ? *q : 0u; }
+}
+__global__ void __launch_bounds__(256) sum_ranks_kernel(const uint32_t* __restrict__ all, uint32_t nranks, uint64_t n, uint32_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = 0;
+    for (uint32_t r = 0; r < nranks; r++) a += all[(uint64_t)r * n + i];     // exactly one rank reports a non-zero word
+    out[i] = a;
 }
 
 }  // namespace
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(256) gather_words_kernel(const uint32_t* const
 // ext5 and batch-inverting there (3 ext5 products per element plus a Frobenius-norm inversion per 8).  Measured per
 // proof: 4.0 ms (ext5 batch inversion) -> 2.27 ms (batch 16, 96 registers) -> 2.07 ms (batch 8, 62 registers, 8 CTAs/SM).
 struct InvdenParams {
-    uint32_t* out; uint64_t H, begin, count; uint32_t log_h, s;
+    uint32_t* out; uint64_t H /* limb stride of out */, begin, count; uint32_t log_h, s;      // out: virtual base (+ global row)
     uint32_t mc[5];          // M(x) = x^5 + sum_j mc[j] x^j
     uint32_t qc[4][5];       // Q(x) = x^4 + sum_j qc[j] x^j   (qc[j] ext5, limb l at qc[j][l])
     const uint32_t* lo; const uint32_t* hi;
@@ -340,17 +350,18 @@ __global__ void __launch_bounds__(128, MINB) invden_norm_kernel(const __grid_con
     }
 }
 
-static int32_t inverse_denominators_range(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint32_t* out, uint64_t begin, uint64_t count) {
-    uint64_t H = 1ull << log_H;
+// 1/(x_i - z) for the rows [begin, begin + count) of the coset of height 2^log_H (committed order): out[l * count + (i - begin)]
+int32_t vg_inverse_denominators(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint64_t begin, uint64_t count, uint32_t* out) {
     KScope ks(ctx, KC_INVDEN, 20.0 * (double)count);
+    uint32_t* out_v = out - begin;
     if ((z.c[1] | z.c[2] | z.c[3] | z.c[4]) == 0) {
         // z in the base field may hit a coset point: the generic path keeps a zero denominator as zero
-        coset_minus_point_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out, H, begin, count, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
+        coset_minus_point_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(out_v, count, begin, count, log_H, bb::to_monty(bb::GEN_CANON), z, ctx->root_table.lo, ctx->root_table.hi);
         VG_LAUNCH_CHECK(ctx);
-        return vg_ext_batch_inverse(ctx, out + begin, H, count, 1);
+        return vg_ext_batch_inverse(ctx, out, count, count, 1);
     }
     InvdenParams p{};
-    p.out = out; p.H = H; p.begin = begin; p.count = count; p.log_h = log_H; p.s = bb::to_monty(bb::GEN_CANON);
+    p.out = out_v; p.H = count; p.begin = begin; p.count = count; p.log_h = log_H; p.s = bb::to_monty(bb::GEN_CANON);
     p.lo = ctx->root_table.lo; p.hi = ctx->root_table.hi;
     {   // poly(x) = prod (x - frob^k z): coefficients low to high, ext5 arithmetic on the host
         uint32_t zp[5];
@@ -384,33 +395,28 @@ static int32_t inverse_denominators_range(vgpu_ctx* ctx, uint32_t log_H, const E
     VG_LAUNCH_CHECK(ctx);
     return 0;
 }
-// When the row sweeps of this height are split across ranks, a rank only ever reads 1/(x - z) on its range of the
-// reduced-opening sweep (all H rows) and on its range of the barycentric sweep (the first H/2 rows); rank 0's second
-// range lies inside its first.
-int32_t vg_inverse_denominators(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint32_t* out) {
-    uint64_t H = 1ull << log_H;
-    if (!vg_split_rows(ctx, H / 2)) return inverse_denominators_range(ctx, log_H, z, out, 0, H);
-    const uint64_t G = (uint64_t)ctx->comm_size, r = (uint64_t)ctx->comm_rank;
-    VG_TRY(inverse_denominators_range(ctx, log_H, z, out, r * (H / G), H / G));
-    if (r > 0) VG_TRY(inverse_denominators_range(ctx, log_H, z, out, r * (H / 2 / G), H / 2 / G));
-    return 0;
-}
 
 // Enqueue the sums behind p_c(z_q) for every column c and point q (q < npoints <= 2) of a committed LDE (height H = 2h):
 // d_out receives w * BARY_OUT words ([c][q*5 + l] = sum_i p_c(x_i) / (x_i - z_q), [c][10] = sum_i p_c(x_i)), stream-ordered, no
 // host synchronisation — open_multi_batches reads the sums of every matrix back with ONE copy.
-int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, const uint32_t* const* invden, uint32_t* d_out) {
-    uint64_t H = lde->h, h = H / 2;
-    uint32_t w = (uint32_t)lde->w;
-    // split across ranks: each rank sums its contiguous range of the h rows, the per-rank sums meet in one small all-gather
-    const bool split = vg_split_rows(ctx, h);
-    const uint64_t rows = split ? h / ctx->comm_size : h, row_begin = split ? rows * ctx->comm_rank : 0;
+int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, const uint32_t* const* invden, uint64_t ics, uint32_t* d_out) {
+    uint64_t H = lde->gh, h = H / 2;
+    uint32_t w = (uint32_t)lde->gw;
+    // split proof: the first h committed rows (the coset g*H) lie in the shards of the first half of the ranks; each of those
+    // sums its rows, the others contribute zeros, and the per-rank sums meet in one small all-gather.  invden: the caller's
+    // vector over the same rows as the matrix part held here (limb stride ics).
+    const bool split = lde->dist == VG_ROWS;
+    const uint64_t rows = split ? (lde->row0 < h ? lde->h : 0) : h;
     BaryParams p{};
-    p.mat = lde->d; p.mcs = lde->col_stride; p.h = rows; p.row_begin = row_begin; p.w = w;
-    p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = H; p.npoints = npoints;
+    p.mat = lde->d; p.mcs = lde->col_stride; p.h = rows; p.row_begin = 0; p.w = w;
+    p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = ics; p.npoints = npoints;
     uint32_t nblocks = 1;
     uint32_t* partial = nullptr;
-    if (rows >= BARY_TILE && rows % BARY_TILE == 0) {
+    const uint32_t nout = w * BARY_OUT;
+    if (rows == 0) {
+        VG_TRY(vg_alloc(ctx, (void**)&partial, (size_t)nout * 4));
+        VG_CUDA(ctx, cudaMemsetAsync(partial, 0, (size_t)nout * 4, ctx->stream));
+    } else if (rows >= BARY_TILE && rows % BARY_TILE == 0) {
         const unsigned by = (w + 31) / 32;
         p.cpg = 2 * (((w + by - 1) / by + 1) / 2);               // columns per CTA, even
         p.rs = std::min<uint32_t>(BARY_CHUNKS, BARY_WARPS / (p.cpg / BARY_COLS));
@@ -427,14 +433,14 @@ int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t np
         KScope ks(ctx, KC_BARY, 4.0 * (double)rows * w);
         if (npoints > 1) bary_kernel<2><<<dim3(bx, by), BARY_THREADS, 2 * 2 * 5 * BARY_TILE * 4, ctx->stream>>>(p);
         else bary_kernel<1><<<dim3(bx, by), BARY_THREADS, 2 * 1 * 5 * BARY_TILE * 4, ctx->stream>>>(p);
+        VG_LAUNCH_CHECK(ctx);
     } else {
         VG_TRY(vg_alloc(ctx, (void**)&partial, (size_t)w * BARY_OUT * 4));
         p.partial = partial;
         KScope ks(ctx, KC_BARY, 4.0 * (double)rows * w);
         bary_small_kernel<<<w, 128, 0, ctx->stream>>>(p);
+        VG_LAUNCH_CHECK(ctx);
     }
-    VG_LAUNCH_CHECK(ctx);
-    const uint32_t nout = w * BARY_OUT;
     if (!split) {
         bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, nblocks, nout, d_out);
         VG_LAUNCH_CHECK(ctx);
@@ -473,23 +479,22 @@ void vg_eval_columns_finish(const uint32_t* sums, uint64_t H, uint32_t w, uint32
 }
 uint32_t vg_eval_columns_words(uint32_t w) { return w * BARY_OUT; }
 
-// ro[i] += sum_q alpha^(off_q) * (sum_c alpha^c p_c(x_i) - sum_y[q]) / (x_i - z_q),  off_1 = off_0 + w.
+// ro[i] += sum_q alpha^(off_q) * (sum_c alpha^c p_c(x_i) - sum_y[q]) / (x_i - z_q),  off_1 = off_0 + w, over the rows of the
+// matrix part held here (all rows, or this rank's run).  invden / ro: vectors over those same rows, limb stride vcs.
 // apow_off[c] = alpha^(off_0 + c) (host, Montgomery), alpha_w = alpha^w, sum_y[q] = sum_c alpha^c p_c(z_q).
 int32_t vg_reduced_opening_accumulate(vgpu_ctx* ctx, const vgpu_dmat* lde, const E5* apow_off, const E5& alpha_w, uint32_t npoints, const uint32_t* const* invden,
-                                      const E5* sum_y, uint32_t* ro) {
+                                      uint64_t vcs, const E5* sum_y, uint32_t* ro) {
     auto p = std::make_unique<RoParams>();
     p->mcs = lde->col_stride; p->H = lde->h;
-    p->npoints = npoints; p->ics = lde->h;
+    p->npoints = npoints; p->ics = vcs;
     p->invden[0] = invden[0]; p->invden[1] = npoints > 1 ? invden[1] : invden[0];
     p->b[0] = bb::e5_mul(apow_off[0], sum_y[0]);                                        // alpha^off_0 * sum_y_0
     p->b[1] = npoints > 1 ? bb::e5_mul(bb::e5_mul(apow_off[0], alpha_w), sum_y[1]) : bb::e5_zero();
     p->aw = alpha_w;
     for (int l = 0; l < 5; l++) p->aw2.c[l] = bb::dbl(alpha_w.c[l]);
-    p->ro = ro; p->rcs = lde->h;
-    // split across ranks: a rank accumulates only its range of rows; vg_reduced_openings_complete() joins the ranges
-    const bool split = vg_split_rows(ctx, lde->h / 2);
-    const uint64_t rows = split ? lde->h / ctx->comm_size : lde->h;
-    p->row_begin = split ? rows * ctx->comm_rank : 0; p->row_end = p->row_begin + rows;
+    p->ro = ro; p->rcs = vcs;
+    const uint64_t rows = lde->h;
+    p->row_begin = 0; p->row_end = rows;
     for (uint64_t c0 = 0; c0 < lde->w; c0 += RO_MAXW) {         // one launch unless the matrix is wider than the parameter table
         const uint32_t wc = (uint32_t)std::min<uint64_t>(RO_MAXW, lde->w - c0);
         p->mat = lde->d + c0 * lde->col_stride; p->w = wc; p->first = c0 == 0;
@@ -502,37 +507,43 @@ int32_t vg_reduced_opening_accumulate(vgpu_ctx* ctx, const vgpu_dmat* lde, const
     return 0;
 }
 
-// after the last vg_reduced_opening_accumulate of a height: every rank gets the whole vector (5 limbs x H)
-int32_t vg_reduced_openings_complete(vgpu_ctx* ctx, uint32_t* ro, uint64_t H) {
-    if (!vg_split_rows(ctx, H / 2)) return 0;
-    VG_TRY(vg_comm_group_begin(ctx));
-    for (int l = 0; l < 5; l++) VG_TRY(vg_comm_allgather_inplace(ctx, ro + (uint64_t)l * H, H / ctx->comm_size));
-    return vg_comm_group_end(ctx);
-}
-
-int32_t vg_fri_fold(vgpu_ctx* ctx, const uint32_t* cur, uint64_t n, const E5& beta, const uint32_t* add_or_null, uint32_t* out) {
+// One FRI fold: `cur` holds the 2 * count values behind outputs [i0, i0 + count) of the n / 2 (limb stride ccs); out_v / add_v are
+// virtual bases (+ global output index) with limb strides ocs / acs.
+int32_t vg_fri_fold(vgpu_ctx* ctx, const uint32_t* cur, uint64_t ccs, uint64_t n, uint64_t i0, uint64_t count, const E5& beta,
+                    const uint32_t* add_v, uint64_t acs, uint32_t* out_v, uint64_t ocs) {
     uint64_t half = n / 2;
     uint32_t log_half = 0; while ((1ull << log_half) < half) log_half++;
     uint32_t one_half = bb::inv(bb::to_monty(2));
     E5 half_beta = bb::e5_mul_base(beta, one_half);
-    KScope ks(ctx, KC_FRI_FOLD, 60.0 * (double)half);
-    fri_fold_kernel<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(cur, n, half, log_half, half_beta, one_half, add_or_null, half, out, half, ctx->root_table.lo, ctx->root_table.hi);
+    KScope ks(ctx, KC_FRI_FOLD, 60.0 * (double)count);
+    fri_fold_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(cur, ccs, i0, count, log_half, half_beta, one_half, add_v, acs, out_v, ocs, ctx->root_table.lo, ctx->root_table.hi);
     VG_LAUNCH_CHECK(ctx);
     return 0;
 }
 
+// The words behind `ptrs` (null = reported by another rank of a split proof), summed over the ranks.
 int32_t vg_gather_words(vgpu_ctx* ctx, const std::vector<const uint32_t*>& ptrs, std::vector<uint32_t>* out) {
     size_t n = ptrs.size();
     out->assign(n, 0);
     if (!n) return 0;
-    const uint32_t** dptr = nullptr; uint32_t* dout = nullptr;
+    const bool all = vg_sharded(ctx);
+    const size_t G = all ? (size_t)ctx->comm_size : 1;
+    const uint32_t** dptr = nullptr; uint32_t* dout = nullptr; uint32_t* dsum = nullptr;
     VG_TRY(vg_alloc(ctx, (void**)&dptr, n * sizeof(void*)));
-    VG_TRY(vg_alloc(ctx, (void**)&dout, n * 4));
+    VG_TRY(vg_alloc(ctx, (void**)&dout, n * 4 * G));
     VG_CUDA(ctx, cudaMemcpyAsync(dptr, ptrs.data(), n * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    gather_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dptr, n, dout);
+    gather_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dptr, n, dout + (all ? n * (size_t)ctx->comm_rank : 0));
     VG_LAUNCH_CHECK(ctx);
-    VG_CUDA(ctx, cudaMemcpyAsync(out->data(), dout, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const uint32_t* res = dout;
+    if (all) {
+        VG_TRY(vg_comm_allgather_inplace(ctx, dout, n));
+        VG_TRY(vg_alloc(ctx, (void**)&dsum, n * 4));
+        sum_ranks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dout, (uint32_t)G, n, dsum);
+        VG_LAUNCH_CHECK(ctx);
+        res = dsum;
+    }
+    VG_CUDA(ctx, cudaMemcpyAsync(out->data(), res, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    vg_free(ctx, dptr); vg_free(ctx, dout);
+    vg_free(ctx, dptr); vg_free(ctx, dout); vg_free(ctx, dsum);
     return 0;
 }

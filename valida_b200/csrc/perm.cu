@@ -180,6 +180,20 @@ __global__ void __launch_bounds__(256) scan_add_offsets_kernel(uint32_t* __restr
     col[i] = bb::add(col[i], chunk_sums[(uint64_t)blockIdx.y * sums_cs + chunk - 1]);
 }
 
+// totals[l] = last element of column l (the sum of this rank's rows after the local scan)
+__global__ void perm_totals_kernel(const uint32_t* __restrict__ phi, uint64_t cs, uint64_t n, uint32_t* __restrict__ totals) {
+    if (threadIdx.x < 5) totals[threadIdx.x] = phi[(uint64_t)threadIdx.x * cs + n - 1];
+}
+// split proof: phi of this rank's rows += the totals of the ranks before it (totals: [rank][limb])
+__global__ void __launch_bounds__(256) scan_add_rank_offset_kernel(uint32_t* __restrict__ phi, uint64_t cs, uint64_t n, const uint32_t* __restrict__ totals, uint32_t rank) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t off = 0;
+    for (uint32_t p = 0; p < rank; p++) off = bb::add(off, totals[p * 5 + blockIdx.y]);
+    uint32_t* col = phi + (uint64_t)blockIdx.y * cs;
+    col[i] = bb::add(col[i], off);
+}
+
 }  // namespace
 
 // Inclusive prefix sum (mod p) of `ncols` columns of length n, in place.
@@ -210,12 +224,17 @@ int32_t vg_ext_batch_inverse(vgpu_ctx* ctx, uint32_t* data, uint64_t cs, uint64_
     return 0;
 }
 
-extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const vgpu_dmat* main, const vgpu_dmat* prep_or_null,
-                                   const uint32_t challenges[15], vgpu_dmat** out_perm, uint32_t cumulative_sum_out[5]) {
+// generate_permutation_trace without a host synchronisation.  d_totals (device, 5 * vg_perm_totals_ranks() words, [rank][limb])
+// receives the per-rank sums of the signed terms; the cumulative sum is their sum over the ranks (one rank unless the chip's
+// rows are split).  Split proof, tall chip: `main` / `prep` are this rank's row shard (VG_ROWS) or the whole trace (VG_FULL, of which
+// this rank's rows are used); the result is the row shard of the permutation trace.
+int32_t vg_perm_trace_enqueue(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const vgpu_dmat* main, const vgpu_dmat* prep_or_null,
+                              const uint32_t challenges[15], vgpu_dmat** out_perm, uint32_t* d_totals, uint32_t* n_totals) {
     if (!chip || !main || !out_perm) VG_FAIL(ctx, "perm_trace: null argument");
     if (main->bitrev_rows) VG_FAIL(ctx, "perm_trace: main trace rows are stored bit-reversed");
-    if (main->w != chip->width) VG_FAIL(ctx, "perm_trace: main width %llu != chip width %u", (unsigned long long)main->w, chip->width);
-    if (chip->preprocessed_width && (!prep_or_null || prep_or_null->w != chip->preprocessed_width || prep_or_null->h != main->h)) {
+    if (main->gw != chip->width) VG_FAIL(ctx, "perm_trace: main width %llu != chip width %u", (unsigned long long)main->gw, chip->width);
+    if (main->dist == VG_COLS || (prep_or_null && prep_or_null->dist == VG_COLS)) VG_FAIL(ctx, "perm_trace: column shares are internal to a commit");
+    if (chip->preprocessed_width && (!prep_or_null || prep_or_null->gw != chip->preprocessed_width || prep_or_null->gh != main->gh)) {
         // interactions of BasicMachine never read preprocessed columns, but the shape must still be coherent when given
         if (prep_or_null) VG_FAIL(ctx, "perm_trace: preprocessed trace shape mismatch");
     }
@@ -224,30 +243,61 @@ extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, co
     auto dchip_h = std::make_unique<DevChip>();
     VG_TRY(vg_build_devchip(ctx, chip, challenges, dchip_h.get()));
     const DevChip& dchip = *dchip_h;
-    uint64_t h = main->h;
+    const bool split = vg_split_rows(ctx, 2 * main->gh);
+    if (!split && main->dist != VG_FULL) VG_FAIL(ctx, "perm_trace: the trace is a shard but too short to be split");
+    const uint64_t h = split ? main->gh / ctx->comm_size : main->gh;          // rows swept here
+    const uint64_t row0 = split ? h * ctx->comm_rank : 0;
     uint32_t k = chip->n_interactions;
     vgpu_dmat* perm = nullptr;
-    int32_t rc = vg_dmat_alloc(ctx, h, 5 * (k + 1), &perm);
-    if (rc) return rc;
-    const uint32_t* pd = prep_or_null ? prep_or_null->d : nullptr;
+    VG_TRY(split ? vg_dmat_alloc_dist(ctx, VG_ROWS, main->gh, 5 * (k + 1), false, &perm) : vg_dmat_alloc(ctx, h, 5 * (k + 1), &perm));
+    // first swept row of a matrix: a shard starts there, a whole trace is entered at row0
+    auto rows_of = [&](const vgpu_dmat* m) { return m->d + (m->dist == VG_ROWS ? 0 : row0); };
+    const uint32_t* md = rows_of(main);
+    const uint32_t* pd = prep_or_null ? rows_of(prep_or_null) : nullptr;
     uint64_t pcs = prep_or_null ? prep_or_null->col_stride : 0;
     unsigned blocks = (unsigned)((h + 255) / 256);
     KScope ks(ctx, KC_PERM, 4.0 * (double)h * (chip->width + 5.0 * (k + 1)));
     if (k) {
-        perm_denominators_kernel<<<blocks, 256, 0, ctx->stream>>>(dchip, main->d, main->col_stride, pd, pcs, h, perm->d, perm->col_stride);
+        perm_denominators_kernel<<<blocks, 256, 0, ctx->stream>>>(dchip, md, main->col_stride, pd, pcs, h, perm->d, perm->col_stride);
         VG_LAUNCH_CHECK(ctx);
         VG_TRY(vg_ext_batch_inverse(ctx, perm->d, perm->col_stride, h, k));
     }
-    perm_terms_kernel<<<blocks, 256, 0, ctx->stream>>>(dchip, main->d, main->col_stride, pd, pcs, h, perm->d, perm->col_stride);
+    perm_terms_kernel<<<blocks, 256, 0, ctx->stream>>>(dchip, md, main->col_stride, pd, pcs, h, perm->d, perm->col_stride);
     VG_LAUNCH_CHECK(ctx);
-    VG_TRY(vg_prefix_sum_columns(ctx, perm->d + (uint64_t)(5 * k) * perm->col_stride, perm->col_stride, h, 5));
-    if (cumulative_sum_out) {
-        uint32_t cs[5];
-        for (int l = 0; l < 5; l++)
-            VG_CUDA(ctx, cudaMemcpyAsync(&cs[l], perm->d + (uint64_t)(5 * k + l) * perm->col_stride + (h - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int l = 0; l < 5; l++) cumulative_sum_out[l] = bb::from_monty(cs[l]);
+    uint32_t* phi = perm->d + (uint64_t)(5 * k) * perm->col_stride;
+    VG_TRY(vg_prefix_sum_columns(ctx, phi, perm->col_stride, h, 5));
+    perm_totals_kernel<<<1, 32, 0, ctx->stream>>>(phi, perm->col_stride, h, d_totals + (split ? 5 * ctx->comm_rank : 0));
+    VG_LAUNCH_CHECK(ctx);
+    if (split) {
+        VG_TRY(vg_comm_allgather_inplace(ctx, d_totals, 5));
+        scan_add_rank_offset_kernel<<<dim3(blocks, 5), 256, 0, ctx->stream>>>(phi, perm->col_stride, h, d_totals, (uint32_t)ctx->comm_rank);
+        VG_LAUNCH_CHECK(ctx);
     }
+    *n_totals = split ? (uint32_t)ctx->comm_size : 1;
     *out_perm = perm;
     return 0;
+}
+uint32_t vg_perm_totals_ranks(const vgpu_ctx* ctx) { return vg_sharded(ctx) ? (uint32_t)ctx->comm_size : 1; }
+
+extern "C" int32_t vgpu_perm_trace(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const vgpu_dmat* main, const vgpu_dmat* prep_or_null,
+                                   const uint32_t challenges[15], vgpu_dmat** out_perm, uint32_t cumulative_sum_out[5]) {
+    VG_TRY(vg_enter(ctx));
+    uint32_t* d_tot = nullptr;
+    const uint32_t slots = vg_perm_totals_ranks(ctx);
+    VG_TRY(vg_alloc(ctx, (void**)&d_tot, slots * 5 * 4));
+    uint32_t nt = 0;
+    int32_t rc = vg_perm_trace_enqueue(ctx, chip, main, prep_or_null, challenges, out_perm, d_tot, &nt);
+    if (rc == 0 && cumulative_sum_out) {
+        uint32_t tot[16 * 5];
+        cudaError_t e = cudaMemcpyAsync(tot, d_tot, nt * 5 * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { vg_free(ctx, d_tot); VG_FAIL(ctx, "perm_trace: reading the cumulative sum failed: %s", cudaGetErrorString(e)); }
+        for (int l = 0; l < 5; l++) {
+            uint32_t a = 0;
+            for (uint32_t p = 0; p < nt; p++) a = bb::add(a, tot[p * 5 + l]);
+            cumulative_sum_out[l] = bb::from_monty(a);
+        }
+    }
+    vg_free(ctx, d_tot);
+    return rc;
 }

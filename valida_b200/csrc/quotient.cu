@@ -35,11 +35,14 @@ using air::F;
 constexpr uint32_t Q_MAX_CONSTRAINTS = 128;   // bitwise: 88 base + interactions + 3
 
 struct QParams {
-    const uint32_t* main; uint64_t mcs;
-    const uint32_t* prep; uint64_t pcs;
-    const uint32_t* perm; uint64_t qcs;
-    uint32_t* out; uint64_t ocs;            // h x 10 chunk matrix
-    const uint32_t* selinv;                 // selinv[r] = 1 / ((x-1)(x-glast)(-x-1)(-x-glast)), x = s * w^bitrev(r)
+    // Base pointers are VIRTUAL: base + (global storage row) is the element, whether the matrix is whole or this rank's row
+    // shard (then base = shard - first row).  The *_n bases serve the "next" rows: natural row i + 2 of every row of a shard
+    // lies in ONE other rank's shard (rows of a shard share i mod comm_size), read through its peer pointer over NVLink.
+    const uint32_t* main; const uint32_t* main_n; uint64_t mcs;
+    const uint32_t* prep; const uint32_t* prep_n; uint64_t pcs;
+    const uint32_t* perm; const uint32_t* perm_n; uint64_t qcs;
+    uint32_t* out; uint64_t ocs;            // h x 10 chunk matrix (virtual base: + chunk row)
+    const uint32_t* selinv;                 // selinv[r] = 1 / ((x-1)(x-glast)(-x-1)(-x-glast)), x = s * w^bitrev(r)  (virtual base: + pair)
     uint32_t log_h;
     uint64_t row_begin, row_end;            // storage rows of the LDE swept by this launch (a rank's range when the sweep is split)
     uint32_t s;                             // coset shift (Montgomery)
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const __grid_consta
     const uint64_t h = 1ull << p.log_h, H = 2 * h;
     const uint64_t rho_raw = p.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // storage row of the committed LDEs
     const bool active = rho_raw < p.row_end;
-    const uint64_t rho = active ? rho_raw : (rho_raw & 1);                         // idle lanes shadow rows 0/1 (shuffles need every lane)
+    const uint64_t rho = active ? rho_raw : p.row_begin + (rho_raw & 1);           // idle lanes shadow the first pair of the range (shuffles need every lane)
     const uint32_t e = (uint32_t)(rho & 1);                                        // 0: x = +x0 (natural row j), 1: x = -x0 (natural row j + h)
     const uint64_t r = rho >> 1;
     const uint32_t j = bb::reverse_bits((uint32_t)r, (int)p.log_h);
@@ -120,15 +123,15 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const __grid_consta
     const uint32_t parity = (uint32_t)(((uint64_t)j + (e ? h : 0)) & 1);
     const uint32_t zh = p.zh[parity];
     DevBuilder b;
-    b.lrow = p.main + rho; b.nrow = p.main + nrow; b.cs = p.mcs;
+    b.lrow = p.main + rho; b.nrow = p.main_n + nrow; b.cs = p.mcs;
     b.first = F{bb::mul(zh, inv_first)};
     b.last = F{bb::mul(zh, inv_last)};
     b.trans = F{bb::sub(x, p.glast)};
     b.apow = p.apow; b.idx = 0; b.acc.init();
     air::eval_chip<CHIP>(b);
     {   // eval_permutation_constraints
-        const uint32_t* ql = p.perm + rho; const uint32_t* qn = p.perm + nrow;
-        const uint32_t* pl = p.prep ? p.prep + rho : nullptr; const uint32_t* pn = p.prep ? p.prep + nrow : nullptr;
+        const uint32_t* ql = p.perm + rho; const uint32_t* qn = p.perm_n + nrow;
+        const uint32_t* pl = p.prep ? p.prep + rho : nullptr; const uint32_t* pn = p.prep ? p.prep_n + nrow : nullptr;
         const E5 phi_local = load_e5(ql, p.qcs, k), phi_next = load_e5(qn, p.qcs, k);
         E5 rhs = bb::e5_zero(), phi0 = bb::e5_zero();
         for (uint32_t m = 0; m < k; m++) {
@@ -231,10 +234,15 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
                                  const vgpu_dmat* main_lde, const vgpu_dmat* perm_lde, const uint32_t cumulative_sum[5],
                                  const uint32_t perm_challenges[15], const uint32_t alpha[5], vgpu_dmat** out_chunks) {
     if (!chip || !main_lde || !perm_lde || !out_chunks) VG_FAIL(ctx, "quotient: null argument");
+    VG_TRY(vg_enter(ctx));
     const uint64_t h = 1ull << log_degree;
-    if (main_lde->h != 2 * h || perm_lde->h != 2 * h) VG_FAIL(ctx, "quotient: LDE height must be 2 * 2^log_degree");
-    if (main_lde->w != chip->width || perm_lde->w != 5 * (chip->n_interactions + 1)) VG_FAIL(ctx, "quotient: LDE width does not match the chip");
+    if (main_lde->gh != 2 * h || perm_lde->gh != 2 * h) VG_FAIL(ctx, "quotient: LDE height must be 2 * 2^log_degree");
+    if (main_lde->gw != chip->width || perm_lde->gw != 5 * (chip->n_interactions + 1)) VG_FAIL(ctx, "quotient: LDE width does not match the chip");
     if (chip->chip_id >= VGPU_NUM_CHIPS) VG_FAIL(ctx, "quotient: unknown chip id %u", chip->chip_id);
+    // split proof: the committed LDEs of a tall chip are row shards (all three the same run of rows), of a short chip whole
+    const bool split = main_lde->dist == VG_ROWS;
+    if ((perm_lde->dist == VG_ROWS) != split || (prep_lde && (prep_lde->dist == VG_ROWS) != split)) VG_FAIL(ctx, "quotient: the LDEs are not distributed alike");
+    if (main_lde->dist == VG_COLS) VG_FAIL(ctx, "quotient: column shares are internal to a commit");
     // alpha powers for N = base + k + 3 constraints
     const uint32_t N = vg_chip_base_constraints(chip->chip_id) + chip->n_interactions + 3;
     if (N > Q_MAX_CONSTRAINTS) { VG_FAIL(ctx, "quotient: %u constraints exceed the parameter table (%u)", N, Q_MAX_CONSTRAINTS); }
@@ -244,13 +252,30 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     VG_TRY(vg_build_devchip(ctx, chip, perm_challenges, &p.chip));
     E5 al; for (int i = 0; i < 5; i++) al.c[i] = bb::to_monty(alpha[i] % bb::P);
     { E5 a = bb::e5_one(); for (uint32_t i = 0; i < N; i++) { for (int l = 0; l < 5; l++) p.apow[N - 1 - i][l] = a.c[l]; a = bb::e5_mul(a, al); } }
+    p.row_begin = split ? main_lde->row0 : 0;
+    p.row_end = split ? main_lde->row0 + main_lde->h : 2 * h;
+    if ((p.row_begin & 1) || (p.row_end & 1)) VG_FAIL(ctx, "quotient: a row shard must hold whole (x, -x) pairs");
+    int next_rank = ctx->comm_rank;
+    if (split) {   // rank holding natural rows i + 2 of this shard's rows: reverse_bits((reverse_bits(rank) + 2) mod G)
+        int lg = 0; while ((1 << lg) < ctx->comm_size) lg++;
+        const uint32_t rho = bb::reverse_bits((uint32_t)ctx->comm_rank, lg);
+        next_rank = (int)bb::reverse_bits((rho + 2) & (uint32_t)(ctx->comm_size - 1), lg);
+    }
+    // virtual bases of a matrix: local rows, and the rows of `next_rank`
+    auto base_of = [&](const vgpu_dmat* m) { return m->d - (split ? m->row0 : 0); };
+    auto next_of = [&](const vgpu_dmat* m) -> const uint32_t* {
+        if (!split || next_rank == ctx->comm_rank) return base_of(m);
+        if (!m->symm) return nullptr;
+        return vg_peer_ptr(ctx, m->d, next_rank) - (uint64_t)next_rank * m->h;
+    };
     vgpu_dmat* out = nullptr;
-    VG_TRY(vg_dmat_alloc(ctx, h, 10, &out));
+    VG_TRY(split ? vg_dmat_alloc_dist(ctx, VG_ROWS, h, 10, false, &out) : vg_dmat_alloc(ctx, h, 10, &out));
     out->bitrev_rows = true;
-    p.main = main_lde->d; p.mcs = main_lde->col_stride;
-    p.prep = prep_lde ? prep_lde->d : nullptr; p.pcs = prep_lde ? prep_lde->col_stride : 0;
-    p.perm = perm_lde->d; p.qcs = perm_lde->col_stride;
-    p.out = out->d; p.ocs = out->col_stride;
+    p.main = base_of(main_lde); p.main_n = next_of(main_lde); p.mcs = main_lde->col_stride;
+    p.prep = prep_lde ? base_of(prep_lde) : nullptr; p.prep_n = prep_lde ? next_of(prep_lde) : nullptr; p.pcs = prep_lde ? prep_lde->col_stride : 0;
+    p.perm = base_of(perm_lde); p.perm_n = next_of(perm_lde); p.qcs = perm_lde->col_stride;
+    if (!p.main_n || !p.perm_n || (prep_lde && !p.prep_n)) { vgpu_dmat_free(out); VG_FAIL(ctx, "quotient: a row shard read by a peer must live in the symmetric heap"); }
+    p.out = out->d - p.row_begin / 2; p.ocs = out->col_stride;
     p.log_h = log_degree;
     p.s = bb::to_monty(bb::GEN_CANON);
     uint32_t g_sub = bb::two_adic_generator_monty((int)log_degree);
@@ -264,16 +289,14 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
     p.odd_scale = bb::mul(p.half, bb::inv(p.s));
     for (int i = 0; i < 5; i++) p.cumsum.c[i] = bb::to_monty(cumulative_sum[i] % bb::P);
     p.root_lo = ctx->root_table.lo; p.root_hi = ctx->root_table.hi;
-    const bool split = vg_split_rows(ctx, 2 * h);
-    p.row_begin = split ? (2 * h / ctx->comm_size) * ctx->comm_rank : 0;
-    p.row_end = split ? p.row_begin + 2 * h / ctx->comm_size : 2 * h;
+    const uint64_t pb = p.row_begin / 2, pc = (p.row_end - p.row_begin) / 2;     // pairs swept here
     uint32_t* selinv = nullptr;
-    VG_TRY(vg_alloc(ctx, (void**)&selinv, h * 4));
-    p.selinv = selinv;
-    KScope* ks = new KScope(ctx, KC_QUOTIENT, 8.0 * (double)h * (main_lde->w + perm_lde->w + (prep_lde ? prep_lde->w : 0)) + 40.0 * (double)h);
-    {   // pairs [row_begin / 2, row_end / 2)
-        const uint64_t pb = p.row_begin / 2, pc = (p.row_end - p.row_begin) / 2, stride = (pc + SEL_BATCH - 1) / SEL_BATCH;
-        selector_inverse_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, ctx->stream>>>(selinv, pb, pc, log_degree, p.s, p.glast, p.root_lo, p.root_hi);
+    { int32_t rc = vg_alloc(ctx, (void**)&selinv, pc * 4); if (rc) { vgpu_dmat_free(out); return rc; } }
+    p.selinv = selinv - pb;
+    KScope* ks = new KScope(ctx, KC_QUOTIENT, 4.0 * (double)(p.row_end - p.row_begin) * (main_lde->gw + perm_lde->gw + (prep_lde ? prep_lde->gw : 0)) + 20.0 * (double)(p.row_end - p.row_begin));
+    {
+        const uint64_t stride = (pc + SEL_BATCH - 1) / SEL_BATCH;
+        selector_inverse_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, ctx->stream>>>(selinv - pb, pb, pc, log_degree, p.s, p.glast, p.root_lo, p.root_hi);
         ctx->launches++;
     }
     switch (chip->chip_id) {
@@ -286,13 +309,8 @@ extern "C" int32_t vgpu_quotient(vgpu_ctx* ctx, const vgpu_chip_desc* chip, uint
         case 12: launch<12>(p, h, ctx->stream); break; case 13: launch<13>(p, h, ctx->stream); break;
     }
     delete ks;
-    VG_LAUNCH_CHECK(ctx);
-    if (split) {   // every rank wrote chunk rows [rank*h/G, (rank+1)*h/G) of each of the 10 columns
-        VG_TRY(vg_comm_group_begin(ctx));
-        for (int c = 0; c < 10; c++) VG_TRY(vg_comm_allgather_inplace(ctx, out->d + (uint64_t)c * out->col_stride, h / ctx->comm_size));
-        VG_TRY(vg_comm_group_end(ctx));
-    }
     vg_free(ctx, selinv);
+    VG_LAUNCH_CHECK(ctx);
     *out_chunks = out;
     return 0;
 }
