@@ -6,8 +6,9 @@ A "step" is one full Machine::prove() of the workload (LDE + Keccak Merkle commi
   value  : whole-job rows/s with the traces already resident in HBM (vgpu_prove_device)
   e2e    : the same metric through the reference-facing C-ABI call with HOST buffers
            (vgpu_prove: H2D of the pinned traces + D2H of the proof inside the timed region)
-  N > 1  : the path shards by independent proofs (no data-path collective): every rank proves its own
-           trace; value = rows of all ranks / max-over-ranks time ("scaling": "weak").
+  N > 1  : ONE proof per step split across the N GPUs (row shards after one peer-store exchange over NVLink,
+           sub-roots all-gathered): value = rows of that proof / max-over-ranks time ("scaling": "strong");
+           the N-independent-proofs figure is reported beside it under "replicas".
   --impl reference : the CPU restatement of the reference prover (oracle/, all host threads) on a
            bounded sample of the same workload; rank 0 only.
 """
@@ -78,15 +79,17 @@ def ncu_traffic_ratio(kernel):
         return None, None
 
 
-def aggregate_throughput(dist, rows_local, ms_local, device=None):
-    """Whole-job rows/s over all ranks: sum of rows / max-over-ranks time (each rank proves its own trace)."""
+def aggregate_throughput(dist, rows_local, ms_local, device=None, sum_rows=True):
+    """Whole-job rows/s: rows / max-over-ranks time.  sum_rows: every rank proves its own trace (replicas); otherwise all
+    ranks work on the SAME proof and the rows count once."""
     import torch
 
     t = torch.tensor([float(ms_local)], dtype=torch.float64, device=device)
     r = torch.tensor([float(rows_local)], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        if sum_rows:
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
     return float(r.item()) / (float(t.item()) / 1000.0), float(t.item())
 
 
@@ -126,66 +129,131 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def tune_oracle_threads(orc, vb):
-    """Pick the OpenMP thread count that proves a small sample fastest (large core counts oversubscribe the
-    oracle's many short parallel regions); returns the chosen count."""
-    t = vb.run_program(vb.fib_program(fib_n_for_log_rows(14)), initial_fp=0x1000)
-    best, best_n = None, None
-    cores = os.cpu_count() or 1
-    for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
-        orc.set_threads(n)
-        t0 = time.perf_counter()
-        pr = orc.prove(t.main, t.preprocessed, debug_checks=False)
-        dt = time.perf_counter() - t0
-        del pr
-        if best is None or dt < best:
-            best, best_n = dt, n
-    orc.set_threads(best_n)
-    return best_n
+def _tracegen_to_files(workload, log_rows, out_prefix):
+    """Child-process entry (python bench.py --tracegen ...): the witness generator lives in the product library, the
+    reference arm must not load it — so the traces reach the reference process as .npy files."""
+    import numpy as np
+
+    t, _, _ = build_traces(workload, log_rows)
+    for i, m in enumerate(list(t.main) + list(t.preprocessed)):
+        np.save("%s.%d.npy" % (out_prefix, i), np.ascontiguousarray(m))
+
+
+def _load_trace_files(workload, log_rows):
+    import numpy as np
+    import tempfile
+
+    d = tempfile.mkdtemp(prefix="vgpu_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    prefix = os.path.join(d, "t")
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--tracegen", prefix, "--workload", workload, "--log-rows", str(log_rows)], check=True)
+    mats = [np.load("%s.%d.npy" % (prefix, i)) for i in range(16)]
+    for i in range(16):
+        os.remove("%s.%d.npy" % (prefix, i))
+    os.rmdir(d)
+    return mats[:14], mats[14:]
 
 
 def run_reference(args, rank):
-    """Reference arm: the oracle prover (CPU restatement of the reference) on a bounded sample."""
+    """Reference arm: the CPU restatement of the reference prover (oracle/, all the host threads it can use) proving a
+    bounded sample of the arm's workload per step.  The warm-up steps double as the thread sweep — on the SAMPLE ITSELF, so the
+    timed steps run at the thread count that proved this very size fastest — and one extra proof at a larger size shows how
+    the per-row cost moves with the size (the extrapolation to the full workload is then visible, not assumed)."""
     if rank != 0:
         return
-    import valida_b200 as vb
-    from valida_b200 import build as vbuild
+    from valida_b200 import build as vbuild          # build helper only: the product library is NOT loaded in this process
     import oracle_binding
 
     vbuild.build_oracle()
     orc = oracle_binding.Oracle()
-    threads = tune_oracle_threads(orc, vb)
-    log_rows = args.ref_log_rows
-    n = fib_n_for_log_rows(log_rows)
-    t = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
-    rows = t.main[0].shape[0]
-    times = []
+    workload, full_log_rows = resolve_workload(args)
+    log_rows = min(args.ref_log_rows, full_log_rows)
+    main, prep = _load_trace_files(workload, log_rows)
+    rows = main[0].shape[0]
+    cores = os.cpu_count() or 1
+    cand = sorted({min(cores, c) for c in (16, 32, 64, cores)})
+    sweep, times = {}, []
+    threads = cand[-1]
     for i in range(args.warmup + args.steps):
+        if i < args.warmup:
+            threads_i = cand[i % len(cand)]
+        else:
+            if i == args.warmup and sweep:
+                threads = min(sweep, key=lambda k: min(sweep[k]))
+            threads_i = threads
+        orc.set_threads(threads_i)
         t0 = time.perf_counter()
-        pr = orc.prove(t.main, t.preprocessed, debug_checks=False)
+        pr = orc.prove(main, prep, debug_checks=False)
         dt = time.perf_counter() - t0
         del pr
-        if i >= args.warmup:
+        if i < args.warmup:
+            sweep.setdefault(threads_i, []).append(dt)
+        else:
             times.append(dt)
     total = sum(times)
     value = rows * len(times) / total
-    cores = threads
-    sample = "Fibonacci n=%d: 2^%d CPU rows (mem 2^%d), full prove per step; %d OpenMP threads (best of a sweep) on %d host cores" % (
-        n, log_rows, (t.main[2].shape[0]).bit_length() - 1, threads, os.cpu_count())
+    sizes = {"2^%d" % log_rows: {"rows_per_s": value, "s_per_proof": total / len(times), "threads": threads}}
+    if args.ref_extra_log_rows and args.ref_extra_log_rows <= full_log_rows and args.ref_extra_log_rows != log_rows:
+        m2, p2 = _load_trace_files(workload, args.ref_extra_log_rows)
+        orc.set_threads(threads)
+        t0 = time.perf_counter()
+        pr = orc.prove(m2, p2, debug_checks=False)
+        dt = time.perf_counter() - t0
+        del pr
+        sizes["2^%d" % args.ref_extra_log_rows] = {"rows_per_s": m2[0].shape[0] / dt, "s_per_proof": dt, "threads": threads, "proofs": 1}
+    sample = "%s at 2^%d CPU rows (one full prove per step; the arm's workload is 2^%d rows); %d OpenMP threads (fastest of %s in the warm-up steps, on this size) of %d host cores" % (
+        workload, log_rows, full_log_rows, threads, cand, cores)
     line = {
-        "impl": "reference", "metric": "trace rows/sec proven (Fibonacci)", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 (BabyBear, 31-bit modular) + ext5", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_rows), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": workload_name(workload, full_log_rows), "sample": sample, "same_config": log_rows == full_log_rows},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the real reference (Rust + un-vendored Plonky3) cannot be built here; this is oracle/, the C++ restatement, OpenMP on all host threads",
+        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()},
+        "note": "the real reference (Rust + un-vendored Plonky3) cannot be built here; this is oracle/, the C++ restatement, OpenMP; rows/s at the measured sizes are in `sizes`",
     }
     emit(line)
 
 
-def workload_name(log_rows):
-    return "Fibonacci 2^%d-row full prove (LDE+perm+quotient+FRI+Keccak Merkle), BasicMachine 14 chips, blowup 2, 40 queries" % log_rows
+METRIC = "trace rows/sec proven"
+DTYPE = "u32 (BabyBear, 31-bit modular) + ext5"
+
+
+def resolve_workload(args):
+    """--workload fib22 | fib24 | config5 | fib | config5 (+ --log-rows) -> (family, log2 CPU rows)."""
+    w = args.workload
+    if w.startswith("fib") and w[3:].isdigit():
+        return "fib", int(w[3:])
+    if w == "config5":
+        return "config5", args.log_rows
+    return w, args.log_rows
+
+
+def build_traces(workload, log_rows):
+    """Host witness of the workload (Chip::generate_trace x14): (traces, CPU rows, description)."""
+    import valida_b200 as vb
+
+    if workload == "fib":
+        n = fib_n_for_log_rows(log_rows)
+        t = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
+        what = "fib n=%d" % n
+    elif workload == "config5":
+        from programs import config5_program
+
+        iters = ((1 << log_rows) - 8) // 15
+        t = vb.run_program(config5_program(iters), initial_fp=0x1000)
+        what = "config5_program(%d)" % iters
+    else:
+        raise SystemExit("unknown workload %r" % workload)
+    rows = t.main[0].shape[0]
+    assert rows == 1 << log_rows, (rows, log_rows)
+    return t, rows, what
+
+
+def workload_name(workload, log_rows):
+    if workload == "fib":
+        return "Fibonacci 2^%d-row full prove (LDE+perm+quotient+FRI+Keccak Merkle), BasicMachine 14 chips, blowup 2, 40 queries" % log_rows
+    return "multi-chip synthetic program (add, sub, lt family, and/or/xor, memory, range; SURVEY 8(d) config 5), 2^%d CPU rows, full prove, BasicMachine 14 chips, blowup 2, 40 queries" % log_rows
 
 
 def main():
@@ -194,12 +262,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log-rows", type=int, default=22, help="log2 of the CPU-chip trace height (BASELINE config: 22)")
-    ap.add_argument("--ref-log-rows", type=int, default=18, help="bounded sample size of the CPU reference arm")
+    ap.add_argument("--workload", default="fib22", help="fib22 (BASELINE config 3, default) | fib24 (config 4) | config5 | fib / config5 with --log-rows")
+    ap.add_argument("--log-rows", type=int, default=22, help="log2 of the CPU-chip trace height for --workload fib / config5")
+    ap.add_argument("--ref-log-rows", type=int, default=18, help="bounded sample size of the CPU reference arm (one proof per step)")
+    ap.add_argument("--ref-extra-log-rows", type=int, default=20, help="reference arm: one extra proof at this size (0 = none)")
     ap.add_argument("--cpu-baseline-log-rows", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharded-timeout", type=int, default=240, help="N > 1: seconds the optional split-proof section may take")
+    ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the independent-proofs-per-GPU figure")
+    ap.add_argument("--tracegen", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.tracegen:
+        w, lr = resolve_workload(args)
+        _tracegen_to_files(w, lr, args.tracegen)
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,16 +326,17 @@ def main():
             rc[k] = c
             k += 1
     cfg = vb.StarkConfig(ctx, rc)
+    if dist is not None:
+        # N > 1: ONE proof per step, split across the ranks (row shards after one peer-store exchange; include/valida_b200.h)
+        ctx.comm_init_from_torch()
 
-    n = fib_n_for_log_rows(args.log_rows)
+    workload, log_rows = resolve_workload(args)
     t0 = time.perf_counter()
-    traces = vb.run_program(vb.fib_program(n), initial_fp=0x1000)
+    traces, rows, what = build_traces(workload, log_rows)
     tracegen_s = time.perf_counter() - t0
-    rows = traces.main[0].shape[0]
-    assert rows == 1 << args.log_rows
     trace_bytes = sum(m.nbytes for m in traces.main) + sum(m.nbytes for m in traces.preprocessed)
 
-    # pinned host copies for the e2e path; device-resident copies for `value`
+    # pinned host copies for the e2e path; device-resident copies (this rank's row shards when the proof is split) for `value`
     pinned = []
     for m in list(traces.main) + list(traces.preprocessed):
         tt = torch.empty(m.shape, dtype=torch.int32, pin_memory=True)
@@ -271,9 +347,13 @@ def main():
         main = [p.numpy().view(np.uint32) for p in pinned[:14]]
         preprocessed = [p.numpy().view(np.uint32) for p in pinned[14:]]
 
-    dm = [ctx.upload(m) for m in traces.main]
-    dp = [ctx.upload(m) for m in traces.preprocessed]
+    dm = [ctx.upload_rows(m) for m in traces.main]
+    dp = [ctx.upload_rows(m) for m in traces.preprocessed]
     ctx.synchronize()
+    # bytes a rank uploads per step on the e2e path: its rows of the tall traces, the short ones whole
+    h2d_local = 0
+    for m, d in zip(list(traces.main) + list(traces.preprocessed), dm + dp):
+        h2d_local += d.local_rows()[1] * m.shape[1] * 4
 
     def barrier():
         if dist is not None:
@@ -289,6 +369,7 @@ def main():
 
     # ---- timed: device-resident, no instrumentation ----
     launches0 = ctx.launch_count
+    ctx.comm_stats()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -299,8 +380,10 @@ def main():
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
+    comm = ctx.comm_stats()
     phases = vb.last_prove_phases(ctx)
-    value, ms_total_max = aggregate_throughput(dist, rows * args.steps, ms_total, device="cuda")
+    # one proof per step whatever N: rows proven = rows * steps, time = the slowest rank's
+    value, ms_total_max = aggregate_throughput(dist, rows * args.steps, ms_total, device="cuda", sum_rows=False)
 
     # ---- the same K steps again with a CUDA-event pair around every kernel launch (per-kernel roofline) ----
     ctx.set_kernel_timing(True)
@@ -317,7 +400,7 @@ def main():
     kstats = ctx.kernel_stats()
     ctx.set_kernel_timing(False)
 
-    # ---- timed: end to end through the host-buffer C-ABI call ----
+    # ---- timed: end to end through the host-buffer C-ABI call (every rank copies ITS rows of the pinned traces) ----
     vb.prove_machine(cfg, PinnedTraces)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -327,10 +410,47 @@ def main():
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    e2e_value, _ = aggregate_throughput(dist, rows * args.steps, ms_e2e, device="cuda")
+    e2e_value, _ = aggregate_throughput(dist, rows * args.steps, ms_e2e, device="cuda", sum_rows=False)
     assert proof_e2e == proof
+    h2d_total = h2d_local
+    proofs_identical = True
+    if dist is not None:
+        tsum = torch.tensor([float(h2d_local)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tsum)
+        h2d_total = float(tsum.item())
+        import hashlib
 
-    def make_line(sharded):
+        dig = int.from_bytes(hashlib.sha256(proof).digest()[:7], "big")
+        tmin = torch.tensor([float(dig)], dtype=torch.float64, device="cuda"); tmax = tmin.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        proofs_identical = bool(tmin.item() == tmax.item())
+
+    # ---- N > 1, beside the headline: N independent proofs (one per GPU, no collective) — the zkVM-segment throughput ----
+    replicas = None
+    if dist is not None and not args.no_replicas:
+        try:
+            ctx.set_sharding(False)
+            for m in dm + dp:
+                m.free()
+            dm = [ctx.upload(m) for m in traces.main]
+            dp = [ctx.upload(m) for m in traces.preprocessed]
+            steps_r = min(args.steps, 3)
+            for _ in range(2):
+                proof_r = vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(steps_r):
+                vb.prove_machine(cfg, traces, device_resident=(dm, dp))
+            r1.record(stream)
+            barrier()
+            rep_value, rep_ms = aggregate_throughput(dist, rows * steps_r, r0.elapsed_time(r1), device="cuda", sum_rows=True)
+            replicas = {"what": "%d independent proofs per step, one per GPU, no collective (weak scaling of the segment throughput)" % world,
+                        "rows_per_s": rep_value, "ms_per_step": rep_ms / steps_r, "proof_equals_split_proof": bool(proof_r == proof)}
+        except Exception as exc:   # noqa: BLE001
+            replicas = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    def make_line():
 
         peak, peak_src = peaks()
         kstats_sorted = sorted(kstats, key=lambda k: -k[2])
@@ -338,8 +458,12 @@ def main():
                     "algorithmic_gb_per_step": k[3] / args.steps / 1e9, "achieved_gbs": (k[3] / 1e9) / (k[2] / 1e3) if k[2] > 0 else None} for k in kstats_sorted]
         top = kstats_sorted[0]
         achieved = (top[3] / 1e9) / (top[2] / 1e3)
-        roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        keccak_top = top[0] in ("compress_layer_kernel", "leaf_hash_kernel", "fri_leaf_hash_kernel")
+        roofline = {"bound": "int_alu" if keccak_top else "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "share_of_step": top[2] / ms_instr, "ms_per_step_instrumented": ms_instr / args.steps}
+        if keccak_top:
+            roofline["bound_note"] = ("the Keccak kernels run at the INT-ALU pipe's ceiling (LOP3/SHF), not at HBM's: `frac` is the HBM fraction the contract asks for, "
+                                      "`int_alu_ceiling` is the binding one (ncu: sm__inst_executed_pipe_alu 99.8 %, DRAM 0.98 x algorithmic bytes)")
         # The Keccak kernels are bound by the INT ALU pipe, not by HBM (profiles/r01_summary.md section 4: 122 LOP3 + 58 SHF per
         # round at 63 lanes/clk/SM = 4.32 G Keccak-f/s on this part, 4.30 measured stand-alone): report that ceiling beside the HBM one.
         KECCAK_PEAK_GPERM = 4.32
@@ -421,26 +545,34 @@ def main():
 
             vbuild.build_oracle()
             orc = oracle_binding.Oracle()
-            threads = tune_oracle_threads(orc, vb)
-            nb = fib_n_for_log_rows(args.cpu_baseline_log_rows)
-            tb = vb.run_program(vb.fib_program(nb), initial_fp=0x1000)
-            t0 = time.perf_counter()
-            ref = orc.prove(tb.main, tb.preprocessed, debug_checks=False)
-            dt = time.perf_counter() - t0
-            del ref
-            cpu_baseline = {"value": tb.main[0].shape[0] / dt, "unit": "rows/s", "cores": threads, "kind": "port",
-                            "sample": "Fibonacci n=%d (2^%d CPU rows), one full oracle prove, %.1f s, %d OpenMP threads (best of a sweep) on %d host cores"
-                                      % (nb, args.cpu_baseline_log_rows, dt, threads, os.cpu_count())}
+            cbl = min(args.cpu_baseline_log_rows, log_rows)
+            tb, _, _ = build_traces(workload, cbl)
+            cores = os.cpu_count() or 1
+            best = None
+            for th in sorted({min(cores, c) for c in (16, 32, 64, cores)}):     # thread sweep on the sample itself
+                orc.set_threads(th)
+                t0 = time.perf_counter()
+                ref = orc.prove(tb.main, tb.preprocessed, debug_checks=False)
+                dt = time.perf_counter() - t0
+                del ref
+                if best is None or dt < best[0]:
+                    best = (dt, th)
+            cpu_baseline = {"value": tb.main[0].shape[0] / best[0], "unit": "rows/s", "cores": best[1], "kind": "port",
+                            "sample": "%s at 2^%d CPU rows, one full oracle prove, %.1f s, %d OpenMP threads (fastest of a sweep on this size) on %d host cores"
+                                      % (workload, cbl, best[0], best[1], cores)}
 
+        G = world
         line = {
-            "metric": "trace rows/sec proven (Fibonacci)", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 (BabyBear, 31-bit modular) + ext5", "data": "synthetic",
-            "config": {"workload": workload_name(args.log_rows), "fib_n": n, "trace_bytes": trace_bytes, "proof_bytes": len(proof),
+            "metric": METRIC + (" (Fibonacci)" if workload == "fib" else " (multi-chip program)"), "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": workload_name(workload, log_rows), "program": what, "trace_bytes": trace_bytes, "proof_bytes": len(proof),
                        "l2": "inputs (%.2f GB of traces, %.1f GB of LDEs) exceed L2" % (trace_bytes / 1e9, 4.5 * trace_bytes / 1e9),
-                       "parallelism": "independent proofs per GPU (no data-path collective)" if world > 1 else "single GPU",
+                       "parallelism": ("ONE proof per step split across %d GPUs: trace columns shard for the coset LDE, one peer-store exchange over NVLink into "
+                                       "contiguous row shards, sub-tree / quotient / openings / FRI per rank, %d x 32 B sub-roots all-gathered" % (G, G)) if G > 1 else "single GPU",
                        "host_tracegen_s": tracegen_s},
-            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": len(proof)},
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": len(proof) * G,
+                    "note": "every rank copies its rows of the tall traces (1/N of them) and the short traces whole; every rank reads the proof back"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
@@ -448,55 +580,20 @@ def main():
             "cpu_baseline": cpu_baseline,
             "phases_ms": {p[0]: p[1] for p in phases},
             "kernels": kernels,
-            "sharded": sharded,
         }
+        if G > 1:
+            per = 1.0 / args.steps
+            line["split"] = {"proof_bytes_identical_across_ranks": proofs_identical,
+                             "collectives_per_proof_rank0": {k: {"calls": v[0] * per, "mb_to_peers": v[1] * per / 1e6} for k, v in comm.items()},
+                             "note": "exchange = kernels storing through peer pointers (rows->columns before the LDE, extended columns->row shards after it); "
+                                     "allgather = sub-roots, LogUp totals, per-rank column sums, the FRI layer that stops being split, the opened rows; ms in `kernels`"}
+            line["replicas"] = replicas
         return line
 
-    # ---- N > 1: the SAME single proof split across the ranks (column shares for the LDE, leaf/layer shares for the
-    # Keccak trees, NCCL exchange over NVLink) — latency of one proof on N GPUs, beside the replica throughput.
-    # The figure is extra to the contract line: a failure is reported inside `sharded`, and a watchdog gives the line out
-    # without it if the section does not finish (a hung collective must not lose the replica measurement above). ----
-    sharded = None
+    if rank == 0:
+        emit(make_line())
     if dist is not None:
-        done = threading.Event()
-
-        def watchdog():
-            if not done.wait(args.sharded_timeout):
-                if rank == 0:
-                    emit(make_line({"error": "split-proof section did not finish within %d s" % args.sharded_timeout}))
-                os._exit(0)
-
-        threading.Thread(target=watchdog, daemon=True).start()
-        try:
-            ctx.comm_init_from_torch()
-            for _ in range(2):
-                proof_sh = vb.prove_machine(cfg, traces, device_resident=(dm, dp))
-            identical = proof_sh == proof
-            barrier()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(stream)
-            for _ in range(args.steps):
-                vb.prove_machine(cfg, traces, device_resident=(dm, dp))
-            s1.record(stream)
-            barrier()
-            ms_sh = s0.elapsed_time(s1)
-            sh_phases = vb.last_prove_phases(ctx)
-            _, ms_sh_max = aggregate_throughput(dist, rows * args.steps, ms_sh, device="cuda")
-            ctx.set_sharding(False)
-            sharded = {"what": "ONE proof per step split across %d GPUs (strong scaling of a single proof)" % world,
-                       "ms_per_proof": ms_sh_max / args.steps, "rows_per_s": rows * args.steps / (ms_sh_max / 1e3),
-                       "proof_bytes_identical": bool(identical), "phases_ms": {k: v for k, v in sh_phases}}
-        except Exception as exc:   # noqa: BLE001
-            sharded = {"error": "%s: %s" % (type(exc).__name__, exc)}
-        finally:
-            done.set()
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    emit(make_line(sharded))
-    if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

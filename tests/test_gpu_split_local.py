@@ -69,6 +69,18 @@ def test_split_prove_bytes_identical(oracle, fib15, fib15_proof, nranks):
         _close(ctxs)
 
 
+def test_split_prove_reserves_the_whole_proof(oracle, fib15, fib15_proof, monkeypatch):
+    """With no floor under the symmetric heap the first proof must size it for all three commits at once."""
+    import valida_b200 as vb
+
+    monkeypatch.setenv("VGPU_SYMM_HEAP_MIN_MB", "1")
+    ctxs, cfgs = _group(2, oracle)
+    try:
+        assert all(p == fib15_proof for p in vb.run_ranks(lambda r, c: vb.prove_machine(cfgs[r], fib15), ctxs))
+    finally:
+        _close(ctxs)
+
+
 def test_split_prove_device_resident_inputs(oracle, fib15, fib15_proof):
     """vgpu_prove_device on whole traces (every rank holds all rows) and on row shards (vgpu_dmat_upload_rows)."""
     import valida_b200 as vb

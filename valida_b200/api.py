@@ -208,6 +208,12 @@ class DeviceMatrix:
         lib().vgpu_dmat_dims(self._h, C.byref(h), C.byref(w))
         return int(h.value), int(w.value)
 
+    def local_rows(self):
+        """(first row, rows) held on this rank — the whole matrix unless it is a row shard of a split proof."""
+        r0, n = C.c_uint64(), C.c_uint64()
+        lib().vgpu_dmat_local_rows(self._h, C.byref(r0), C.byref(n))
+        return int(r0.value), int(n.value)
+
     def download(self, repr=REPR_CANONICAL):
         h, w = self.shape
         out = np.empty((h, w), dtype=np.uint32)

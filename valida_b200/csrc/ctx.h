@@ -22,7 +22,7 @@ struct PowTable {            // device tables of Montgomery words
 };
 
 // kernel classes for the optional per-launch CUDA-event timing (bench.py's roofline line)
-enum KClass { KC_NTT = 0, KC_LEAF_HASH, KC_COMPRESS, KC_FRI_LEAF, KC_TRANSPOSE, KC_PERM, KC_QUOTIENT, KC_INVDEN, KC_BARY, KC_REDUCED_OPENING, KC_FRI_FOLD, KC_EXCHANGE, KC_OTHER, KC_COUNT };
+enum KClass { KC_NTT = 0, KC_LEAF_HASH, KC_COMPRESS, KC_FRI_LEAF, KC_TRANSPOSE, KC_PERM, KC_QUOTIENT, KC_INVDEN, KC_BARY, KC_REDUCED_OPENING, KC_FRI_FOLD, KC_EXCHANGE, KC_COLLECTIVE, KC_OTHER, KC_COUNT };
 struct KTimer { cudaEvent_t a, b; int cls; double bytes; };
 
 struct vgpu_ctx {
@@ -103,7 +103,7 @@ struct vgpu_dmat {
 
 // RAII scope: when ctx->ktiming is on, brackets the launches inside it with a CUDA event pair on ctx->stream.
 struct KScope {
-    vgpu_ctx* ctx; bool on;
+    vgpu_ctx* ctx; bool on; size_t idx = 0;      // scopes nest (a collective inside a sweep): each closes ITS pair
     KScope(vgpu_ctx* c, int cls, double bytes) : ctx(c), on(c->ktiming) {
         if (!on) return;
         KTimer t; t.cls = cls; t.bytes = bytes;
@@ -113,8 +113,9 @@ struct KScope {
         }
         cudaEventRecord(t.a, c->stream);
         c->ktimers.push_back(t);
+        idx = c->ktimers.size() - 1;
     }
-    ~KScope() { if (on) cudaEventRecord(ctx->ktimers.back().b, ctx->stream); }
+    ~KScope() { if (on) cudaEventRecord(ctx->ktimers[idx].b, ctx->stream); }
 };
 
 int32_t vg_enter(vgpu_ctx* ctx);                          // make ctx->device current on the calling thread

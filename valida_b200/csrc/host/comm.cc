@@ -123,6 +123,7 @@ int32_t vg_comm_group_end(vgpu_ctx* ctx) { if (ctx->nccl) VG_NCCL(ctx, nccl().Gr
 int32_t vg_comm_barrier(vgpu_ctx* ctx) {
     if (ctx->comm_size <= 1) return 0;
     ctx->stat_barrier.calls++;
+    KScope ks(ctx, KC_COLLECTIVE, 0.0);
     if (ctx->local_group) return local_barrier(ctx);
     // an all-gather of one word per rank: completes on a rank only after every rank has enqueued it behind its earlier work
     VG_NCCL(ctx, nccl().AllGather(ctx->comm_scratch + ctx->comm_rank, ctx->comm_scratch, 1, ncclUint32, (ncclComm_t)ctx->nccl, ctx->stream));
@@ -132,6 +133,7 @@ int32_t vg_comm_barrier(vgpu_ctx* ctx) {
 int32_t vg_comm_allgather_inplace(vgpu_ctx* ctx, uint32_t* buf, uint64_t words_per_rank) {
     if (ctx->comm_size <= 1 || !words_per_rank) return 0;
     ctx->stat_allgather.calls++; ctx->stat_allgather.bytes += 4.0 * (double)words_per_rank * (ctx->comm_size - 1);
+    KScope ks(ctx, KC_COLLECTIVE, 4.0 * (double)words_per_rank * (ctx->comm_size - 1));
     if (ctx->nccl) {
         VG_NCCL(ctx, nccl().AllGather(buf + (uint64_t)ctx->comm_rank * words_per_rank, buf, words_per_rank, ncclUint32, (ncclComm_t)ctx->nccl, ctx->stream));
         return 0;
@@ -201,7 +203,9 @@ int32_t vg_symm_reserve(vgpu_ctx* ctx, size_t extra_bytes) {
         VG_FAIL(ctx, "symmetric heap: %zu MB live + %zu MB requested exceed the %zu MB heap and it cannot grow while buffers are live (set VGPU_SYMM_HEAP_MB)",
                 ctx->symm_live_bytes >> 20, extra_bytes >> 20, ctx->symm_bytes >> 20);
     size_t bytes = need + need / 8;
-    if (bytes < ((size_t)512 << 20)) bytes = (size_t)512 << 20;      // floor: small commits one after the other never regrow
+    size_t floor_mb = 512;                                            // floor: small commits one after the other never regrow
+    if (const char* e = getenv("VGPU_SYMM_HEAP_MIN_MB")) floor_mb = (size_t)atoll(e);
+    if (bytes < (floor_mb << 20)) bytes = floor_mb << 20;
     if (const char* e = getenv("VGPU_SYMM_HEAP_MB")) { const size_t v = (size_t)atoll(e) << 20; if (v > bytes) bytes = v; }
     bytes = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
     // quiesce: peers may still be reading the old heap

@@ -421,6 +421,20 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
         log_degrees[i] = log2u(main[i]->gh);
         if ((1ull << log_degrees[i]) != main[i]->gh) VG_FAIL(ctx, "prove: chip %d trace height is not a power of two", i);
     }
+    if (vg_sharded(ctx)) {
+        // Split proof: room in the symmetric heap for everything the three commits put there — the row shards of every tall
+        // chip's main / permutation / quotient LDEs and the column buffers of the rows -> columns hand-over (counted as if never
+        // released: first-fit then always finds a run) — reserved ONCE, before the first shard is live.
+        const uint64_t G = (uint64_t)ctx->comm_size;
+        size_t need = 0;
+        for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
+            const uint64_t h = main[i]->gh;
+            if (!vg_split_rows(ctx, 2 * h)) continue;
+            const uint64_t widths[4] = {chips[i]->width, 5ull * (chips[i]->n_interactions + 1), 10, chips[i]->preprocessed_width};
+            for (uint64_t w : widths) if (w) need += vg_symm_round((2 * h / G) * w * 4) + vg_symm_round(h * ((w + G - 1) / G) * 4);
+        }
+        if (need) VG_TRY(vg_symm_reserve(ctx, need));
+    }
     vgh::Challenger ch;
     { delete (vgh::Poseidon16*)ctx->poseidon; ctx->poseidon = nullptr; }
     ch.perm = poseidon_of(ctx);

@@ -256,7 +256,7 @@ int32_t vg_perm_trace_enqueue(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const v
     const uint32_t* pd = prep_or_null ? rows_of(prep_or_null) : nullptr;
     uint64_t pcs = prep_or_null ? prep_or_null->col_stride : 0;
     unsigned blocks = (unsigned)((h + 255) / 256);
-    KScope ks(ctx, KC_PERM, 4.0 * (double)h * (chip->width + 5.0 * (k + 1)));
+    auto ks = std::make_unique<KScope>(ctx, KC_PERM, 4.0 * (double)h * (chip->width + 5.0 * (k + 1)));
     if (k) {
         perm_denominators_kernel<<<blocks, 256, 0, ctx->stream>>>(dchip, md, main->col_stride, pd, pcs, h, perm->d, perm->col_stride);
         VG_LAUNCH_CHECK(ctx);
@@ -268,8 +268,10 @@ int32_t vg_perm_trace_enqueue(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const v
     VG_TRY(vg_prefix_sum_columns(ctx, phi, perm->col_stride, h, 5));
     perm_totals_kernel<<<1, 32, 0, ctx->stream>>>(phi, perm->col_stride, h, d_totals + (split ? 5 * ctx->comm_rank : 0));
     VG_LAUNCH_CHECK(ctx);
+    ks.reset();
     if (split) {
         VG_TRY(vg_comm_allgather_inplace(ctx, d_totals, 5));
+        KScope ks2(ctx, KC_PERM, 0.0);
         scan_add_rank_offset_kernel<<<dim3(blocks, 5), 256, 0, ctx->stream>>>(phi, perm->col_stride, h, d_totals, (uint32_t)ctx->comm_rank);
         VG_LAUNCH_CHECK(ctx);
     }
