@@ -358,6 +358,8 @@ static inline int verify_constraints(const ChipDef& chip, const ChipOpenedValues
 static inline int machine_verify(const MachineProof& proof, const Matrix& program_prep, const Matrix& range_prep, const Poseidon16& perm16) {
     const auto& cd = chips();
     if (proof.chip_proofs.size() != (size_t)NUM_CHIPS) return -1;
+    // chips with preprocessed columns (program ROM, range table) have the height of those columns
+    if (((size_t)1 << proof.chip_proofs[1].log_degree) != program_prep.height() || ((size_t)1 << proof.chip_proofs[12].log_degree) != range_prep.height()) return -1;
     Pcs pcs;
     Challenger ch(&perm16);
     PcsData prep_data = pcs.commit_batches({program_prep, range_prep});

@@ -281,6 +281,9 @@ struct Pcs {
                 index = index_pair;
                 x = mul(x, x);
             }
+            // reduced openings of the height-2 LDEs (one-row traces: constant polynomials, exactly 0 when honest) are added by
+            // the prover's last fold but never reached by the loop above: bind them here
+            if (!ro[fri.log_blowup].is_zero()) return -5;
             if (folded != proof.fri.final_poly) return -5;
         }
         return 0;

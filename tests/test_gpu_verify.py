@@ -66,7 +66,21 @@ TAMPERS = {
     "input_path": lambda d: _flip(d["opening_proof"]["query_openings"][7][2]["opening_proof"][1][3]),
     "log_degree": lambda d: d["chip_proofs"][3].__setitem__("log_degree", d["chip_proofs"][3]["log_degree"] + 1),
     "drop_query": lambda d: d["opening_proof"]["query_openings"].pop(),
+    # one-row chips (height-2 LDEs, folded by no FRI round) and the heights of the chips with preprocessed columns
+    "one_row_chip_trace": lambda d: _flip(d["chip_proofs"][13]["opened_values"]["trace_local"][2]["value"][0]),
+    "one_row_chip_perm": lambda d: _flip(d["chip_proofs"][11]["opened_values"]["permutation_local"][0]["value"][0]),
+    "one_row_chip_quotient": lambda d: _flip(d["chip_proofs"][9]["opened_values"]["quotient_chunks"][3]["value"][0]),
+    "program_log_degree": lambda d: d["chip_proofs"][1].__setitem__("log_degree", 0),
+    "range_log_degree": lambda d: d["chip_proofs"][12].__setitem__("log_degree", 0),
 }
+
+
+def test_one_row_chips_are_bound_by_the_opening_check(fib25):
+    vb, cfg, t, proof = fib25
+    for what in ("one_row_chip_trace", "one_row_chip_perm", "one_row_chip_quotient"):
+        d = cbor2.loads(proof)
+        TAMPERS[what](d)
+        assert product_verdict(vb, cfg, cbor2.dumps(d), t.preprocessed) == -6, what      # VGPU_REJECT_FRI_FINAL, not a later check
 
 
 @pytest.mark.parametrize("what", sorted(TAMPERS))

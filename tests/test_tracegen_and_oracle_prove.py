@@ -106,6 +106,23 @@ def test_verifier_rejects_tampering(fib25, oracle):
     assert oracle.verify(pr.cbor(), fib25.preprocessed) != 0
 
 
+def test_verifier_binds_one_row_chips_and_preprocessed_heights(fib25, oracle):
+    """A chip with a ONE-row trace has height-2 LDEs whose reduced openings no FRI round folds; the verifier must still
+    check them (they are exactly 0 for an honest proof), or the opened values and the cumulative sum of such a chip are
+    free — eight of the fourteen chips in a Fibonacci proof.  Likewise the program / range chips keep the height of
+    their preprocessed columns."""
+    proof = oracle.prove(fib25.main, fib25.preprocessed, debug_checks=False).cbor()
+    assert fib25.main[13].shape[0] == 1 and fib25.main[6].shape[0] == 1
+    for chip, which, col in ((13, "trace_local", 2), (6, "trace_next", 5), (11, "permutation_local", 0), (9, "quotient_chunks", 3)):
+        d = cbor2.loads(proof)
+        _flip_value(d, ["chip_proofs", chip, "opened_values", which, col, "value", 0])
+        assert oracle.verify(cbor2.dumps(d), fib25.preprocessed) == -5, (chip, which)      # the opening check itself, not a later one
+    for chip in (1, 12):
+        d = cbor2.loads(proof)
+        d["chip_proofs"][chip]["log_degree"] = 0
+        assert oracle.verify(cbor2.dumps(d), fib25.preprocessed) == -1
+
+
 # ---- the reference's other proving tests (basic/tests/test_prover.rs:490-625), via tests/golden/programs.json ----
 import json
 import os

@@ -46,6 +46,7 @@ struct vgpu_ctx {
     std::vector<std::pair<const char*, float>> phases;          // last prove: per-phase milliseconds
     struct PhaseMark { const char* name; cudaEvent_t a, b; };
     std::vector<PhaseMark> phase_marks;                         // event pairs of the last prove (read by vgpu_last_prove_phases)
+    std::vector<std::pair<const char*, float>> host_phases;     // host-side stretches of the last prove (wall clock)
     bool in_host_prove = false;
     // size-keyed cache of device buffers: a proof repeats the same allocation sizes every step, so after the
     // first step no driver allocator call is made (single stream => reuse in enqueue order is safe)

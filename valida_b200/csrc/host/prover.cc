@@ -37,6 +37,37 @@ struct OpeningH {
 };
 struct OpenRound { const vgpu_prover_data* pd; std::vector<std::vector<E5>> points; };
 
+// Device time of a phase: an event pair on the context's stream, read back by vgpu_last_prove_phases — no host
+// synchronisation inside the proof.
+struct Phase {
+    vgpu_ctx* ctx;
+    static cudaEvent_t ev(vgpu_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e);
+        return e;
+    }
+    Phase(vgpu_ctx* c, const char* n) : ctx(c) {
+        vgpu_ctx::PhaseMark m; m.name = n; m.a = ev(c); m.b = ev(c);
+        cudaEventRecord(m.a, c->stream);
+        c->phase_marks.push_back(m);
+        idx = c->phase_marks.size() - 1;
+    }
+    ~Phase() { cudaEventRecord(ctx->phase_marks[idx].b, ctx->stream); }
+    size_t idx;
+};
+// host-side stretches between device work (pointer lists, CBOR): wall-clock, reported beside the device phases
+struct HostPhase {
+    vgpu_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
+    HostPhase(vgpu_ctx* c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
+    ~HostPhase() { ctx->host_phases.push_back({name, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count()}); }
+};
+void phases_reset(vgpu_ctx* ctx) {
+    for (auto& m : ctx->phase_marks) { ctx->event_pool.push_back(m.a); ctx->event_pool.push_back(m.b); }
+    ctx->phase_marks.clear();
+    ctx->phases.clear();
+    ctx->host_phases.clear();
+}
+
 // An ext5 vector over the rows of one LDE height (reduced openings, inverse denominators, FRI layers): limb-major.
 // Split proof: a vector of a height whose matrices are row shards holds this rank's run [begin, begin + count) only.
 struct RowVec {
@@ -206,11 +237,12 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
                 if (fin[l * cur.n + i] != f0.c[l]) VG_FAIL(ctx, "FRI: final layer is not constant (the committed functions are not low degree)");
         out->fri.final_poly = canon(f0);
     }
-    out->fri.pow_witness = bb::from_monty(ch.grind(POW_BITS));
+    { HostPhase hp(ctx, "host: proof-of-work grind"); out->fri.pow_witness = bb::from_monty(ch.grind(POW_BITS)); }
     std::vector<uint64_t> indices;
     for (int q = 0; q < NUM_QUERIES; q++) indices.push_back(ch.sample_bits(log_max));
 
     // ---- query phase: one gather for every word the proof needs (split proof: every rank reports the words it holds) ------
+    HostPhase hq(ctx, "host+device: query phase (pointer list, gather, answers)");
     std::vector<const uint32_t*> ptrs;
     auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) ptrs.push_back(d ? d + k : nullptr); };
     for (uint64_t index : indices) {
@@ -303,30 +335,6 @@ void write_opening_proof(Cbor& w, const OpeningH& op) {
             w.key("opening_proof"); w.digests(bo.opening_proof);
         }
     }
-}
-
-// Device time of a phase: an event pair on the context's stream, read back by vgpu_last_prove_phases — no host
-// synchronisation inside the proof.
-struct Phase {
-    vgpu_ctx* ctx;
-    static cudaEvent_t ev(vgpu_ctx* c) {
-        cudaEvent_t e = nullptr;
-        if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e);
-        return e;
-    }
-    Phase(vgpu_ctx* c, const char* n) : ctx(c) {
-        vgpu_ctx::PhaseMark m; m.name = n; m.a = ev(c); m.b = ev(c);
-        cudaEventRecord(m.a, c->stream);
-        c->phase_marks.push_back(m);
-        idx = c->phase_marks.size() - 1;
-    }
-    ~Phase() { cudaEventRecord(ctx->phase_marks[idx].b, ctx->stream); }
-    size_t idx;
-};
-void phases_reset(vgpu_ctx* ctx) {
-    for (auto& m : ctx->phase_marks) { ctx->event_pool.push_back(m.a); ctx->event_pool.push_back(m.b); }
-    ctx->phase_marks.clear();
-    ctx->phases.clear();
 }
 
 vgh::Poseidon16* poseidon_of(vgpu_ctx* ctx) {
@@ -521,6 +529,7 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
         VG_TRY(open_multi_batches(ctx, rounds, ch, &op));
     }
     // MachineProof -> CBOR
+    HostPhase hc(ctx, "host: MachineProof -> CBOR");
     Cbor w;
     w.map(3);
     w.key("commitments"); w.map(3);
@@ -595,6 +604,8 @@ uint32_t vgpu_last_prove_phases(const vgpu_ctx* cctx, const char** names, float*
         ctx->event_pool.push_back(m.a); ctx->event_pool.push_back(m.b);
     }
     ctx->phase_marks.clear();
+    for (auto& hp : ctx->host_phases) ctx->phases.push_back(hp);
+    ctx->host_phases.clear();
     uint32_t n = (uint32_t)ctx->phases.size();
     for (uint32_t i = 0; i < n && i < cap; i++) { names[i] = ctx->phases[i].first; ms[i] = ctx->phases[i].second; }
     return n;

@@ -283,6 +283,10 @@ int32_t verify_openings(const std::vector<RoundV>& rounds, const ProofV& pf, vgh
             index = pair;
             x = bb::sqr(x);
         }
+        // The prover's last fold also adds the reduced openings of the height-2 LDEs (traces of ONE row: constant polynomials,
+        // for which (p(x) - p(z)) / (x - z) is exactly 0).  The loop above never reaches them, so they are checked here: without
+        // this the opened values of every one-row chip — and with them its cumulative sum — would be bound by nothing.
+        if (!bb::e5_is_zero(ro[LOG_BLOWUP])) return VGPU_REJECT_FRI_FINAL;
         for (int l = 0; l < 5; l++) if (folded.c[l] != pf.final_poly.c[l]) return VGPU_REJECT_FRI_FINAL;
     }
     return VGPU_ACCEPT;
@@ -299,6 +303,9 @@ extern "C" int32_t vgpu_verify(vgpu_ctx* ctx, const uint8_t* proof, uint64_t pro
     if (!decode(proof, proof_len, &pf)) return 0;
     if (pf.chips.size() != (size_t)VGPU_NUM_CHIPS) { *verdict = VGPU_REJECT_SHAPE; return 0; }
     for (auto& c : pf.chips) if (c.log_degree > (uint32_t)MAX_LOG_DEGREE || c.n_prep_local || c.n_prep_next) { *verdict = VGPU_REJECT_SHAPE; return 0; }
+    // the two chips with preprocessed columns have the height of those columns (program ROM, range table): a proof may not
+    // shrink them (an all-one-row proof has no FRI layers at all)
+    if ((1ull << pf.chips[1].log_degree) != prep[0].height || (1ull << pf.chips[12].log_degree) != prep[1].height) { *verdict = VGPU_REJECT_SHAPE; return 0; }
 
     vgh::Poseidon16 perm;
     perm.set(ctx->poseidon_rc, ctx->poseidon_has_mds ? ctx->poseidon_mds : nullptr);

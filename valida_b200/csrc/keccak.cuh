@@ -57,52 +57,61 @@ __device__ __forceinline__ uint2 x5(uint2 a, uint2 b, uint2 c, uint2 d, uint2 e)
 __device__ __forceinline__ uint2 chi(uint2 a, uint2 b, uint2 c) { return make_uint2(a.x ^ (~b.x & c.x), a.y ^ (~b.y & c.y)); }
 
 // State lane (x, y) lives in A[x + 5 y].
-__device__ __forceinline__ void keccak_f(uint2 A[25]) {
-#pragma unroll 1
-    for (int round = 0; round < 24; round++) {
-        uint2 C0 = x5(A[0], A[5], A[10], A[15], A[20]);
-        uint2 C1 = x5(A[1], A[6], A[11], A[16], A[21]);
-        uint2 C2 = x5(A[2], A[7], A[12], A[17], A[22]);
-        uint2 C3 = x5(A[3], A[8], A[13], A[18], A[23]);
-        uint2 C4 = x5(A[4], A[9], A[14], A[19], A[24]);
-        const uint2 R0 = rol<1>(C1), R1 = rol<1>(C2), R2 = rol<1>(C3), R3 = rol<1>(C4), R4 = rol<1>(C0);
-        // D[x] = C[x-1] ^ rol(C[x+1], 1) is folded into the 3-input xor with the lane (one LOP3 per half)
-        // theta + rho + pi:  B[y, 2x+3y] = rol(A[x,y] ^ D[x], r[x,y])
-        uint2 B0 = x3(A[0], C4, R0);
-        uint2 B10 = rol<1>(x3(A[1], C0, R1));
-        uint2 B20 = rol<62>(x3(A[2], C1, R2));
-        uint2 B5 = rol<28>(x3(A[3], C2, R3));
-        uint2 B15 = rol<27>(x3(A[4], C3, R4));
-        uint2 B16 = rol<36>(x3(A[5], C4, R0));
-        uint2 B1 = rol<44>(x3(A[6], C0, R1));
-        uint2 B11 = rol<6>(x3(A[7], C1, R2));
-        uint2 B21 = rol<55>(x3(A[8], C2, R3));
-        uint2 B6 = rol<20>(x3(A[9], C3, R4));
-        uint2 B7 = rol<3>(x3(A[10], C4, R0));
-        uint2 B17 = rol<10>(x3(A[11], C0, R1));
-        uint2 B2 = rol<43>(x3(A[12], C1, R2));
-        uint2 B12 = rol<25>(x3(A[13], C2, R3));
-        uint2 B22 = rol<39>(x3(A[14], C3, R4));
-        uint2 B23 = rol<41>(x3(A[15], C4, R0));
-        uint2 B8 = rol<45>(x3(A[16], C0, R1));
-        uint2 B18 = rol<15>(x3(A[17], C1, R2));
-        uint2 B3 = rol<21>(x3(A[18], C2, R3));
-        uint2 B13 = rol<8>(x3(A[19], C3, R4));
-        uint2 B14 = rol<18>(x3(A[20], C4, R0));
-        uint2 B24 = rol<2>(x3(A[21], C0, R1));
-        uint2 B9 = rol<61>(x3(A[22], C1, R2));
-        uint2 B19 = rol<56>(x3(A[23], C2, R3));
-        uint2 B4 = rol<14>(x3(A[24], C3, R4));
-        // chi
-        A[0] = chi(B0, B1, B2); A[1] = chi(B1, B2, B3); A[2] = chi(B2, B3, B4); A[3] = chi(B3, B4, B0); A[4] = chi(B4, B0, B1);
-        A[5] = chi(B5, B6, B7); A[6] = chi(B6, B7, B8); A[7] = chi(B7, B8, B9); A[8] = chi(B8, B9, B5); A[9] = chi(B9, B5, B6);
-        A[10] = chi(B10, B11, B12); A[11] = chi(B11, B12, B13); A[12] = chi(B12, B13, B14); A[13] = chi(B13, B14, B10); A[14] = chi(B14, B10, B11);
-        A[15] = chi(B15, B16, B17); A[16] = chi(B16, B17, B18); A[17] = chi(B17, B18, B19); A[18] = chi(B18, B19, B15); A[19] = chi(B19, B15, B16);
-        A[20] = chi(B20, B21, B22); A[21] = chi(B21, B22, B23); A[22] = chi(B22, B23, B24); A[23] = chi(B23, B24, B20); A[24] = chi(B24, B20, B21);
-        // iota
-        uint2 rc = RC[round];
-        A[0].x ^= rc.x; A[0].y ^= rc.y;
-    }
+__device__ __forceinline__ void keccak_round(uint2 A[25], const uint2 rc) {
+    uint2 C0 = x5(A[0], A[5], A[10], A[15], A[20]);
+    uint2 C1 = x5(A[1], A[6], A[11], A[16], A[21]);
+    uint2 C2 = x5(A[2], A[7], A[12], A[17], A[22]);
+    uint2 C3 = x5(A[3], A[8], A[13], A[18], A[23]);
+    uint2 C4 = x5(A[4], A[9], A[14], A[19], A[24]);
+    const uint2 R0 = rol<1>(C1), R1 = rol<1>(C2), R2 = rol<1>(C3), R3 = rol<1>(C4), R4 = rol<1>(C0);
+    // D[x] = C[x-1] ^ rol(C[x+1], 1) is folded into the 3-input xor with the lane (one LOP3 per half)
+    // theta + rho + pi:  B[y, 2x+3y] = rol(A[x,y] ^ D[x], r[x,y])
+    uint2 B0 = x3(A[0], C4, R0);
+    uint2 B10 = rol<1>(x3(A[1], C0, R1));
+    uint2 B20 = rol<62>(x3(A[2], C1, R2));
+    uint2 B5 = rol<28>(x3(A[3], C2, R3));
+    uint2 B15 = rol<27>(x3(A[4], C3, R4));
+    uint2 B16 = rol<36>(x3(A[5], C4, R0));
+    uint2 B1 = rol<44>(x3(A[6], C0, R1));
+    uint2 B11 = rol<6>(x3(A[7], C1, R2));
+    uint2 B21 = rol<55>(x3(A[8], C2, R3));
+    uint2 B6 = rol<20>(x3(A[9], C3, R4));
+    uint2 B7 = rol<3>(x3(A[10], C4, R0));
+    uint2 B17 = rol<10>(x3(A[11], C0, R1));
+    uint2 B2 = rol<43>(x3(A[12], C1, R2));
+    uint2 B12 = rol<25>(x3(A[13], C2, R3));
+    uint2 B22 = rol<39>(x3(A[14], C3, R4));
+    uint2 B23 = rol<41>(x3(A[15], C4, R0));
+    uint2 B8 = rol<45>(x3(A[16], C0, R1));
+    uint2 B18 = rol<15>(x3(A[17], C1, R2));
+    uint2 B3 = rol<21>(x3(A[18], C2, R3));
+    uint2 B13 = rol<8>(x3(A[19], C3, R4));
+    uint2 B14 = rol<18>(x3(A[20], C4, R0));
+    uint2 B24 = rol<2>(x3(A[21], C0, R1));
+    uint2 B9 = rol<61>(x3(A[22], C1, R2));
+    uint2 B19 = rol<56>(x3(A[23], C2, R3));
+    uint2 B4 = rol<14>(x3(A[24], C3, R4));
+    // chi
+    A[0] = chi(B0, B1, B2); A[1] = chi(B1, B2, B3); A[2] = chi(B2, B3, B4); A[3] = chi(B3, B4, B0); A[4] = chi(B4, B0, B1);
+    A[5] = chi(B5, B6, B7); A[6] = chi(B6, B7, B8); A[7] = chi(B7, B8, B9); A[8] = chi(B8, B9, B5); A[9] = chi(B9, B5, B6);
+    A[10] = chi(B10, B11, B12); A[11] = chi(B11, B12, B13); A[12] = chi(B12, B13, B14); A[13] = chi(B13, B14, B10); A[14] = chi(B14, B10, B11);
+    A[15] = chi(B15, B16, B17); A[16] = chi(B16, B17, B18); A[17] = chi(B17, B18, B19); A[18] = chi(B18, B19, B15); A[19] = chi(B19, B15, B16);
+    A[20] = chi(B20, B21, B22); A[21] = chi(B21, B22, B23); A[22] = chi(B22, B23, B24); A[23] = chi(B23, B24, B20); A[24] = chi(B24, B20, B21);
+    // iota
+    A[0].x ^= rc.x; A[0].y ^= rc.y;
 }
+
+// FIRST: round 0 stands outside the loop, so lanes the caller set to literal zeros (the capacity, and most of the rate of a
+// 64-byte compression) are folded away by the compiler.  LAST: round 23 stands outside the loop and the caller reads only
+// A[0..3] (a 256-bit digest): chi / rho / pi of the other 21 lanes are dead code there.  Both leave the permutation's
+// value unchanged — they only expose what the generic loop hides from the optimiser.
+template <bool FIRST, bool LAST>
+__device__ __forceinline__ void keccak_f_peeled(uint2 A[25]) {
+    if (FIRST) keccak_round(A, make_uint2(0x00000001u, 0x00000000u));
+#pragma unroll 1
+    for (int round = FIRST ? 1 : 0; round < (LAST ? 23 : 24); round++) keccak_round(A, RC[round]);
+    if (LAST) keccak_round(A, make_uint2(0x80008008u, 0x80000000u));
+}
+__device__ __forceinline__ void keccak_f(uint2 A[25]) { keccak_f_peeled<false, false>(A); }
 
 }  // namespace kk
