@@ -4,10 +4,7 @@ import pytest
 
 import programs
 
-# Written after this round's GPU budget was spent: the CPU half (tests/test_static_data.py: witness generation, oracle proof with
-# the reference's debug invariants, verifier) is green, the GPU half below has its FIRST run at the round-end driver pass.  It is
-# therefore marked non-strict xfail — an XPASS in the report means the parity holds; the marker goes away once that is seen.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run happens at round end (added with no GPU minutes left)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_prove_static_data_bytes_equal_oracle_and_verify(ctx, oracle):

@@ -1,6 +1,7 @@
 // C ABI entry points (include/valida_b200.h): context, device matrices, NTT/LDE, commit.
 #include "ctx.h"
 #include "merkle.h"
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -157,6 +158,7 @@ void vgpu_ctx_destroy(vgpu_ctx* ctx) {
         for (auto& kv : ctx->live_bufs) cudaFree(kv.first);
         for (auto e : ctx->event_pool) cudaEventDestroy(e);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->xfer_stream) { cudaStreamDestroy(ctx->xfer_stream); for (auto e : ctx->xfer_ev) if (e) cudaEventDestroy(e); }
         if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -313,6 +315,24 @@ static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat
         moved = true;
     }
     if (moved) VG_TRY(vg_comm_barrier(ctx));
+    // (2) extend the column share of matrix k on the context's stream while the exchange of matrix k-1 runs on a second
+    // stream: the LDE kernels are issue bound, the exchange is NVLink bound.  Two extension buffers alternate; a buffer is
+    // rewritten only after its exchange has finished.  (With per-kernel timing on everything stays on one stream.)
+    const bool overlap = !ctx->ktiming;
+    if (overlap && !ctx->xfer_stream) {
+        VG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->xfer_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->xfer_ev) VG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    size_t ext_words = 0;
+    for (size_t i : tall) {
+        uint64_t c0, c1;
+        vg_shard_range(mats[i]->gw, (int)G, ctx->comm_rank, &c0, &c1);
+        ext_words = std::max<size_t>(ext_words, 2 * mats[i]->gh * (c1 - c0));
+    }
+    uint32_t* ext[2] = {nullptr, nullptr};
+    struct ExtGuard { vgpu_ctx* c; uint32_t** e; ~ExtGuard() { vg_free(c, e[0]); vg_free(c, e[1]); } } eg{ctx, ext};
+    if (ext_words) { VG_TRY(vg_alloc(ctx, (void**)&ext[0], ext_words * 4)); if (overlap) VG_TRY(vg_alloc(ctx, (void**)&ext[1], ext_words * 4)); }
+    bool used[2] = {false, false};
     for (size_t k = 0; k < tall.size(); k++) {
         const size_t i = tall[k];
         const vgpu_dmat* m = mats[i];
@@ -321,19 +341,25 @@ static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat
         vg_shard_range(m->gw, (int)G, ctx->comm_rank, &c0, &c1);
         VG_TRY(vg_dmat_alloc_dist(ctx, VG_ROWS, H, m->gw, true, &pd->ldes[i]));
         pd->ldes[i]->bitrev_rows = false;        // committed order IS the stored order of an LDE (rows at reverse_bits)
-        if (c1 > c0) {
-            const uint32_t* src; uint64_t scs;
-            if (m->dist == VG_ROWS) { src = cols[k]->d; scs = h; }
-            else if (m->dist == VG_COLS) { src = m->d; scs = m->col_stride; }
-            else { src = m->d + c0 * m->col_stride; scs = m->col_stride; }
-            uint32_t* ext = nullptr;
-            VG_TRY(vg_alloc(ctx, (void**)&ext, H * (c1 - c0) * 4));
-            int32_t rc = vg_coset_lde(ctx, src, scs, h, c1 - c0, lde_shift_of(coset_shifts_or_null, (uint32_t)i), ext, H, true, m->bitrev_rows);
-            if (rc == 0) rc = vg_exchange_cols_to_rows(ctx, ext, H, c0, c1, pd->ldes[i]);
-            vg_free(ctx, ext);
-            if (rc) return rc;
+        if (c1 <= c0) continue;
+        const uint32_t* src; uint64_t scs;
+        if (m->dist == VG_ROWS) { src = cols[k]->d; scs = h; }
+        else if (m->dist == VG_COLS) { src = m->d; scs = m->col_stride; }
+        else { src = m->d + c0 * m->col_stride; scs = m->col_stride; }
+        const int b = overlap ? (int)(k & 1) : 0;
+        if (overlap && used[b]) VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->xfer_ev[b], 0));
+        VG_TRY(vg_coset_lde(ctx, src, scs, h, c1 - c0, lde_shift_of(coset_shifts_or_null, (uint32_t)i), ext[b], H, true, m->bitrev_rows));
+        if (overlap) {
+            VG_CUDA(ctx, cudaEventRecord(ctx->xfer_ev[2], ctx->stream));
+            VG_CUDA(ctx, cudaStreamWaitEvent(ctx->xfer_stream, ctx->xfer_ev[2], 0));
+            VG_TRY(vg_exchange_cols_to_rows(ctx, ext[b], H, c0, c1, pd->ldes[i], ctx->xfer_stream));
+            VG_CUDA(ctx, cudaEventRecord(ctx->xfer_ev[b], ctx->xfer_stream));
+            used[b] = true;
+        } else {
+            VG_TRY(vg_exchange_cols_to_rows(ctx, ext[0], H, c0, c1, pd->ldes[i]));
         }
     }
+    if (overlap) for (int b = 0; b < 2; b++) if (used[b]) VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->xfer_ev[b], 0));
     return vg_comm_barrier(ctx);   // also orders the release of the column buffers (guard) behind every peer's stores
 }
 

@@ -43,6 +43,7 @@ struct vgpu_ctx {
     bool poseidon_has_mds = false;
     void* challenger = nullptr;                                  // vgh::Challenger* (host/challenger.h)
     void* poseidon = nullptr;                                    // vgh::Poseidon16*
+    uint32_t* d_poseidon = nullptr;                              // device copy of the round constants + MDS (pow.cu), dropped when they change
     std::vector<std::pair<const char*, float>> phases;          // last prove: per-phase milliseconds
     struct PhaseMark { const char* name; cudaEvent_t a, b; };
     std::vector<PhaseMark> phase_marks;                         // event pairs of the last prove (read by vgpu_last_prove_phases)
@@ -71,6 +72,8 @@ struct vgpu_ctx {
     struct CommStat { uint32_t calls = 0; double bytes = 0; };
     CommStat stat_barrier, stat_allgather, stat_exchange;        // per-proof collective counters (bench.py)
     cudaStream_t copy_stream = nullptr;                         // H2D copies of a pipelined vgpu_prove (staging.cu)
+    cudaStream_t xfer_stream = nullptr;                         // split proof: peer-store exchange of matrix i behind the LDE of matrix i+1
+    cudaEvent_t xfer_ev[3] = {nullptr, nullptr, nullptr};       // [0], [1]: exchange out of buffer 0 / 1 done; [2]: LDE done
     bool ntt_attrs_set = false, bary_attrs_set = false;          // cudaFuncSetAttribute is per device: tracked per context, not per process
     bool ktiming = false;
     std::vector<KTimer> ktimers;
@@ -149,7 +152,7 @@ template <class T> inline T* vg_peer_ptr(const vgpu_ctx* ctx, T* mine, int peer)
 }
 // exchange.cu — the two transposing exchanges of a split commit, as kernels storing through peer pointers
 int32_t vg_exchange_rows_to_cols(vgpu_ctx* ctx, const vgpu_dmat* rows, uint32_t* cols_symm, uint64_t max_share_w);
-int32_t vg_exchange_cols_to_rows(vgpu_ctx* ctx, const uint32_t* lde_cols, uint64_t H, uint64_t c0, uint64_t c1, vgpu_dmat* shard);
+int32_t vg_exchange_cols_to_rows(vgpu_ctx* ctx, const uint32_t* lde_cols, uint64_t H, uint64_t c0, uint64_t c1, vgpu_dmat* shard, cudaStream_t on = nullptr);
 int32_t vg_dmat_alloc_dist(vgpu_ctx* ctx, int dist, uint64_t gh, uint64_t gw, bool symm, vgpu_dmat** out);
 
 // ntt.cu

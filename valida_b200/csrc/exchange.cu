@@ -73,7 +73,8 @@ int32_t vg_exchange_rows_to_cols(vgpu_ctx* ctx, const vgpu_dmat* rows, uint32_t*
 
 // lde_cols: this rank's extended columns [c0, c1) of a matrix of H rows (stride H, committed row order).  shard: the VG_ROWS
 // matrix (H / G rows x gw, symmetric heap) that receives, on every rank, that rank's run of rows of ALL columns.
-int32_t vg_exchange_cols_to_rows(vgpu_ctx* ctx, const uint32_t* lde_cols, uint64_t H, uint64_t c0, uint64_t c1, vgpu_dmat* shard) {
+int32_t vg_exchange_cols_to_rows(vgpu_ctx* ctx, const uint32_t* lde_cols, uint64_t H, uint64_t c0, uint64_t c1, vgpu_dmat* shard, cudaStream_t on) {
+    const cudaStream_t st = on ? on : ctx->stream;
     const int G = ctx->comm_size;
     if (c1 <= c0) return 0;
     if (shard->dist != VG_ROWS || !shard->symm || shard->h * (uint64_t)G != H || (shard->h & 3)) VG_FAIL(ctx, "exchange: shard matrix does not match the extended columns");
@@ -84,7 +85,7 @@ int32_t vg_exchange_cols_to_rows(vgpu_ctx* ctx, const uint32_t* lde_cols, uint64
     unsigned gx = (unsigned)((n4 + 255) / 256);
     if (gx > 64) gx = 64;
     KScope ks(ctx, KC_EXCHANGE, 8.0 * (double)H * (double)(c1 - c0));
-    cols_to_rows_kernel<<<dim3(gx, (unsigned)(c1 - c0), (unsigned)G), 256, 0, ctx->stream>>>(p);
+    cols_to_rows_kernel<<<dim3(gx, (unsigned)(c1 - c0), (unsigned)G), 256, 0, st>>>(p);
     VG_LAUNCH_CHECK(ctx);
     ctx->stat_exchange.calls++; ctx->stat_exchange.bytes += 4.0 * (double)H * (double)(c1 - c0) * (G - 1) / G;
     return 0;

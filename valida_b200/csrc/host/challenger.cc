@@ -40,11 +40,15 @@ void Poseidon16::set(const uint32_t rc_canonical[480], const uint32_t* mds_canon
 static inline uint32_t sbox5(uint32_t x) { uint32_t x2 = bb::sqr(x), x4 = bb::sqr(x2); return bb::mul(x4, x); }
 
 void Poseidon16::permute(uint32_t s[16]) const {
+    // dense 16 x 16 product with lazy sums: four raw 64-bit products (each < p^2 < 2^62) per Montgomery reduction
     auto mds_layer = [&]() {
         uint32_t o[16];
         for (int i = 0; i < 16; i++) {
             uint32_t acc = 0;
-            for (int j = 0; j < 16; j++) acc = bb::add(acc, bb::mul(mds[i][j], s[j]));
+            for (int j = 0; j < 16; j += 4) {
+                const uint64_t t = (uint64_t)mds[i][j] * s[j] + (uint64_t)mds[i][j + 1] * s[j + 1] + (uint64_t)mds[i][j + 2] * s[j + 2] + (uint64_t)mds[i][j + 3] * s[j + 3];
+                acc = bb::add(acc, bb::monty_reduce64(t));
+            }
             o[i] = acc;
         }
         std::memcpy(s, o, sizeof o);
@@ -96,6 +100,7 @@ uint32_t Challenger::grind(int bits) {
 extern "C" int32_t vgpu_set_challenger(vgpu_ctx* ctx, const uint32_t round_constants[480], const uint32_t* mds_16x16_or_null) {
     if (!ctx || !round_constants) return -1;
     std::memcpy(ctx->poseidon_rc, round_constants, sizeof ctx->poseidon_rc);
+    if (ctx->d_poseidon) { vg_free(ctx, ctx->d_poseidon); ctx->d_poseidon = nullptr; }
     if (mds_16x16_or_null) std::memcpy(ctx->poseidon_mds, mds_16x16_or_null, sizeof ctx->poseidon_mds);
     ctx->challenger_set = true;
     ctx->poseidon_has_mds = mds_16x16_or_null != nullptr;

@@ -237,7 +237,12 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
                 if (fin[l * cur.n + i] != f0.c[l]) VG_FAIL(ctx, "FRI: final layer is not constant (the committed functions are not low degree)");
         out->fri.final_poly = canon(f0);
     }
-    { HostPhase hp(ctx, "host: proof-of-work grind"); out->fri.pow_witness = bb::from_monty(ch.grind(POW_BITS)); }
+    {
+        HostPhase hp(ctx, "proof-of-work grind (device search + host check)");
+        uint32_t wm = 0;
+        VG_TRY(vg_pow_grind(ctx, ch, POW_BITS, &wm));
+        out->fri.pow_witness = bb::from_monty(wm);
+    }
     std::vector<uint64_t> indices;
     for (int q = 0; q < NUM_QUERIES; q++) indices.push_back(ch.sample_bits(log_max));
 
@@ -306,7 +311,21 @@ struct Cbor {
     void key(const char* s) { size_t n = std::strlen(s); head(3, n); b.insert(b.end(), s, s + n); }
     void map(uint64_t n) { head(5, n); }
     void arr(uint64_t n) { head(4, n); }
-    void felt(uint32_t canonical) { map(1); key("value"); head(0, bb::to_monty(canonical)); }   // BabyBear { value } holds the Montgomery word
+    // BabyBear { value } holds the Montgomery word: {"value": u32}.  ~150 k of these per proof: written as one 12-byte store
+    void felt(uint32_t canonical) {
+        static const uint8_t pre[7] = {0xa1, 0x65, 'v', 'a', 'l', 'u', 'e'};
+        const uint32_t v = bb::to_monty(canonical);
+        const size_t n = b.size();
+        b.resize(n + 12);
+        uint8_t* o = b.data() + n;
+        std::memcpy(o, pre, 7);
+        size_t len;
+        if (v < 24) { o[7] = (uint8_t)v; len = 8; }
+        else if (v <= 0xff) { o[7] = 24; o[8] = (uint8_t)v; len = 9; }
+        else if (v <= 0xffff) { o[7] = 25; o[8] = (uint8_t)(v >> 8); o[9] = (uint8_t)v; len = 10; }
+        else { o[7] = 26; o[8] = (uint8_t)(v >> 24); o[9] = (uint8_t)(v >> 16); o[10] = (uint8_t)(v >> 8); o[11] = (uint8_t)v; len = 12; }
+        b.resize(n + len);
+    }
     void ext(const ExtC& e) { map(1); key("value"); arr(5); for (int i = 0; i < 5; i++) felt(e.c[i]); }
     void digest(const Digest& d) { arr(8); for (int i = 0; i < 8; i++) felt(d[i]); }
     void digests(const std::vector<Digest>& v) { arr(v.size()); for (auto& d : v) digest(d); }
@@ -531,6 +550,7 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
     // MachineProof -> CBOR
     HostPhase hc(ctx, "host: MachineProof -> CBOR");
     Cbor w;
+    w.b.reserve(4u << 20);
     w.map(3);
     w.key("commitments"); w.map(3);
     w.key("main_trace"); w.digest(main_commit);
