@@ -12,6 +12,7 @@
 #include "keccak.cuh"
 #include "merkle.h"
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 namespace {
@@ -106,6 +107,54 @@ __global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __r
     w[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// The short layers of a tree in ONE launch: a CTA owns `sub` consecutive nodes of the first fused layer and reduces that sub-tree
+// level by level in shared memory (each level is written to its place in global memory as well), so the 10 - 16 launches of a tree's
+// tail — each a handful of warps waiting on a single Keccak-f — become one or two.  Bases are virtual (+ global node index), as in
+// compress_layer_kernel; inj_v[k] = digests of the rows a shorter matrix group contributes at fused level k, or null.
+constexpr int TAIL_SUB = 512, TAIL_THREADS = 256, TAIL_MAX_LEVELS = 10;
+struct TailParams {
+    const uint32_t* prev_v;
+    uint32_t* next_v[TAIL_MAX_LEVELS];
+    const uint32_t* inj_v[TAIL_MAX_LEVELS];
+    uint64_t first_begin;     // first node of the first fused layer computed by this launch
+    uint32_t sub;             // nodes of the first fused layer per CTA (power of two <= TAIL_SUB)
+    uint32_t levels;          // fused levels: level k has sub >> k nodes per CTA
+};
+__global__ void __launch_bounds__(TAIL_THREADS) tree_tail_kernel(const __grid_constant__ TailParams p) {
+    __shared__ uint4 buf_a[2 * TAIL_SUB * 2];     // children of the current level: 2 * sub digests (two uint4 each)
+    __shared__ uint4 buf_b[TAIL_SUB * 2];
+    const uint64_t node0 = p.first_begin + (uint64_t)blockIdx.x * p.sub;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.prev_v + 2 * node0 * 8);
+        for (uint32_t i = threadIdx.x; i < 4 * p.sub; i += TAIL_THREADS) buf_a[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    uint4* cur = buf_a; uint4* nxt = buf_b;
+    for (uint32_t k = 0; k < p.levels; k++) {
+        const uint32_t n = p.sub >> k;
+        const uint64_t base = node0 >> k;
+        for (uint32_t t = threadIdx.x; t < n; t += TAIL_THREADS) {
+            const uint4 a = cur[4 * t], b = cur[4 * t + 1], c = cur[4 * t + 2], d = cur[4 * t + 3];
+            uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, r[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w}, o[8];
+            compress_pair(l, r, o);
+            if (p.inj_v[k]) {
+                const uint4* q = reinterpret_cast<const uint4*>(p.inj_v[k] + (base + t) * 8);
+                const uint4 e = __ldg(q), f = __ldg(q + 1);
+                uint32_t tt[8] = {e.x, e.y, e.z, e.w, f.x, f.y, f.z, f.w}, o2[8];
+                compress_pair(o, tt, o2);
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[i] = o2[i];
+            }
+            const uint4 w0 = make_uint4(o[0], o[1], o[2], o[3]), w1 = make_uint4(o[4], o[5], o[6], o[7]);
+            nxt[2 * t] = w0; nxt[2 * t + 1] = w1;
+            uint4* g = reinterpret_cast<uint4*>(p.next_v[k] + (base + t) * 8);
+            g[0] = w0; g[1] = w1;
+        }
+        __syncthreads();
+        uint4* tmp = cur; cur = nxt; nxt = tmp;
+    }
+}
+
 // FRI commit-phase leaf: the pair (v[2i], v[2i+1]) of ext5 values flattened to 10 base words
 // (ExtensionMmcs over a width-2 matrix); v is limb-major: limb l of element e at v[l * cs + e].
 __global__ void __launch_bounds__(128) fri_leaf_hash_kernel(const uint32_t* __restrict__ v, uint64_t cs, uint64_t i0, uint64_t npairs, uint32_t* __restrict__ digests) {
@@ -176,14 +225,52 @@ static int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mat
     return 0;
 }
 
-// layers 1.. of a planned tree whose leaf layer is already hashed; inject(lvl, plan, inj_v) fills the digests of the rows a
-// shorter matrix group contributes at layer lvl (returns false when there is none)
+// layers 1.. of a planned tree whose leaf layer is already hashed; inject(lvl, plan, inj_v, &have) fills the digests of the rows a
+// shorter matrix group contributes at layer lvl.  Long layers take one launch each; from the first layer of at most TAIL_FUSE nodes
+// (computed here) on, runs of up to 10 layers go into ONE launch of tree_tail_kernel; a run ends at the sub-root layer of a split tree
+// (its all-gather comes next) and at the root.
+constexpr uint64_t TAIL_FUSE = 1u << 15;
 template <class Inject>
 static int32_t build_upper_layers(vgpu_ctx* ctx, const std::vector<LayerPlan>& plan, VgTree* t, uint32_t* inject_buf, Inject inject) {
     if (plan[0].gather) VG_TRY(vg_comm_allgather_inplace(ctx, t->layer_ptr[0], 8));
-    for (size_t lvl = 1; lvl < plan.size(); lvl++) {
+    static const bool fuse = [] { const char* e = getenv("VGPU_TREE_TAIL"); return !e || atoi(e) != 0; }();   // tuning knob (profiles/)
+    size_t lvl = 1;
+    while (lvl < plan.size()) {
         const LayerPlan& p = plan[lvl];
         const uint32_t* prev_v = t->layer_ptr[lvl - 1] - plan[lvl - 1].sbegin * 8;
+        if (fuse && p.ccount <= TAIL_FUSE) {
+            // one launch: levels lvl .. lvl + n - 1, each half the one below; stop after a gather layer and at the root
+            TailParams tp{};
+            tp.prev_v = prev_v; tp.first_begin = p.cbegin;
+            tp.sub = (uint32_t)std::min<uint64_t>(TAIL_SUB, p.ccount);
+            uint32_t n = 0;
+            uint32_t* inj_at = inject_buf;
+            double bytes = 0;
+            while (n < TAIL_MAX_LEVELS && lvl + n < plan.size() && (tp.sub >> n) >= 1) {
+                const LayerPlan& q = plan[lvl + n];
+                if (q.ccount != (p.ccount >> n) || q.cbegin != (p.cbegin >> n)) break;      // the run of halving layers ends (past a gather layer)
+                tp.next_v[n] = t->layer_ptr[lvl + n] - q.sbegin * 8;
+                tp.inj_v[n] = nullptr;
+                if (inject_buf) {
+                    uint32_t* buf_v = inj_at - q.cbegin * 8;
+                    bool have = false;
+                    VG_TRY(inject(lvl + n, q, buf_v, &have));
+                    if (have) { tp.inj_v[n] = buf_v; inj_at += q.ccount * 8; }
+                }
+                bytes += (double)q.ccount * (tp.inj_v[n] ? 128.0 : 96.0);
+                n++;
+                if (q.gather) break;
+            }
+            tp.levels = n;
+            {
+                KScope ks(ctx, KC_COMPRESS, bytes);
+                tree_tail_kernel<<<(unsigned)(p.ccount / tp.sub), TAIL_THREADS, 0, ctx->stream>>>(tp);
+            }
+            VG_LAUNCH_CHECK(ctx);
+            lvl += n;
+            if (plan[lvl - 1].gather) VG_TRY(vg_comm_allgather_inplace(ctx, t->layer_ptr[lvl - 1], 8));
+            continue;
+        }
         uint32_t* next_v = t->layer_ptr[lvl] - p.sbegin * 8;
         const uint32_t* inj_v = nullptr;
         if (inject_buf) {
@@ -198,6 +285,7 @@ static int32_t build_upper_layers(vgpu_ctx* ctx, const std::vector<LayerPlan>& p
         }
         VG_LAUNCH_CHECK(ctx);
         if (p.gather) VG_TRY(vg_comm_allgather_inplace(ctx, t->layer_ptr[lvl], 8));
+        lvl++;
     }
     return 0;
 }
@@ -250,7 +338,12 @@ int32_t vg_merkle_build(vgpu_ctx* ctx, vgpu_prover_data* pd, const std::vector<u
     VG_TRY(take(max_h));
     VG_TRY(hash_rows(ctx, group, plan[0].cbegin, plan[0].ccount, pd->tree.layer_ptr[0] - plan[0].sbegin * 8));
     uint32_t* inject_buf = nullptr;
-    if (pos < n) VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (plan.size() > 1 ? plan[1].ccount : 1) * 32));
+    if (pos < n) {
+        // one layer's row digests at a time — except inside a fused run of short layers, where the digests of every injecting
+        // layer of the run (at most 2 * TAIL_FUSE in all) must coexist
+        const uint64_t c1 = plan.size() > 1 ? plan[1].ccount : 1;
+        VG_TRY(vg_alloc(ctx, (void**)&inject_buf, (c1 <= 2 * TAIL_FUSE ? 2 * c1 : c1) * 32));
+    }
     int32_t rc = build_upper_layers(ctx, plan, &pd->tree, inject_buf, [&](size_t, const LayerPlan& p, uint32_t* buf_v, bool* have) -> int32_t {
         VG_TRY(take(p.len));
         *have = !group.empty();
