@@ -218,6 +218,20 @@ const vgpu_matrix* vgpu_traces_preprocessed(const vgpu_traces* t, uint32_t which
 void vgpu_traces_stats(const vgpu_traces* t, uint32_t* clock, uint32_t* mem_ops, uint32_t* add_ops);
 int32_t vgpu_traces_mem_cell(const vgpu_traces* t, uint32_t addr, uint32_t* value);
 void vgpu_traces_free(vgpu_traces* t);
+/* ---- witness generation on the device ------------------------------------------------------------------
+ * Machine::run alone (the interpreter is a serial host loop): what it leaves behind are its LOGS — one record per cycle, per
+ * memory operation, per ALU operation.  vgpu_witness_device expands them into the 14 main and 2 preprocessed traces ON THE
+ * GPU (cpu/src/lib.rs:79-97,163-373; memory/src/lib.rs:143-194 with the (addr, clk) sort; alu_u32 op_to_row), column-major
+ * Montgomery words ready for vgpu_prove_device: no host row fill, no 2 GB upload, no transpose.  vgpu_vmlog_traces builds the
+ * same traces on the host from the same logs (equal word for word; the parity tests compare the two). */
+typedef struct vgpu_vmlog vgpu_vmlog;
+int32_t vgpu_vm_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                    const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static, vgpu_vmlog** out, char* err, uint64_t err_len);
+void vgpu_vmlog_stats(const vgpu_vmlog* log, uint32_t* clock, uint32_t* mem_ops, uint32_t* add_ops);
+int32_t vgpu_vmlog_traces(vgpu_vmlog* log, vgpu_traces** out, char* err, uint64_t err_len);
+int32_t vgpu_witness_device(vgpu_ctx* ctx, const vgpu_vmlog* log, vgpu_dmat* main_out[VGPU_NUM_CHIPS], vgpu_dmat* prep_out[2]);
+void vgpu_vmlog_free(vgpu_vmlog* log);
+
 /* fib_program of basic/tests/test_prover.rs:35-188 with `imm32 -8(fp)` = n; returns the instruction count (23). */
 uint64_t vgpu_fib_program(uint32_t n, int32_t* out_words /* >= 23*6 */);
 

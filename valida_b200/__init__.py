@@ -24,6 +24,8 @@ from .api import (  # noqa: F401
     lib,
     lib_path,
     run_program,
+    run_program_log,
+    VmLog,
     comm_unique_id,
     comm_init_local,
     run_ranks,

@@ -85,6 +85,11 @@ def _load():
         "vgpu_traces_mem_cell": (C.c_int32, [vp, C.c_uint32, u32p]),
         "vgpu_traces_free": (None, [vp]),
         "vgpu_fib_program": (u64, [C.c_uint32, C.POINTER(C.c_int32)]),
+        "vgpu_vm_run": (C.c_int32, [C.POINTER(C.c_int32), u64, C.c_uint32, C.c_uint32, u64, u32p, u32p, u64, C.POINTER(vp), C.c_char_p, u64]),
+        "vgpu_vmlog_stats": (None, [vp, u32p, u32p, u32p]),
+        "vgpu_vmlog_traces": (C.c_int32, [vp, C.POINTER(vp), C.c_char_p, u64]),
+        "vgpu_witness_device": (C.c_int32, [vp, vp, C.POINTER(vp), C.POINTER(vp)]),
+        "vgpu_vmlog_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -522,6 +527,57 @@ class MachineTraces:
             self.free()
         except Exception:
             pass
+
+
+class VmLog:
+    """Machine::run without the row fill: the interpreter's logs (one record per cycle / memory operation / ALU operation)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        c, mo, ao = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().vgpu_vmlog_stats(handle, C.byref(c), C.byref(mo), C.byref(ao))
+        self.clock, self.mem_ops, self.add_ops = c.value, mo.value, ao.value
+
+    def traces(self):
+        """Chip::generate_trace x14 on the host from these logs."""
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        if lib().vgpu_vmlog_traces(self._h, C.byref(h), err, 512) != 0:
+            raise VgpuError(err.value.decode())
+        return MachineTraces(h)
+
+    def witness_device(self, ctx):
+        """Chip::generate_trace x14 on the GPU: ([14 DeviceMatrix], [2 DeviceMatrix]) for prove_machine(device_resident=...)."""
+        main = (C.c_void_p * NUM_CHIPS)()
+        prep = (C.c_void_p * 2)()
+        ctx.check(lib().vgpu_witness_device(ctx._h, self._h, main, prep))
+        return [DeviceMatrix(ctx, C.c_void_p(main[i])) for i in range(NUM_CHIPS)], [DeviceMatrix(ctx, C.c_void_p(prep[i])) for i in range(2)]
+
+    def free(self):
+        if self._h:
+            lib().vgpu_vmlog_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def run_program_log(program, initial_fp=0x1000, initial_pc=0, max_cycles=1 << 30, static_data=None):
+    """Machine::run only (host interpreter): returns the VmLog the host or the device expands into traces."""
+    p = np.ascontiguousarray(program, dtype=np.int32)
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    sa = np.array(sorted((static_data or {}).keys()), dtype=np.uint32)
+    sv = np.array([(static_data or {})[int(a)] for a in sa], dtype=np.uint32)
+    u32ptr = C.POINTER(C.c_uint32)
+    rc = lib().vgpu_vm_run(p.ctypes.data_as(C.POINTER(C.c_int32)), p.shape[0], initial_pc, initial_fp, max_cycles,
+                           sa.ctypes.data_as(u32ptr), sv.ctypes.data_as(u32ptr), len(sa), C.byref(h), err, 512)
+    if rc != 0:
+        raise VgpuError(err.value.decode())
+    return VmLog(h)
 
 
 def fib_program(n):

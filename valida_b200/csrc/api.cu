@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <utility>
 
 // ---- memory ------------------------------------------------------------------------------------
 int32_t vg_alloc(vgpu_ctx* ctx, void** p, size_t bytes) {
@@ -292,26 +293,69 @@ static uint32_t lde_shift_of(const uint32_t* coset_shifts_or_null, uint32_t i) {
     return bb::from_monty(bb::mul(bb::to_monty(bb::GEN_CANON), bb::inv(bb::to_monty(cs))));
 }
 
+// Which rank extends which columns of the tall matrices of one commit: contiguous column ranges per rank, sized by water-filling
+// over the whole commit — tallest matrix first, every column goes to the rank with the least work so far (a column of height h
+// weighs h) — so that a rank that had to take two of the ten columns of a 2^24-row matrix takes fewer columns of the others.
+// (An even split of every matrix on its own leaves the first ranks with up to 60 % more LDE work than the mean at 8 ranks.)
+struct ColPlan { uint32_t begin[17]; uint32_t widest; };
+static std::vector<ColPlan> plan_columns(const vgpu_ctx* ctx, const std::vector<std::pair<uint64_t, uint64_t>>& dims /* (height, width) of the tall matrices */) {
+    const int G = ctx->comm_size;
+    std::vector<size_t> order(dims.size());
+    for (size_t k = 0; k < dims.size(); k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dims[a].first > dims[b].first; });
+    std::vector<uint64_t> load(G, 0);
+    std::vector<ColPlan> plan(dims.size());
+    for (size_t k : order) {
+        uint32_t count[16] = {0};
+        for (uint64_t c = 0; c < dims[k].second; c++) {
+            int best = 0;
+            for (int r = 1; r < G; r++) if (load[r] < load[best]) best = r;
+            count[best]++; load[best] += dims[k].first;
+        }
+        ColPlan& p = plan[k];
+        p.begin[0] = 0; p.widest = 0;
+        for (int r = 0; r < G; r++) { p.begin[r + 1] = p.begin[r] + count[r]; p.widest = std::max(p.widest, count[r]); }
+    }
+    return plan;
+}
+
+// Symmetric-heap bytes one commit of matrices with these (height, width) puts there when they arrive as row shards (prover.cc sizes
+// the heap for a whole proof with it).
+extern "C++" size_t vg_commit_symm_need(const vgpu_ctx* ctx, const std::vector<std::pair<uint64_t, uint64_t>>& dims_all) {
+    std::vector<std::pair<uint64_t, uint64_t>> dims;
+    for (auto& d : dims_all) if (vg_split_rows(ctx, 2 * d.first)) dims.push_back(d);
+    const std::vector<ColPlan> plan = plan_columns(ctx, dims);
+    size_t need = 0;
+    for (size_t k = 0; k < dims.size(); k++)
+        need += vg_symm_round((2 * dims[k].first / (uint64_t)ctx->comm_size) * dims[k].second * 4) + vg_symm_round(dims[k].first * plan[k].widest * 4);
+    return need;
+}
+
 // Split proof: the tall matrices of a commit.  (1) a matrix that arrives as row shards is handed to the ranks that extend
 // its columns; (2) every rank extends its column share and stores, through peer pointers, each rank's run of the committed
 // rows into that rank's shard.  After the closing barrier pd->ldes[i] holds rows [rank * H/G, (rank+1) * H/G) of all columns.
 static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat* const* mats, const std::vector<size_t>& tall, const uint32_t* coset_shifts_or_null) {
     const uint64_t G = (uint64_t)ctx->comm_size;
+    std::vector<std::pair<uint64_t, uint64_t>> dims;
+    for (size_t i : tall) dims.push_back({mats[i]->gh, mats[i]->gw});
+    const std::vector<ColPlan> plan = plan_columns(ctx, dims);
     size_t need = 0;
-    for (size_t i : tall) {
-        need += vg_symm_round((2 * mats[i]->gh / G) * mats[i]->gw * 4);
-        if (mats[i]->dist == VG_ROWS) need += vg_symm_round(mats[i]->gh * ((mats[i]->gw + G - 1) / G) * 4);
+    for (size_t k = 0; k < tall.size(); k++) {
+        const vgpu_dmat* m = mats[tall[k]];
+        need += vg_symm_round((2 * m->gh / G) * m->gw * 4);
+        if (m->dist == VG_ROWS) need += vg_symm_round(m->gh * plan[k].widest * 4);
     }
     VG_TRY(vg_symm_reserve(ctx, need));
-    std::vector<vgpu_dmat*> cols(mats ? tall.size() : 0, nullptr);
-    struct Guard { std::vector<vgpu_dmat*>& v; ~Guard() { for (auto* m : v) vgpu_dmat_free(m); } } guard{cols};
+    std::vector<uint32_t*> cols(tall.size(), nullptr);      // column buffers of the matrices that arrive as row shards (symmetric heap)
+    struct Guard { vgpu_ctx* c; std::vector<uint32_t*>& v; ~Guard() { for (auto* p : v) vg_symm_free(c, p); } } guard{ctx, cols};
     bool moved = false;
     for (size_t k = 0; k < tall.size(); k++) {
         const vgpu_dmat* m = mats[tall[k]];
         VG_TRY(vg_dmat_materialize(ctx, m));
+        if (m->dist == VG_COLS) VG_FAIL(ctx, "commit: column shares are internal to a commit");
         if (m->dist != VG_ROWS) continue;
-        VG_TRY(vg_dmat_alloc_dist(ctx, VG_COLS, m->gh, m->gw, true, &cols[k]));
-        VG_TRY(vg_exchange_rows_to_cols(ctx, m, cols[k]->d, (m->gw + G - 1) / G));
+        VG_TRY(vg_symm_alloc(ctx, (void**)&cols[k], m->gh * plan[k].widest * 4));
+        VG_TRY(vg_exchange_rows_to_cols(ctx, m, cols[k], plan[k].begin));
         moved = true;
     }
     if (moved) VG_TRY(vg_comm_barrier(ctx));
@@ -324,11 +368,8 @@ static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat
         for (auto& e : ctx->xfer_ev) VG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     size_t ext_words = 0;
-    for (size_t i : tall) {
-        uint64_t c0, c1;
-        vg_shard_range(mats[i]->gw, (int)G, ctx->comm_rank, &c0, &c1);
-        ext_words = std::max<size_t>(ext_words, 2 * mats[i]->gh * (c1 - c0));
-    }
+    for (size_t k = 0; k < tall.size(); k++)
+        ext_words = std::max<size_t>(ext_words, 2 * mats[tall[k]]->gh * (plan[k].begin[ctx->comm_rank + 1] - plan[k].begin[ctx->comm_rank]));
     uint32_t* ext[2] = {nullptr, nullptr};
     struct ExtGuard { vgpu_ctx* c; uint32_t** e; ~ExtGuard() { vg_free(c, e[0]); vg_free(c, e[1]); } } eg{ctx, ext};
     if (ext_words) { VG_TRY(vg_alloc(ctx, (void**)&ext[0], ext_words * 4)); if (overlap) VG_TRY(vg_alloc(ctx, (void**)&ext[1], ext_words * 4)); }
@@ -337,14 +378,12 @@ static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat
         const size_t i = tall[k];
         const vgpu_dmat* m = mats[i];
         const uint64_t h = m->gh, H = 2 * h;
-        uint64_t c0, c1;
-        vg_shard_range(m->gw, (int)G, ctx->comm_rank, &c0, &c1);
+        const uint64_t c0 = plan[k].begin[ctx->comm_rank], c1 = plan[k].begin[ctx->comm_rank + 1];
         VG_TRY(vg_dmat_alloc_dist(ctx, VG_ROWS, H, m->gw, true, &pd->ldes[i]));
         pd->ldes[i]->bitrev_rows = false;        // committed order IS the stored order of an LDE (rows at reverse_bits)
         if (c1 <= c0) continue;
         const uint32_t* src; uint64_t scs;
-        if (m->dist == VG_ROWS) { src = cols[k]->d; scs = h; }
-        else if (m->dist == VG_COLS) { src = m->d; scs = m->col_stride; }
+        if (m->dist == VG_ROWS) { src = cols[k]; scs = h; }
         else { src = m->d + c0 * m->col_stride; scs = m->col_stride; }
         const int b = overlap ? (int)(k & 1) : 0;
         if (overlap && used[b]) VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->xfer_ev[b], 0));

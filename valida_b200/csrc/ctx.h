@@ -151,8 +151,9 @@ template <class T> inline T* vg_peer_ptr(const vgpu_ctx* ctx, T* mine, int peer)
     return reinterpret_cast<T*>(ctx->peer_base[peer] + (reinterpret_cast<uint8_t*>(const_cast<typename std::remove_const<T>::type*>(mine)) - ctx->symm_base));
 }
 // exchange.cu — the two transposing exchanges of a split commit, as kernels storing through peer pointers
-int32_t vg_exchange_rows_to_cols(vgpu_ctx* ctx, const vgpu_dmat* rows, uint32_t* cols_symm, uint64_t max_share_w);
+int32_t vg_exchange_rows_to_cols(vgpu_ctx* ctx, const vgpu_dmat* rows, uint32_t* cols_symm, const uint32_t* col_begin);
 int32_t vg_exchange_cols_to_rows(vgpu_ctx* ctx, const uint32_t* lde_cols, uint64_t H, uint64_t c0, uint64_t c1, vgpu_dmat* shard, cudaStream_t on = nullptr);
+size_t vg_commit_symm_need(const vgpu_ctx* ctx, const std::vector<std::pair<uint64_t, uint64_t>>& dims_all);
 int32_t vg_dmat_alloc_dist(vgpu_ctx* ctx, int dist, uint64_t gh, uint64_t gw, bool symm, vgpu_dmat** out);
 
 // ntt.cu

@@ -47,20 +47,15 @@ __global__ void __launch_bounds__(256) cols_to_rows_kernel(const __grid_constant
 
 }  // namespace
 
-// rows: this rank's row shard (VG_ROWS) of a gh x gw matrix.  cols_symm: a symmetric-heap buffer of gh * max_share_w words on
-// every rank; after the barrier that follows, it holds this rank's column share [c0, c1) (vg_shard_range of gw) at stride gh.
-int32_t vg_exchange_rows_to_cols(vgpu_ctx* ctx, const vgpu_dmat* rows, uint32_t* cols_symm, uint64_t max_share_w) {
-    (void)max_share_w;
+// rows: this rank's row shard (VG_ROWS) of a gh x gw matrix.  cols_symm: a symmetric-heap buffer (the same size on every rank, room
+// for the widest share); after the barrier that follows, it holds this rank's columns [col_begin[rank], col_begin[rank + 1]) at stride gh.
+int32_t vg_exchange_rows_to_cols(vgpu_ctx* ctx, const vgpu_dmat* rows, uint32_t* cols_symm, const uint32_t* col_begin /* comm_size + 1 */) {
     const int G = ctx->comm_size;
     if (rows->dist != VG_ROWS || (rows->h & 3) || (rows->row0 & 3) || (rows->col_stride & 3)) VG_FAIL(ctx, "exchange: row shard of %llu rows at %llu is not 16-byte aligned", (unsigned long long)rows->h, (unsigned long long)rows->row0);
     R2CParams p{};
     p.src = rows->d; p.scs = rows->col_stride; p.hl = rows->h; p.gh = rows->gh; p.row0 = rows->row0; p.nranks = (uint32_t)G;
-    for (int d = 0; d < G; d++) {
-        uint64_t a, b;
-        vg_shard_range(rows->gw, G, d, &a, &b);
-        p.c0[d] = (uint32_t)a; p.c0[d + 1] = (uint32_t)b;
-        p.dst[d] = vg_peer_ptr(ctx, cols_symm, d);
-    }
+    for (int d = 0; d <= G; d++) p.c0[d] = col_begin[d];
+    for (int d = 0; d < G; d++) p.dst[d] = vg_peer_ptr(ctx, cols_symm, d);
     const uint64_t n4 = rows->h >> 2;
     unsigned gx = (unsigned)((n4 + 255) / 256);
     if (gx > 64) gx = 64;

@@ -299,32 +299,32 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
 
 // ---- CBOR (serde/ciborium image of MachineProof; machine/src/proof.rs:13-44) -------------------------
 struct Cbor {
-    std::vector<uint8_t> b;
+    // append-only byte buffer with a raw cursor: the ~150 k field elements of a proof are 12-byte stores, not push_backs
+    std::vector<uint8_t> b; size_t n = 0;
+    uint8_t* room(size_t k) { if (n + k > b.size()) b.resize(std::max(2 * b.size(), n + k + (1u << 20))); return b.data() + n; }
+    void finish() { b.resize(n); }
     void head(uint8_t major, uint64_t v) {
-        uint8_t m = (uint8_t)(major << 5);
-        if (v < 24) b.push_back(m | (uint8_t)v);
-        else if (v <= 0xff) { b.push_back(m | 24); b.push_back((uint8_t)v); }
-        else if (v <= 0xffff) { b.push_back(m | 25); b.push_back((uint8_t)(v >> 8)); b.push_back((uint8_t)v); }
-        else if (v <= 0xffffffffull) { b.push_back(m | 26); for (int s = 24; s >= 0; s -= 8) b.push_back((uint8_t)(v >> s)); }
-        else { b.push_back(m | 27); for (int s = 56; s >= 0; s -= 8) b.push_back((uint8_t)(v >> s)); }
+        uint8_t* o = room(9);
+        const uint8_t m = (uint8_t)(major << 5);
+        if (v < 24) { o[0] = m | (uint8_t)v; n += 1; }
+        else if (v <= 0xff) { o[0] = m | 24; o[1] = (uint8_t)v; n += 2; }
+        else if (v <= 0xffff) { o[0] = m | 25; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)v; n += 3; }
+        else if (v <= 0xffffffffull) { o[0] = m | 26; for (int i = 0; i < 4; i++) o[1 + i] = (uint8_t)(v >> (24 - 8 * i)); n += 5; }
+        else { o[0] = m | 27; for (int i = 0; i < 8; i++) o[1 + i] = (uint8_t)(v >> (56 - 8 * i)); n += 9; }
     }
-    void key(const char* s) { size_t n = std::strlen(s); head(3, n); b.insert(b.end(), s, s + n); }
-    void map(uint64_t n) { head(5, n); }
-    void arr(uint64_t n) { head(4, n); }
-    // BabyBear { value } holds the Montgomery word: {"value": u32}.  ~150 k of these per proof: written as one 12-byte store
+    void key(const char* s) { size_t k = std::strlen(s); head(3, k); std::memcpy(room(k), s, k); n += k; }
+    void map(uint64_t k) { head(5, k); }
+    void arr(uint64_t k) { head(4, k); }
+    // BabyBear { value } holds the Montgomery word: {"value": u32}
     void felt(uint32_t canonical) {
         static const uint8_t pre[7] = {0xa1, 0x65, 'v', 'a', 'l', 'u', 'e'};
         const uint32_t v = bb::to_monty(canonical);
-        const size_t n = b.size();
-        b.resize(n + 12);
-        uint8_t* o = b.data() + n;
+        uint8_t* o = room(12);
         std::memcpy(o, pre, 7);
-        size_t len;
-        if (v < 24) { o[7] = (uint8_t)v; len = 8; }
-        else if (v <= 0xff) { o[7] = 24; o[8] = (uint8_t)v; len = 9; }
-        else if (v <= 0xffff) { o[7] = 25; o[8] = (uint8_t)(v >> 8); o[9] = (uint8_t)v; len = 10; }
-        else { o[7] = 26; o[8] = (uint8_t)(v >> 24); o[9] = (uint8_t)(v >> 16); o[10] = (uint8_t)(v >> 8); o[11] = (uint8_t)v; len = 12; }
-        b.resize(n + len);
+        if (v < 24) { o[7] = (uint8_t)v; n += 8; }
+        else if (v <= 0xff) { o[7] = 24; o[8] = (uint8_t)v; n += 9; }
+        else if (v <= 0xffff) { o[7] = 25; o[8] = (uint8_t)(v >> 8); o[9] = (uint8_t)v; n += 10; }
+        else { o[7] = 26; o[8] = (uint8_t)(v >> 24); o[9] = (uint8_t)(v >> 16); o[10] = (uint8_t)(v >> 8); o[11] = (uint8_t)v; n += 12; }
     }
     void ext(const ExtC& e) { map(1); key("value"); arr(5); for (int i = 0; i < 5; i++) felt(e.c[i]); }
     void digest(const Digest& d) { arr(8); for (int i = 0; i < 8; i++) felt(d[i]); }
@@ -427,6 +427,7 @@ int32_t vgpu_open(vgpu_ctx* ctx, const vgpu_prover_data* const* rounds, uint32_t
         for (auto& mat : round) { w.arr(mat.size()); for (auto& at_point : mat) w.exts(at_point); }
     }
     write_opening_proof(w, op);
+    w.finish();
     uint8_t* buf = (uint8_t*)std::malloc(w.b.size());
     if (!buf) VG_FAIL(ctx, "out of host memory");
     std::memcpy(buf, w.b.data(), w.b.size());
@@ -452,14 +453,13 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
         // Split proof: room in the symmetric heap for everything the three commits put there — the row shards of every tall
         // chip's main / permutation / quotient LDEs and the column buffers of the rows -> columns hand-over (counted as if never
         // released: first-fit then always finds a run) — reserved ONCE, before the first shard is live.
-        const uint64_t G = (uint64_t)ctx->comm_size;
-        size_t need = 0;
+        std::vector<std::pair<uint64_t, uint64_t>> dm, dq, dc, dpre;
         for (int i = 0; i < VGPU_NUM_CHIPS; i++) {
             const uint64_t h = main[i]->gh;
-            if (!vg_split_rows(ctx, 2 * h)) continue;
-            const uint64_t widths[4] = {chips[i]->width, 5ull * (chips[i]->n_interactions + 1), 10, chips[i]->preprocessed_width};
-            for (uint64_t w : widths) if (w) need += vg_symm_round((2 * h / G) * w * 4) + vg_symm_round(h * ((w + G - 1) / G) * 4);
+            dm.push_back({h, chips[i]->width}); dq.push_back({h, 5ull * (chips[i]->n_interactions + 1)}); dc.push_back({h, 10});
+            if (chips[i]->preprocessed_width) dpre.push_back({h, chips[i]->preprocessed_width});
         }
+        const size_t need = vg_commit_symm_need(ctx, dm) + vg_commit_symm_need(ctx, dq) + vg_commit_symm_need(ctx, dc) + vg_commit_symm_need(ctx, dpre);
         if (need) VG_TRY(vg_symm_reserve(ctx, need));
     }
     vgh::Challenger ch;
@@ -550,7 +550,7 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
     // MachineProof -> CBOR
     HostPhase hc(ctx, "host: MachineProof -> CBOR");
     Cbor w;
-    w.b.reserve(4u << 20);
+    w.b.resize(4u << 20);
     w.map(3);
     w.key("commitments"); w.map(3);
     w.key("main_trace"); w.digest(main_commit);
@@ -574,6 +574,7 @@ int32_t vgpu_prove_device(vgpu_ctx* ctx, const vgpu_dmat* const main[VGPU_NUM_CH
         ExtC cs; for (int l = 0; l < 5; l++) cs.c[l] = cumsum[i][l];
         w.ext(cs);
     }
+    w.finish();
     uint8_t* buf = (uint8_t*)std::malloc(w.b.size());
     if (!buf) VG_FAIL(ctx, "out of host memory");
     std::memcpy(buf, w.b.data(), w.b.size());

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <omp.h>
 #include "../../../include/valida_b200.h"
+#include "vmlog.h"
 
 namespace {
 
@@ -39,13 +40,16 @@ inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return 
 
 enum : uint32_t { OP_LOAD32 = 1, OP_STORE32 = 2, OP_JAL = 3, OP_JALV = 4, OP_BEQ = 5, OP_BNE = 6, OP_IMM32 = 7, OP_STOP = 8, OP_LOADFP = 10,
                   OP_ADD32 = 100, OP_SUB32 = 101, OP_LT32 = 104, OP_AND32 = 107, OP_OR32 = 108, OP_XOR32 = 109, OP_LTE32 = 115, OP_SLT32 = 117, OP_SLE32 = 118 };
-enum CpuOp : uint8_t { K_STORE32, K_LOAD32, K_JAL, K_JALV, K_BEQ, K_BNE, K_IMM32, K_BUS, K_STOP, K_LOADFP, K_BUS_LEFT_IMM };
+using CpuOp = uint8_t;
+enum : uint8_t { K_STORE32 = VG_K_STORE32, K_LOAD32 = VG_K_LOAD32, K_JAL = VG_K_JAL, K_JALV = VG_K_JALV, K_BEQ = VG_K_BEQ, K_BNE = VG_K_BNE, K_IMM32 = VG_K_IMM32,
+                 K_BUS = VG_K_BUS, K_STOP = VG_K_STOP, K_LOADFP = VG_K_LOADFP, K_BUS_LEFT_IMM = VG_K_BUS_LEFT_IMM };
 
-struct MemOp { uint32_t clk, addr, value; uint8_t is_write; };
-struct CpuRec { uint32_t pc, fp; uint32_t instr; CpuOp kind; bool has_imm; uint32_t imm; };
-struct AluRec { uint32_t a, b, c; };
-struct LtRec { uint32_t a, b, c; uint32_t opcode; };
-using BitRec = LtRec;
+// log records: the layouts of host/vmlog.h (the device witness builder reads the same arrays)
+using MemOp = VgMemOp;
+using CpuRec = VgCpuRec;
+using AluRec = VgAluRec;
+using LtRec = VgAluOpRec;
+using BitRec = VgAluOpRec;
 
 // Append-only log of trivially copyable records.  Growth goes through realloc(), which glibc serves with mremap() for large
 // blocks — no copy of the 150 MB memory log at every doubling (std::vector growth cost 0.2-0.3 s of a 0.5 s run loop).
@@ -145,13 +149,15 @@ struct Vm {
 
     bool read(uint32_t addr, uint32_t& v) {
         if (!cells.get(addr, &v)) { err = "memory chip: read before write at " + std::to_string(addr) + " (pc=" + std::to_string(pc) + ")"; return false; }
-        mem_ops.push_back({clock, addr, v, 0});
+        mem_ops.push_back({clock, addr, v, 0u});
         return true;
     }
-    void write(uint32_t addr, uint32_t v) { mem_ops.push_back({clock, addr, v, 1}); cells.set(addr, v); }
+    void write(uint32_t addr, uint32_t v) { mem_ops.push_back({clock, addr, v, 1u}); cells.set(addr, v); }
     void range_check(uint32_t w) { for (int i = 0; i < 4; i++) range_count[(w >> (8 * i)) & 0xff]++; }
+    size_t cycle_mem0 = 0;      // first memory operation of the cycle being executed
     void push(CpuOp kind, uint32_t instr_pc, uint32_t pc_before, uint32_t fp_before, bool has_imm = false, uint32_t imm = 0) {
-        cpu.push_back({pc_before, fp_before, instr_pc, kind, has_imm, imm});
+        cpu.push_back({pc_before, fp_before, instr_pc, imm, (uint32_t)cycle_mem0, kind, (uint8_t)(has_imm ? 1 : 0), {0, 0}});
+        cycle_mem0 = mem_ops.size();
         clock++;
     }
     // returns 1 when STOP executed, 0 otherwise, -1 on error
@@ -248,9 +254,8 @@ void build_cpu(const Vm& vm, Traces& t) {
     size_t n = vm.cpu.size(), h = next_pow2(n);
     Buf& v = t.store[0];
     v.zeros(h * W);
-    // per-clk memory ops are contiguous in vm.mem_ops (clk non-decreasing)
-    std::vector<size_t> first(n + 1, 0);
-    { size_t k = 0; for (size_t clk = 0; clk <= n; clk++) { while (k < vm.mem_ops.size() && vm.mem_ops[k].clk < clk) k++; first[clk] = k; } }
+    // the memory operations of a cycle are contiguous in vm.mem_ops: [cpu[i].mem0, cpu[i + 1].mem0)
+    auto first_of = [&](size_t i) { return i < n ? (size_t)vm.cpu[i].mem0 : vm.mem_ops.size(); };
     std::vector<uint32_t> diff(n, 0);
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)n; i++) {
@@ -285,7 +290,7 @@ void build_cpu(const Vm& vm, Traces& t) {
         }
         row[29 + 1] = 1; row[36 + 1] = 1; row[43 + 1] = 0;
         bool first_read = true;
-        for (size_t k = first[i]; k < first[i + 1]; k++) {
+        for (size_t k = first_of(i), ke = first_of(i + 1); k < ke; k++) {
             const MemOp& m = vm.mem_ops[k];
             uint32_t ch;
             if (m.is_write) ch = 43;
@@ -481,13 +486,9 @@ struct vgpu_traces { Traces t; };
 
 extern "C" {
 
-static int machine_run_impl(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
-                            const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
-                            vgpu_traces** out, char* err, uint64_t err_len) {
-    // VGPU_TRACEGEN_TIMING=1 prints the time of each stage to stderr (development aid)
-    auto T0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) { if (getenv("VGPU_TRACEGEN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "tracegen %-12s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
-    Vm vm;
+// Machine::run: the interpreter loop; what it leaves behind is the input of every Chip::generate_trace
+static int vm_run_impl(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                       const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static, Vm& vm, char* err, uint64_t err_len) {
     vm.prog = program_words; vm.n_instr = n_instr; vm.pc = initial_pc; vm.fp = initial_fp;
     vm.prog_counts.assign(n_instr, 0);
     {   // MachineWithStaticDataChip::initialize_memory (static_data/src/lib.rs:26-30): cells are preloaded, nothing is logged
@@ -508,11 +509,19 @@ static int machine_run_impl(const int32_t* program_words, uint64_t n_instr, uint
     // STOP padding reads the program word at the final pc (basic/src/lib.rs:140-144)
     size_t padded = next_pow2(vm.clock);
     vm.prog_counts[vm.pc] += (uint32_t)(padded - vm.clock);
+    return 0;
+}
 
+// Chip::generate_trace x14 on the host
+static vgpu_traces* build_traces_host(Vm& vm) {
+    // VGPU_TRACEGEN_TIMING=1 prints the time of each stage to stderr (development aid)
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (getenv("VGPU_TRACEGEN_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "tracegen %-12s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
+    const int32_t* program_words = vm.prog;
+    const uint64_t n_instr = vm.n_instr;
     std::unique_ptr<vgpu_traces> tr(new vgpu_traces());      // released to the caller at the end; freed if an allocation below throws
     Traces& t = tr->t;
     t.clock = vm.clock; t.n_mem_ops = (uint32_t)vm.mem_ops.size(); t.n_add_ops = (uint32_t)vm.adds.size(); t.n_sub_ops = (uint32_t)vm.subs.size();
-    lap("vm run");
     build_cpu(vm, t);
     lap("cpu");
     build_mem(vm, t);
@@ -559,11 +568,61 @@ static int machine_run_impl(const int32_t* program_words, uint64_t n_instr, uint
         }
         t.main[13] = {t.store[13].data(), h, 6};
     }
-    t.cells = std::move(vm.cells);
+    t.cells = vm.cells;
     lap("rest");
-    *out = tr.release();
+    return tr.release();
+}
+
+static int machine_run_impl(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                            const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
+                            vgpu_traces** out, char* err, uint64_t err_len) {
+    Vm vm;
+    if (vm_run_impl(program_words, n_instr, initial_pc, initial_fp, max_cycles, static_addrs, static_values, n_static, vm, err, err_len) != 0) return -1;
+    *out = build_traces_host(vm);
     return 0;
 }
+
+// ---- the interpreter's logs as an object: Machine::run without the row fill (the device builds the rows, witness.cu) ----
+}  // extern "C"
+struct vgpu_vmlog { Vm vm; std::vector<int32_t> program; std::vector<uint32_t> st_addr, st_val; VgVmLogs view; };
+extern "C" {
+
+int32_t vgpu_vm_run(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
+                    const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static, vgpu_vmlog** out, char* err, uint64_t err_len) {
+    try {
+        std::unique_ptr<vgpu_vmlog> L(new vgpu_vmlog());
+        L->program.assign(program_words, program_words + 6 * n_instr);
+        if (vm_run_impl(L->program.data(), n_instr, initial_pc, initial_fp, max_cycles, static_addrs, static_values, n_static, L->vm, err, err_len) != 0) return -1;
+        Vm& vm = L->vm;
+        for (auto& c : vm.static_cells) { L->st_addr.push_back(c.first); L->st_val.push_back(c.second); }
+        VgVmLogs& v = L->view;
+        v.program = L->program.data(); v.n_instr = n_instr;
+        v.cpu = vm.cpu.data(); v.n_cpu = vm.cpu.size();
+        v.mem = vm.mem_ops.data(); v.n_mem = vm.mem_ops.size();
+        v.adds = vm.adds.data(); v.n_adds = vm.adds.size();
+        v.subs = vm.subs.data(); v.n_subs = vm.subs.size();
+        v.lts = vm.lts.data(); v.n_lts = vm.lts.size();
+        v.bits = vm.bits.data(); v.n_bits = vm.bits.size();
+        v.prog_counts = vm.prog_counts.data(); v.range_count = vm.range_count;
+        v.static_addr = L->st_addr.data(); v.static_value = L->st_val.data(); v.n_static = L->st_addr.size();
+        *out = L.release();
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && err_len) { std::snprintf(err, err_len, "interpreter run failed: %s", e.what()); }
+        return -1;
+    }
+}
+const VgVmLogs* vg_vmlog_view(const vgpu_vmlog* l) { return &l->view; }
+void vgpu_vmlog_stats(const vgpu_vmlog* l, uint32_t* clock, uint32_t* mem_ops, uint32_t* add_ops) {
+    *clock = l->vm.clock; *mem_ops = (uint32_t)l->vm.mem_ops.size(); *add_ops = (uint32_t)l->vm.adds.size();
+}
+// Chip::generate_trace x14 on the host from the same logs (the reference witness the device builder is compared with)
+int32_t vgpu_vmlog_traces(vgpu_vmlog* l, vgpu_traces** out, char* err, uint64_t err_len) {
+    try { *out = build_traces_host(l->vm); return 0; }
+    catch (const std::exception& e) { if (err && err_len) std::snprintf(err, err_len, "host witness generation failed: %s", e.what()); return -1; }
+}
+void vgpu_vmlog_free(vgpu_vmlog* l) { delete l; }
+
 
 int vgpu_machine_run_static(const int32_t* program_words, uint64_t n_instr, uint32_t initial_pc, uint32_t initial_fp, uint64_t max_cycles,
                           const uint32_t* static_addrs, const uint32_t* static_values, uint64_t n_static,
