@@ -429,6 +429,32 @@ def main():
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         proofs_identical = bool(tmin.item() == tmax.item())
 
+    # ---- the same call from PAGEABLE caller memory (what a Rust Vec is), and from the same memory page-locked in place ----
+    e2e_other = {}
+    try:
+        steps_p = min(args.steps, 3)
+        def timed(label):
+            vb.prove_machine(cfg, traces)
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(steps_p):
+                pr = vb.prove_machine(cfg, traces)
+            p1.record(stream)
+            barrier()
+            v, _ = aggregate_throughput(dist, rows * steps_p, p0.elapsed_time(p1), device="cuda", sum_rows=False)
+            e2e_other[label] = {"value": v, "unit": "rows/s", "proof_equals": bool(pr == proof)}
+        timed("pageable")
+        t0 = time.perf_counter()
+        for m in list(traces.main) + list(traces.preprocessed):
+            ctx.host_register(m)
+        e2e_other["register_s"] = time.perf_counter() - t0
+        timed("registered_in_place")
+        for m in list(traces.main) + list(traces.preprocessed):
+            ctx.host_unregister(m)
+    except Exception as exc:   # noqa: BLE001
+        e2e_other["error"] = "%s: %s" % (type(exc).__name__, exc)
+
     # ---- from the PROGRAM to the proof: host interpreter -> logs -> device row fill (witness.cu) -> prove; beside it the host row fill ----
     with_witness = None
     try:
@@ -608,7 +634,8 @@ def main():
                                        "contiguous row shards, sub-tree / quotient / openings / FRI per rank, %d x 32 B sub-roots all-gathered" % (G, G)) if G > 1 else "single GPU",
                        "host_tracegen_s": tracegen_s},
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": len(proof) * G,
-                    "note": "every rank copies its rows of the tall traces (1/N of them) and the short traces whole; every rank reads the proof back"},
+                    "note": "every rank copies its rows of the tall traces (1/N of them) and the short traces whole; every rank reads the proof back; `value` is from page-locked (torch pinned) buffers",
+                    "other_host_memory": e2e_other},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

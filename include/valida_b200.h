@@ -56,6 +56,12 @@ uint32_t vgpu_ctx_kernel_stats(vgpu_ctx* ctx, const char** names, uint32_t* laun
  * row-major or NULL for CosetMds<_,16>::default(). */
 int32_t vgpu_set_challenger(vgpu_ctx* ctx, const uint32_t round_constants[480], const uint32_t* mds_16x16_or_null);
 
+/* ---- caller memory: page-lock the buffers that vgpu_prove / vgpu_commit_batches_host read (RowMajorMatrix<Val>.values of the traces), so
+ * that their host-to-device copies run asynchronously and overlap the commits; without it the CUDA runtime stages each copy and the call
+ * blocks.  Registration costs about as much as one copy of the buffer: register once per buffer that is proven from repeatedly. ------------ */
+int32_t vgpu_host_register(vgpu_ctx* ctx, const void* p, uint64_t bytes);
+int32_t vgpu_host_unregister(vgpu_ctx* ctx, const void* p);
+
 /* ---- device matrices (K12 staging: H2D + row-major -> column-major + repr conversion) ---------- */
 int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out);
 /* Split proof (multi-GPU section below): of a trace tall enough to be split a rank keeps ITS contiguous run of rows only;
@@ -72,7 +78,11 @@ void vgpu_dmat_free(vgpu_dmat* m);
 /* ---- p3-dft: TwoAdicSubgroupDft::dft_batch / idft_batch / coset_lde_batch ------------------------
  * (reached via pcs.commit_batches, derive/src/lib.rs:309,330,355).  In place, natural order in and out. */
 int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse);
-/* out = evaluations over shift*K, |K| = height << log_blowup; bit_reversed != 0 stores row r at reverse_bits(r). */
+/* out = evaluations over shift*K, |K| = height << log_blowup; bit_reversed != 0 stores row r at reverse_bits(r).
+ * Sizes: vgpu_ntt_batch takes every power-of-two height up to 2^27 (BabyBear's two-adicity; heights up to 2^24 run on the fast tiles the
+ * prover uses, taller ones on generic tile movement).  vgpu_coset_lde_batch takes log_blowup 1..4 with natural-order output and
+ * log_blowup = 1 (the FriConfig of basic/src/bin/valida.rs:385-390, what every commit uses) with bit-reversed output; anything else
+ * returns an error naming the limit. */
 int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_blowup, uint32_t shift_canonical,
                              int32_t bit_reversed, vgpu_dmat** out);
 /* Host-buffer variants (row-major, `repr` words; H2D/D2H inside): the e2e path of bench.py. */

@@ -128,3 +128,40 @@ def test_ntt_config2_full_size_vs_oracle(ctx, oracle, w):
     got = dft.dft_batch(d).download()
     assert np.array_equal(got, oracle.dft(x))
     assert np.array_equal(dft.idft_batch(d).download(), x)
+
+
+@pytest.mark.parametrize("log_h", [25, 26])
+def test_ntt_above_2p24_roundtrip_and_oracle(ctx, oracle, log_h):
+    """Natural-order transforms above 2^24 (the split halves exceed the fast 2^12 tiles): forward == oracle, inverse restores."""
+    import valida_b200 as vb
+
+    rng = np.random.default_rng(log_h)
+    x = rng.integers(0, P, (1 << log_h, 1), dtype=np.uint32)
+    dft = vb.Radix2Dft(ctx)
+    d = ctx.upload(x)
+    dft.dft_batch(d)
+    got = d.download()
+    if log_h == 25:
+        assert np.array_equal(got, oracle.dft(x))
+    else:   # two outputs by the defining sum (the oracle would need a minute): X[0] = sum_j x[j], X[n/2] = sum_j (-1)^j x[j]
+        col = x[:, 0].astype(np.uint64)
+        even, odd = int(col[0::2].sum() % P), int(col[1::2].sum() % P)
+        assert int(got[0, 0]) == (even + odd) % P
+        assert int(got[1 << (log_h - 1), 0]) == (even - odd) % P
+    dft.idft_batch(d)
+    assert np.array_equal(d.download(), x)
+
+
+def test_coset_lde_larger_blowups_natural_order(ctx, oracle):
+    import valida_b200 as vb
+
+    rng = np.random.default_rng(77)
+    x = rng.integers(0, P, (1 << 9, 3), dtype=np.uint32)
+    dft = vb.Radix2Dft(ctx)
+    for added_bits in (2, 3):
+        got = dft.coset_lde_batch(ctx.upload(x), added_bits, 31).download()
+        assert np.array_equal(got, oracle.coset_lde(x, added_bits, 31, False))
+    with pytest.raises(vb.VgpuError, match="log_blowup = 1 only"):
+        dft.coset_lde_batch(ctx.upload(x), 2, 31, bit_reversed=True)
+    with pytest.raises(vb.VgpuError, match="1..4"):
+        dft.coset_lde_batch(ctx.upload(x), 5, 31)

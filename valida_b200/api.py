@@ -44,6 +44,8 @@ def _load():
         "vgpu_ctx_launch_count": (u64, [vp]),
         "vgpu_ctx_set_kernel_timing": (C.c_int32, [vp, C.c_int32]),
         "vgpu_ctx_kernel_stats": (C.c_uint32, [vp, C.POINTER(C.c_char_p), u32p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_uint32]),
+        "vgpu_host_register": (C.c_int32, [vp, vp, u64]),
+        "vgpu_host_unregister": (C.c_int32, [vp, vp]),
         "vgpu_dmat_upload": (C.c_int32, [vp, C.POINTER(_Matrix), C.c_int32, C.POINTER(vp)]),
         "vgpu_dmat_upload_rows": (C.c_int32, [vp, C.POINTER(_Matrix), C.c_int32, C.POINTER(vp)]),
         "vgpu_dmat_local_rows": (C.c_int32, [vp, C.POINTER(u64), C.POINTER(u64)]),
@@ -181,6 +183,13 @@ class Context:
         self.check(lib().vgpu_dmat_upload_rows(self._h, C.byref(m), repr, C.byref(out)))
         return DeviceMatrix(self, out)
 
+    def host_register(self, array):
+        """Page-lock a numpy array the caller will prove from repeatedly (its uploads then overlap the commits)."""
+        self.check(lib().vgpu_host_register(self._h, C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def host_unregister(self, array):
+        self.check(lib().vgpu_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
+
     def upload(self, row_major, repr=REPR_CANONICAL):
         """RowMajorMatrix<Val> (numpy h x w uint32) -> DeviceMatrix."""
         a = _as_u32(row_major)
@@ -280,7 +289,7 @@ class TwoAdicFriPcs:
 
     def __init__(self, ctx, log_blowup=1, num_queries=40, proof_of_work_bits=8):
         if log_blowup != 1:
-            raise VgpuError("only log_blowup = 1 is built (basic/src/bin/valida.rs:385-390)")
+            raise VgpuError("the commit path is built for log_blowup = 1 (FriConfig of basic/src/bin/valida.rs:385-390); Radix2Dft.coset_lde_batch takes 1..4")
         self.ctx, self._log_blowup = ctx, log_blowup
         self.num_queries, self.proof_of_work_bits = num_queries, proof_of_work_bits
 

@@ -187,6 +187,24 @@ uint32_t vgpu_ctx_kernel_stats(vgpu_ctx* ctx, const char** names, uint32_t* laun
     return out;
 }
 
+// ---- caller memory ---------------------------------------------------------------------------------
+// vgpu_prove copies the traces out of the caller's buffers on a copy stream while the commits of earlier matrices run.  From
+// PAGEABLE memory (a Rust Vec, a numpy array) the CUDA runtime stages every copy through its own bounce buffer and the copy call
+// blocks the host; page-locking the buffers once lets the same call overlap for real.
+int32_t vgpu_host_register(vgpu_ctx* ctx, const void* p, uint64_t bytes) {
+    VG_TRY(vg_enter(ctx));
+    cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) VG_FAIL(ctx, "cudaHostRegister(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return 0;
+}
+int32_t vgpu_host_unregister(vgpu_ctx* ctx, const void* p) {
+    VG_TRY(vg_enter(ctx));
+    cudaError_t e = cudaHostUnregister(const_cast<void*>(p));
+    if (e != cudaSuccess) { cudaGetLastError(); VG_FAIL(ctx, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
 // ---- device matrices -----------------------------------------------------------------------------
 int32_t vgpu_dmat_upload(vgpu_ctx* ctx, const vgpu_matrix* host, int32_t repr, vgpu_dmat** out) {
     if (!host || !out) VG_FAIL(ctx, "dmat_upload: null argument");
@@ -253,7 +271,6 @@ int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
     while ((1ull << log_n) < m->h) log_n++;
     if ((1ull << log_n) != m->h) VG_FAIL(ctx, "ntt_batch: height %llu is not a power of two", (unsigned long long)m->h);
     if (log_n > VG_LOG_NMAX) VG_FAIL(ctx, "ntt_batch: height exceeds two-adicity");
-    if (log_n > 24) VG_FAIL(ctx, "ntt_batch: heights above 2^24 need a three-pass split (not built yet)");
     if (m->bitrev_rows) VG_FAIL(ctx, "ntt_batch: matrix rows are stored bit-reversed");
     VG_TRY(vg_dmat_materialize(ctx, m));
     uint32_t* tmp = nullptr;
@@ -264,13 +281,13 @@ int32_t vgpu_ntt_batch(vgpu_ctx* ctx, vgpu_dmat* m, int32_t inverse) {
 }
 
 int32_t vgpu_coset_lde_batch(vgpu_ctx* ctx, const vgpu_dmat* in, uint32_t log_blowup, uint32_t shift_canonical, int32_t bit_reversed, vgpu_dmat** out) {
-    if (log_blowup != 1) VG_FAIL(ctx, "coset_lde: only log_blowup = 1 (FriConfig of basic/src/bin/valida.rs:385-390) is built");
+    if (log_blowup < 1 || log_blowup > 4) VG_FAIL(ctx, "coset_lde: log_blowup must be 1..4");
     VG_TRY(vg_enter(ctx));
     if (in->dist != VG_FULL) VG_FAIL(ctx, "coset_lde: the matrix is a shard of a split proof");
     VG_TRY(vg_dmat_materialize(ctx, in));
     vgpu_dmat* o = nullptr;
-    VG_TRY(vg_dmat_alloc(ctx, in->h * 2, in->w, &o));
-    int32_t rc = vg_coset_lde(ctx, in->d, in->col_stride, in->h, in->w, shift_canonical, o->d, o->col_stride, bit_reversed != 0, in->bitrev_rows);
+    VG_TRY(vg_dmat_alloc(ctx, in->h << log_blowup, in->w, &o));
+    int32_t rc = vg_coset_lde(ctx, in->d, in->col_stride, in->h, in->w, shift_canonical, o->d, o->col_stride, bit_reversed != 0, in->bitrev_rows, log_blowup);
     if (rc) { vgpu_dmat_free(o); return rc; }
     *out = o;
     return 0;

@@ -160,7 +160,7 @@ int32_t vg_dmat_alloc_dist(vgpu_ctx* ctx, int dist, uint64_t gh, uint64_t gw, bo
 int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, int log_n, uint64_t w,
                        bool inverse, const PowTable* coset_or_null, uint32_t* tmp, uint64_t tmp_cs);
 int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64_t h, uint64_t w, uint32_t shift_canonical,
-                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev = false);
+                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev = false, uint32_t log_blowup = 1);
 // staging.cu
 int32_t vg_upload_begin(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);   // async copy only
 int32_t vg_dmat_materialize(vgpu_ctx* ctx, const vgpu_dmat* m);                                                       // no-op unless an upload is pending

@@ -600,7 +600,9 @@ int32_t vg_ntt_nat2nat(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint
         else if (inverse) { p.post_mode = 3; p.post_scale = ninv; }
         return launch_pass(ctx, p, w);
     }
-    if (log_n > 2 * LOG_COL_MAX) VG_FAIL(ctx, "ntt: natural->natural transforms above 2^%d are not built", 2 * LOG_COL_MAX);
+    // up to 2^24 both halves of the split are <= 2^12 (the fast strided tiles); above that the halves grow to 2^13 / 2^14 and fall back
+    // on the generic tile movement: every size up to the field's two-adicity works, the sizes the prover uses are the fast ones
+    if (log_n > VG_LOG_NMAX) VG_FAIL(ctx, "ntt: 2^%d exceeds BabyBear's two-adicity (2^%d)", log_n, VG_LOG_NMAX);
     const int l1 = (log_n + 1) / 2, l2 = log_n - l1;
     const uint64_t n1 = 1ull << l1, n2 = 1ull << l2;
     // pass 1: over i1 (stride n2) for each i2; times w_n^(+-i2*k1); transposed store tmp[i2][k1]
@@ -699,12 +701,13 @@ static int32_t ntt_bitrev2bitrev(vgpu_ctx* ctx, const uint32_t* coef, uint64_t c
 
 // coset_lde_batch(mat, added_bits = 1, shift): dst (2h rows per column).
 int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64_t h, uint64_t w, uint32_t shift_canonical,
-                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev) {
+                     uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev, uint32_t log_blowup) {
     if (src_bitrev && !bit_reversed) VG_FAIL(ctx, "coset_lde: a bit-reversed-row input is only supported with bit-reversed output");
+    if (bit_reversed && log_blowup != 1) VG_FAIL(ctx, "coset_lde: committed (bit-reversed) extensions are built for log_blowup = 1 only (FriConfig of basic/src/bin/valida.rs:385-390)");
     int log_n = 0;
     while ((1ull << log_n) < h) log_n++;
     if ((1ull << log_n) != h) VG_FAIL(ctx, "coset_lde: height %llu is not a power of two", (unsigned long long)h);
-    if (log_n + 1 > VG_LOG_NMAX) VG_FAIL(ctx, "coset_lde: LDE height 2^%d exceeds BabyBear two-adicity", log_n + 1);
+    if (log_n + (int)log_blowup > VG_LOG_NMAX) VG_FAIL(ctx, "coset_lde: LDE height 2^%d exceeds BabyBear two-adicity", log_n + (int)log_blowup);
     if (log_n > LOG_ROW_MAX + LOG_COL_MAX) VG_FAIL(ctx, "coset_lde: heights above 2^%d are not built", LOG_ROW_MAX + LOG_COL_MAX);
     const PowTable* tab = nullptr;
     uint32_t ninv_canon = bb::from_monty(bb::inv(bb::to_monty((uint32_t)(h % bb::P))));
@@ -728,16 +731,17 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
             if (rc) break;
             rc = ntt_bitrev2bitrev(ctx, coef, h, dst + c0 * dst_cs + h, dst_cs, tmp, h, log_n, wc, true);
         } else {
-            // natural-order output (API completeness, not on the proving path): zero-pad and transform at size 2h
+            // natural-order output (API completeness, not on the proving path): zero-pad and transform at size h << log_blowup
             rc = vg_ntt_nat2nat(ctx, src + c0 * src_cs, src_cs, coef, h, log_n, wc, true, tab, tmp, h);
             if (rc) break;
+            const uint64_t H = h << log_blowup;
             uint32_t* padb = nullptr; uint32_t* tmp2 = nullptr;
-            rc = vg_alloc(ctx, (void**)&padb, wc * 2 * h * 4); if (rc) break;
-            rc = vg_alloc(ctx, (void**)&tmp2, wc * 2 * h * 4); if (rc) { vg_free(ctx, padb); break; }
-            uint64_t tot = 2 * h * wc;
-            zero_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(coef, h, padb, 2 * h, h, 2 * h, wc);
+            rc = vg_alloc(ctx, (void**)&padb, wc * H * 4); if (rc) break;
+            rc = vg_alloc(ctx, (void**)&tmp2, wc * H * 4); if (rc) { vg_free(ctx, padb); break; }
+            uint64_t tot = H * wc;
+            zero_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(coef, h, padb, H, h, H, wc);
             ctx->launches++;
-            rc = vg_ntt_nat2nat(ctx, padb, 2 * h, dst + c0 * dst_cs, dst_cs, log_n + 1, wc, false, nullptr, tmp2, 2 * h);
+            rc = vg_ntt_nat2nat(ctx, padb, H, dst + c0 * dst_cs, dst_cs, log_n + (int)log_blowup, wc, false, nullptr, tmp2, H);
             vg_free(ctx, padb); vg_free(ctx, tmp2);
         }
     }
