@@ -549,6 +549,22 @@ def main():
         if ntt:
             a = (ntt[0][3] / 1e9) / (ntt[0][2] / 1e3)
             roofline["ntt_pass"] = {"achieved": a, "frac": a / peak, "unit": "GB/s", "bytes": "8 B per element per pass (read+write)"}
+            # What bounds a pass (ncu --set full of the shipping kernel, profiles/r02_ntt_v7_raw.csv + the source page): it is ISSUE bound,
+            # not HBM bound.  A radix-2 butterfly on 32-bit Montgomery words is 8 instructions (3 IMAD for the product, 3 adds, 2 min) =
+            # 4 per element-stage; a 14-stage pass executes 100.5 instructions per element (67 arithmetic — 56 butterfly floor + the
+            # inter-pass twiddle and its running product — 13.5 shared-memory accesses, 20 addressing / control) at 57-62 % issue-slot
+            # utilisation (two-way bank conflicts on the last radix-4 step, math-pipe throttle).  At the butterfly floor and full issue a
+            # pass would run at about the HBM peak; a transform is two passes, so its ALGORITHMIC rate (8 B per element per transform)
+            # is capped at half of whatever a pass reaches: 50 % of HBM at best, the north star's 70 % is not reachable in two passes.
+            sm_hz = (clocks.get("sm_mhz") or 1965) * 1e6
+            issue = 148 * 128 * sm_hz                                   # thread-instructions per second, one per lane per clock
+            roofline["ntt_pass"]["ceiling"] = {
+                "bound": "issue slots (INT32 butterflies), not HBM",
+                "gbs_per_pass_at_butterfly_floor": 8.0 * issue / (11.5 * 4) / 1e9,      # 11.5 stages per pass on average, 4 instructions per element-stage
+                "algorithmic_cap_of_a_two_pass_transform": "half of the per-pass rate",
+                "measured": {"instructions_per_element_14_stage_pass": 100.5, "of_which_arithmetic": 67, "butterfly_floor": 56, "issue_active_pct": "57-62",
+                             "gbs_per_pass_ncu": {"2^8-stage column pass": 3010, "2^10": "1580-2260", "2^14-stage row pass": "1460-1640"}},
+                "source": "profiles/r02_ntt_v7_raw.csv (ncu --set full, shipping kernel), profiles/r02_summary.md"}
 
         # ---- second headline figure: BASELINE config 2 — 2^20 x 64 BabyBear NTT + inverse, device resident ----
         ntt_line = None

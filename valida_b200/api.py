@@ -10,6 +10,7 @@ VgpuError carrying vgpu_last_error().
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -122,6 +123,7 @@ class Context:
     """One context per device/stream (single-threaded)."""
 
     def __init__(self, device=0, stream=None):
+        self._children = weakref.WeakSet()      # handles that point into this context: released before the context goes
         self._h = C.c_void_p()
         rc = lib().vgpu_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h))
         if rc != 0:
@@ -201,7 +203,13 @@ class Context:
         return DeviceMatrix(self, out)
 
     def close(self):
+        """Destroys the context.  Device matrices / prover data created from it are released first (their handles would dangle)."""
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):
+                try:
+                    child.free()
+                except Exception:
+                    pass
             lib().vgpu_ctx_destroy(self._h)
             self._h = None
 
@@ -215,6 +223,7 @@ class Context:
 class DeviceMatrix:
     def __init__(self, ctx, handle, owned=True):
         self.ctx, self._h, self._owned = ctx, handle, owned
+        ctx._children.add(self)
 
     @property
     def shape(self):
@@ -235,7 +244,7 @@ class DeviceMatrix:
         return out
 
     def free(self):
-        if self._h and self._owned:
+        if self._h and self._owned and self.ctx._h:
             lib().vgpu_dmat_free(self._h)
         self._h = None
 
@@ -269,11 +278,12 @@ class Radix2Dft:
 class ProverData:
     def __init__(self, ctx, handle, n):
         self.ctx, self._h, self.n = ctx, handle, n
+        ctx._children.add(self)
 
     def free(self):
-        if self._h:
+        if self._h and self.ctx._h:
             lib().vgpu_prover_data_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:

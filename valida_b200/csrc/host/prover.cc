@@ -402,6 +402,7 @@ int32_t vgpu_challenger_sample_ext(vgpu_ctx* ctx, uint32_t out[5]) {
 int32_t vgpu_open(vgpu_ctx* ctx, const vgpu_prover_data* const* rounds, uint32_t n_rounds, const uint32_t* n_points, const uint32_t* points,
                   uint8_t** out_cbor, uint64_t* out_len) {
     if (!rounds || !n_points || !points || !out_cbor || !out_len) VG_FAIL(ctx, "open: null argument");
+    VG_TRY(vg_enter(ctx));
     if (!ctx->challenger) VG_TRY(vgpu_challenger_reset(ctx));
     std::vector<OpenRound> rds(n_rounds);
     size_t mi = 0, pi = 0;

@@ -298,6 +298,7 @@ extern "C" int32_t vgpu_verify(vgpu_ctx* ctx, const uint8_t* proof, uint64_t pro
     if (!ctx) return -1;
     if (!proof || !prep || !verdict) VG_FAIL(ctx, "verify: null argument");
     if (!ctx->challenger_set) VG_FAIL(ctx, "verify: vgpu_set_challenger has not been called");
+    VG_TRY(vg_enter(ctx));
     *verdict = VGPU_REJECT_MALFORMED;
     ProofV pf;
     if (!decode(proof, proof_len, &pf)) return 0;

@@ -250,6 +250,7 @@ int32_t vg_perm_trace_enqueue(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const v
     uint32_t k = chip->n_interactions;
     vgpu_dmat* perm = nullptr;
     VG_TRY(split ? vg_dmat_alloc_dist(ctx, VG_ROWS, main->gh, 5 * (k + 1), false, &perm) : vg_dmat_alloc(ctx, h, 5 * (k + 1), &perm));
+    struct Undo { vgpu_dmat* m; ~Undo() { vgpu_dmat_free(m); } } undo{perm};       // released on every failing exit below
     // first swept row of a matrix: a shard starts there, a whole trace is entered at row0
     auto rows_of = [&](const vgpu_dmat* m) { return m->d + (m->dist == VG_ROWS ? 0 : row0); };
     const uint32_t* md = rows_of(main);
@@ -277,6 +278,7 @@ int32_t vg_perm_trace_enqueue(vgpu_ctx* ctx, const vgpu_chip_desc* chip, const v
     }
     *n_totals = split ? (uint32_t)ctx->comm_size : 1;
     *out_perm = perm;
+    undo.m = nullptr;
     return 0;
 }
 uint32_t vg_perm_totals_ranks(const vgpu_ctx* ctx) { return vg_sharded(ctx) ? (uint32_t)ctx->comm_size : 1; }
