@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __r
 // level by level in shared memory (each level is written to its place in global memory as well), so the 10 - 16 launches of a tree's
 // tail — each a handful of warps waiting on a single Keccak-f — become one or two.  Bases are virtual (+ global node index), as in
 // compress_layer_kernel; inj_v[k] = digests of the rows a shorter matrix group contributes at fused level k, or null.
-constexpr int TAIL_SUB = 512, TAIL_THREADS = 256, TAIL_MAX_LEVELS = 10;
+constexpr int TAIL_SUB = 256, TAIL_THREADS = 256, TAIL_MAX_LEVELS = 9;      // one node per thread at the first fused level
 struct TailParams {
     const uint32_t* prev_v;
     uint32_t* next_v[TAIL_MAX_LEVELS];
