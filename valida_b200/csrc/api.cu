@@ -149,6 +149,7 @@ int32_t vgpu_ctx_create(int32_t device, void* cuda_stream, vgpu_ctx** out) {
 void vgpu_ctx_destroy(vgpu_ctx* ctx) {
     if (!ctx) return;
     vg_host_state_free(ctx);
+    vg_stager_free(ctx);
     vg_comm_free(ctx);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
@@ -255,9 +256,11 @@ int32_t vgpu_dmat_local_rows(const vgpu_dmat* m, uint64_t* row0, uint64_t* rows)
 void vgpu_dmat_free(vgpu_dmat* m) {
     if (!m) return;
     if (m->pend_stage) {   // an upload that was never consumed: let the copy finish, then release
-        cudaEventSynchronize(m->pend_ev);
+        if (m->pend_job) vg_stager_finish(m->ctx);       // joins the staging threads: every chunk is enqueued
+        if (m->pend_ev) cudaEventSynchronize(m->pend_ev);
+        else if (m->ctx->copy_stream) cudaStreamSynchronize(m->ctx->copy_stream);
         vg_free(m->ctx, m->pend_stage);
-        m->ctx->event_pool.push_back(m->pend_ev);
+        if (m->pend_ev) m->ctx->event_pool.push_back(m->pend_ev);
     }
     if (m->owns) { if (m->symm) vg_symm_free(m->ctx, m->d); else vg_free(m->ctx, m->d); }
     delete m;

@@ -72,6 +72,7 @@ struct vgpu_ctx {
     struct CommStat { uint32_t calls = 0; double bytes = 0; };
     CommStat stat_barrier, stat_allgather, stat_exchange;        // per-proof collective counters (bench.py)
     cudaStream_t copy_stream = nullptr;                         // H2D copies of a pipelined vgpu_prove (staging.cu)
+    void* stager = nullptr;                                     // VgStager*: host threads staging pageable traces through pinned chunks
     cudaStream_t xfer_stream = nullptr;                         // split proof: peer-store exchange of matrix i behind the LDE of matrix i+1
     cudaEvent_t xfer_ev[3] = {nullptr, nullptr, nullptr};       // [0], [1]: exchange out of buffer 0 / 1 done; [2]: LDE done
     bool ntt_attrs_set = false, bary_attrs_set = false;          // cudaFuncSetAttribute is per device: tracked per context, not per process
@@ -98,6 +99,7 @@ struct vgpu_dmat {
     uint32_t* pend_stage = nullptr;
     cudaEvent_t pend_ev = nullptr;
     int32_t pend_repr = 0;
+    void* pend_job = nullptr;    // StageJob* when the source is pageable memory copied by the context's staging threads
 };
 
 #define VG_FAIL(ctx, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (ctx)->err = _b; return -1; } while (0)
@@ -163,6 +165,9 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
                      uint32_t* dst, uint64_t dst_cs, bool bit_reversed, bool src_bitrev = false, uint32_t log_blowup = 1);
 // staging.cu
 int32_t vg_upload_begin(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);   // async copy only
+int32_t vg_stager_start(vgpu_ctx* ctx);                       // after the last vg_upload_begin of a proof
+int32_t vg_stager_finish(vgpu_ctx* ctx);                      // before the caller's buffers may change again
+void vg_stager_free(vgpu_ctx* ctx);
 int32_t vg_dmat_materialize(vgpu_ctx* ctx, const vgpu_dmat* m);                                                       // no-op unless an upload is pending
 int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst);
 int32_t vg_download_rowmajor(vgpu_ctx* ctx, const vgpu_dmat* src, int32_t repr, uint32_t* host);

@@ -608,9 +608,13 @@ int32_t vgpu_prove(vgpu_ctx* ctx, const vgpu_matrix main[VGPU_NUM_CHIPS], const 
     for (int i : order) VG_TRY(begin_upload(main[i], dm.v[i]));
     float up = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     ctx->phases.push_back({"upload traces (H2D enqueue; copies overlap the commits)", up});
+    // traces in pageable memory are copied by the context's staging threads from here on (staging.cu)
+    struct StagerGuard { vgpu_ctx* c; ~StagerGuard() { vg_stager_finish(c); } } sg{ctx};
+    VG_TRY(vg_stager_start(ctx));
     ctx->in_host_prove = true;
     int32_t rc = vgpu_prove_device(ctx, dm.v.data(), dp.v.data(), proof_out, proof_len);
     ctx->in_host_prove = false;
+    if (rc == 0) rc = vg_stager_finish(ctx);
     return rc;
 }
 

@@ -3,6 +3,12 @@
 // a shared-memory tile transpose: 64 rows x w words are read as one contiguous run (coalesced) and
 // written as w runs of 64 consecutive rows (256 B segments).
 #include "ctx.h"
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
 
 namespace {
 constexpr int TR = 64;      // rows per tile
@@ -60,6 +66,101 @@ int32_t vg_upload_rowmajor(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint
     return rc;
 }
 
+// ---- uploads out of PAGEABLE caller memory (a Rust Vec, a numpy array) ------------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the runtime through one bounce buffer on the calling thread (~7 GB/s measured:
+// 0.3 s for the 2 GB of a 2^22-row witness, twice the proving time).  Here a few host threads copy 16 MB chunks into page-locked
+// buffers of the context and enqueue the chunk copies on the copy stream themselves; the proving thread goes on enqueueing kernels
+// and only waits, per matrix, until that matrix's last chunk has been ENQUEUED (vg_dmat_materialize), not until it has arrived.
+namespace {
+constexpr size_t STAGE_CHUNK = 16u << 20, STAGE_MIN = 8u << 20;
+constexpr int STAGE_THREADS = 6;
+struct StageJob {
+    const uint8_t* src; uint8_t* dst; size_t bytes, first_chunk, nchunks;
+    cudaEvent_t done = nullptr;
+    std::atomic<size_t> left{0};
+    std::atomic<bool> issued{false};
+};
+}  // namespace
+struct VgStager {
+    std::vector<std::unique_ptr<StageJob>> jobs;
+    std::vector<std::thread> threads;
+    std::mutex mu; std::condition_variable cv;
+    uint8_t* pinned[STAGE_THREADS][2] = {};
+    cudaEvent_t free_ev[STAGE_THREADS][2] = {};
+    std::atomic<bool> failed{false};
+    bool running = false;
+};
+namespace {
+void stager_worker(vgpu_ctx* ctx, VgStager* st, int t) {
+    cudaSetDevice(ctx->device);
+    bool used[2] = {false, false};
+    int b = 0;
+    for (auto& jp : st->jobs) {
+        StageJob& j = *jp;
+        for (size_t c = 0; c < j.nchunks; c++) {
+            if ((j.first_chunk + c) % STAGE_THREADS != (size_t)t) continue;
+            const size_t off = c * STAGE_CHUNK, n = std::min(STAGE_CHUNK, j.bytes - off);
+            bool ok = !st->failed.load();
+            if (ok && used[b]) ok = cudaEventSynchronize(st->free_ev[t][b]) == cudaSuccess;
+            if (ok) {
+                std::memcpy(st->pinned[t][b], j.src + off, n);
+                ok = cudaMemcpyAsync(j.dst + off, st->pinned[t][b], n, cudaMemcpyHostToDevice, ctx->copy_stream) == cudaSuccess &&
+                     cudaEventRecord(st->free_ev[t][b], ctx->copy_stream) == cudaSuccess;
+                used[b] = true; b ^= 1;
+            }
+            if (!ok) st->failed.store(true);
+            if (j.left.fetch_sub(1) == 1) {        // the last chunk of this matrix has been enqueued (by whichever thread)
+                if (cudaEventRecord(j.done, ctx->copy_stream) != cudaSuccess) st->failed.store(true);
+                { std::lock_guard<std::mutex> lk(st->mu); j.issued.store(true); }
+                st->cv.notify_all();
+            }
+        }
+    }
+}
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+}  // namespace
+
+// after the last vg_upload_begin of a vgpu_prove: start copying
+int32_t vg_stager_start(vgpu_ctx* ctx) {
+    VgStager* st = (VgStager*)ctx->stager;
+    if (!st || st->jobs.empty() || st->running) return 0;
+    for (int t = 0; t < STAGE_THREADS; t++)
+        for (int b = 0; b < 2; b++)
+            if (!st->pinned[t][b]) {
+                VG_CUDA(ctx, cudaHostAlloc((void**)&st->pinned[t][b], STAGE_CHUNK, cudaHostAllocDefault));
+                VG_CUDA(ctx, cudaEventCreateWithFlags(&st->free_ev[t][b], cudaEventDisableTiming));
+            }
+    st->failed.store(false);
+    st->running = true;
+    for (int t = 0; t < STAGE_THREADS; t++) st->threads.emplace_back(stager_worker, ctx, st, t);
+    return 0;
+}
+// before vgpu_prove returns (also on its error paths): the caller's buffers are no longer read after this
+int32_t vg_stager_finish(vgpu_ctx* ctx) {
+    VgStager* st = (VgStager*)ctx->stager;
+    if (!st) return 0;
+    for (auto& th : st->threads) th.join();
+    st->threads.clear();
+    const bool failed = st->running && st->failed.load();
+    st->running = false;
+    for (auto& j : st->jobs) if (j->done) ctx->event_pool.push_back(j->done);
+    st->jobs.clear();
+    if (failed) VG_FAIL(ctx, "upload: a staged copy out of pageable memory failed");
+    return 0;
+}
+void vg_stager_free(vgpu_ctx* ctx) {
+    VgStager* st = (VgStager*)ctx->stager;
+    if (!st) return;
+    vg_stager_finish(ctx);
+    for (int t = 0; t < STAGE_THREADS; t++) for (int b = 0; b < 2; b++) { if (st->pinned[t][b]) cudaFreeHost(st->pinned[t][b]); if (st->free_ev[t][b]) cudaEventDestroy(st->free_ev[t][b]); }
+    delete st;
+    ctx->stager = nullptr;
+}
+
 // Pipelined form used by vgpu_prove: the copy is queued on the context's copy stream (so it overlaps the kernels of
 // matrices that arrived earlier) and the transpose is deferred to the matrix's first use on the compute stream.
 int32_t vg_upload_begin(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_t w, int32_t repr, vgpu_dmat* dst) {
@@ -74,23 +175,57 @@ int32_t vg_upload_begin(vgpu_ctx* ctx, const uint32_t* host, uint64_t h, uint64_
         VG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, fence, 0));
         ctx->event_pool.push_back(fence);
     }
-    VG_CUDA(ctx, cudaMemcpyAsync(dst->pend_stage, host, h * w * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     if (!ctx->event_pool.empty()) { dst->pend_ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
     else VG_CUDA(ctx, cudaEventCreate(&dst->pend_ev));
-    VG_CUDA(ctx, cudaEventRecord(dst->pend_ev, ctx->copy_stream));
     dst->pend_repr = repr;
+    const size_t bytes = h * w * 4;
+    if (bytes >= STAGE_MIN && is_pageable(host)) {
+        if (!ctx->stager) ctx->stager = new VgStager();
+        VgStager* st = (VgStager*)ctx->stager;
+        if (st->running) VG_FAIL(ctx, "upload: a staged upload is already running on this context");
+        std::unique_ptr<StageJob> j(new StageJob());
+        j->src = (const uint8_t*)host; j->dst = (uint8_t*)dst->pend_stage; j->bytes = bytes;
+        j->nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+        j->first_chunk = st->jobs.empty() ? 0 : st->jobs.back()->first_chunk + st->jobs.back()->nchunks;
+        j->left.store(j->nchunks);
+        j->done = dst->pend_ev;              // recorded by the thread that enqueues the last chunk
+        dst->pend_job = j.get();
+        dst->pend_ev = nullptr;              // owned by the job until it is issued
+        st->jobs.push_back(std::move(j));
+        return 0;
+    }
+    VG_CUDA(ctx, cudaMemcpyAsync(dst->pend_stage, host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VG_CUDA(ctx, cudaEventRecord(dst->pend_ev, ctx->copy_stream));
+    return 0;
+}
+
+// the event after which the row-major image of `m` is in pend_stage (waits, for a staged upload, until its last chunk is enqueued)
+static int32_t pending_event(vgpu_ctx* ctx, vgpu_dmat* m, cudaEvent_t* ev) {
+    if (m->pend_job) {
+        VgStager* st = (VgStager*)ctx->stager;
+        StageJob* j = (StageJob*)m->pend_job;
+        if (!st || !st->running) VG_FAIL(ctx, "upload: the staged copy of this matrix was never started");
+        std::unique_lock<std::mutex> lk(st->mu);
+        st->cv.wait(lk, [&] { return j->issued.load(); });
+        if (st->failed.load()) VG_FAIL(ctx, "upload: a staged copy out of pageable memory failed");
+        *ev = j->done;
+        return 0;
+    }
+    *ev = m->pend_ev;
     return 0;
 }
 
 int32_t vg_dmat_materialize(vgpu_ctx* ctx, const vgpu_dmat* cm) {
     vgpu_dmat* m = const_cast<vgpu_dmat*>(cm);   // completing a pending upload does not change the matrix's value
     if (!m || !m->pend_stage) return 0;
-    VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->pend_ev, 0));
+    cudaEvent_t ev = nullptr;
+    VG_TRY(pending_event(ctx, m, &ev));
+    VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
     int32_t rc = transpose_in(ctx, m->pend_stage, m->h, m->w, m->pend_repr, m);
     vg_free(ctx, m->pend_stage);                 // reused only by later work on the compute stream, i.e. after the transpose
     m->pend_stage = nullptr;
-    ctx->event_pool.push_back(m->pend_ev);
-    m->pend_ev = nullptr;
+    if (m->pend_ev) ctx->event_pool.push_back(m->pend_ev);      // a staged upload's event goes back with its job (vg_stager_finish)
+    m->pend_ev = nullptr; m->pend_job = nullptr;
     return rc;
 }
 
