@@ -170,7 +170,7 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
                 const Job& j = jobs[ji];
                 const uint32_t w = j.w, np = (uint32_t)j.pts->size();
                 std::vector<E5> ys;
-                vg_eval_columns_finish(sums.data() + j.sums_at, j.lde->gh, w, np, j.pts->data(), &ys);
+                vg_eval_columns_finish(sums.data() + j.sums_at, j.lde->gh, w, np, j.pts->data(), &ys, j.lde->dist == VG_ROWS ? vg_eval_columns_first_coset(w) : w);
                 E5 sum_y[2];
                 out->values.back().emplace_back();
                 for (uint32_t q = 0; q < np; q++) {
@@ -249,6 +249,7 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
     // ---- query phase: one gather for every word the proof needs (split proof: every rank reports the words it holds) ------
     HostPhase hq(ctx, "host+device: query phase (pointer list, gather, answers)");
     std::vector<const uint32_t*> ptrs;
+    ptrs.reserve(1u << 18);
     auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) ptrs.push_back(d ? d + k : nullptr); };
     for (uint64_t index : indices) {
         for (size_t i = 0; i < S.layers.size(); i++) {

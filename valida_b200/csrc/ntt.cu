@@ -566,6 +566,13 @@ int32_t launch_pass(vgpu_ctx* ctx, PassParams p, uint64_t w) {
     return 0;
 }
 
+// a one-row trace is a constant polynomial: its extension repeats the row (eight of BasicMachine's fourteen chips in a Fibonacci proof)
+__global__ void repeat_row_kernel(const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, uint64_t H, uint64_t w) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * w) return;
+    dst[(i / H) * dst_cs + (i % H)] = src[(i / H) * src_cs];
+}
+
 __global__ void zero_pad_kernel(const uint32_t* src, uint64_t src_cs, uint32_t* dst, uint64_t dst_cs, uint64_t h, uint64_t H, uint64_t w) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H * w) return;
@@ -709,6 +716,12 @@ int32_t vg_coset_lde(vgpu_ctx* ctx, const uint32_t* src, uint64_t src_cs, uint64
     if ((1ull << log_n) != h) VG_FAIL(ctx, "coset_lde: height %llu is not a power of two", (unsigned long long)h);
     if (log_n + (int)log_blowup > VG_LOG_NMAX) VG_FAIL(ctx, "coset_lde: LDE height 2^%d exceeds BabyBear two-adicity", log_n + (int)log_blowup);
     if (log_n > LOG_ROW_MAX + LOG_COL_MAX) VG_FAIL(ctx, "coset_lde: heights above 2^%d are not built", LOG_ROW_MAX + LOG_COL_MAX);
+    if (h == 1) {
+        const uint64_t H = 1ull << log_blowup;
+        repeat_row_kernel<<<(unsigned)((H * w + 127) / 128), 128, 0, ctx->stream>>>(src, src_cs, dst, dst_cs, H, w);
+        VG_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     const PowTable* tab = nullptr;
     uint32_t ninv_canon = bb::from_monty(bb::inv(bb::to_monty((uint32_t)(h % bb::P))));
     VG_TRY(vg_get_shift_table(ctx, shift_canonical, ninv_canon, h, &tab));

@@ -402,20 +402,24 @@ int32_t vg_inverse_denominators(vgpu_ctx* ctx, uint32_t log_H, const E5& z, uint
 int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t npoints, const uint32_t* const* invden, uint64_t ics, uint32_t* d_out) {
     uint64_t H = lde->gh, h = H / 2;
     uint32_t w = (uint32_t)lde->gw;
-    // split proof: the first h committed rows (the coset g*H) lie in the shards of the first half of the ranks; each of those
-    // sums its rows, the others contribute zeros, and the per-rank sums meet in one small all-gather.  invden: the caller's
-    // vector over the same rows as the matrix part held here (limb stride ics).
+    // split proof: the first h committed rows are the coset g*H and lie in the shards of the first half of the ranks, the other
+    // h rows are the coset g*w_2h*H in the shards of the second half — and EITHER coset determines p(z).  So the first-half ranks
+    // evaluate the first ceil(w/2) columns from their rows, the second-half ranks the remaining columns from theirs (all ranks
+    // work, each on half the columns); the per-rank sums meet in one small all-gather and vg_eval_columns_finish normalises a
+    // column by the coset it was summed over.  invden: the caller's vector over the same rows as the matrix part held here.
     const bool split = lde->dist == VG_ROWS;
-    const uint64_t rows = split ? (lde->row0 < h ? lde->h : 0) : h;
+    const uint32_t w_first = split ? vg_eval_columns_first_coset(w) : w;
+    const uint32_t c_begin = split && lde->row0 >= h ? w_first : 0;
+    w = split ? (lde->row0 < h ? w_first : w - w_first) : w;                // columns summed here
+    const uint64_t rows = split ? (w ? lde->h : 0) : h;
     BaryParams p{};
-    p.mat = lde->d; p.mcs = lde->col_stride; p.h = rows; p.row_begin = 0; p.w = w;
+    p.mat = lde->d + (uint64_t)c_begin * lde->col_stride; p.mcs = lde->col_stride; p.h = rows; p.row_begin = 0; p.w = w;
     p.invden[0] = invden[0]; p.invden[1] = npoints > 1 ? invden[1] : invden[0]; p.ics = ics; p.npoints = npoints;
     uint32_t nblocks = 1;
     uint32_t* partial = nullptr;
-    const uint32_t nout = w * BARY_OUT;
+    const uint32_t nout = w * BARY_OUT, nout_all = (uint32_t)lde->gw * BARY_OUT;
     if (rows == 0) {
-        VG_TRY(vg_alloc(ctx, (void**)&partial, (size_t)nout * 4));
-        VG_CUDA(ctx, cudaMemsetAsync(partial, 0, (size_t)nout * 4, ctx->stream));
+        VG_TRY(vg_alloc(ctx, (void**)&partial, 512));
     } else if (rows >= BARY_TILE && rows % BARY_TILE == 0) {
         const unsigned by = (w + 31) / 32;
         p.cpg = 2 * (((w + by - 1) / by + 1) / 2);               // columns per CTA, even
@@ -445,12 +449,16 @@ int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t np
         bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, nblocks, nout, d_out);
         VG_LAUNCH_CHECK(ctx);
     } else {
-        uint32_t* gathered = nullptr;                                                      // [rank 0 | rank 1 | ...]
-        VG_TRY(vg_alloc(ctx, (void**)&gathered, (size_t)nout * 4 * ctx->comm_size));
-        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, nblocks, nout, gathered + (size_t)nout * ctx->comm_rank);
-        VG_LAUNCH_CHECK(ctx);
-        VG_TRY(vg_comm_allgather_inplace(ctx, gathered, nout));
-        bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(gathered, (uint32_t)ctx->comm_size, nout, d_out);
+        uint32_t* gathered = nullptr;                                                      // [rank 0 | rank 1 | ...], all columns each
+        VG_TRY(vg_alloc(ctx, (void**)&gathered, (size_t)nout_all * 4 * ctx->comm_size));
+        uint32_t* mine = gathered + (size_t)nout_all * ctx->comm_rank;
+        VG_CUDA(ctx, cudaMemsetAsync(mine, 0, (size_t)nout_all * 4, ctx->stream));         // the columns the other coset's ranks sum
+        if (nout) {
+            bary_reduce_kernel<<<(nout + 255) / 256, 256, 0, ctx->stream>>>(partial, nblocks, nout, mine + (size_t)c_begin * BARY_OUT);
+            VG_LAUNCH_CHECK(ctx);
+        }
+        VG_TRY(vg_comm_allgather_inplace(ctx, gathered, nout_all));
+        bary_reduce_kernel<<<(nout_all + 255) / 256, 256, 0, ctx->stream>>>(gathered, (uint32_t)ctx->comm_size, nout_all, d_out);
         VG_LAUNCH_CHECK(ctx);
         vg_free(ctx, gathered);
     }
@@ -458,8 +466,11 @@ int32_t vg_eval_columns_enqueue(vgpu_ctx* ctx, const vgpu_dmat* lde, uint32_t np
     return 0;
 }
 
-// host arithmetic on the sums of vg_eval_columns_enqueue:  p(z) = -(z^h - s^h) / (h s^h) * (sum_i p(x_i) + z sum_i p(x_i)/(x_i - z))
-void vg_eval_columns_finish(const uint32_t* sums, uint64_t H, uint32_t w, uint32_t npoints, const E5* z, std::vector<E5>* ys /* [q][c] */) {
+uint32_t vg_eval_columns_first_coset(uint32_t w) { return (w + 1) / 2; }
+
+// host arithmetic on the sums of vg_eval_columns_enqueue:  p(z) = -(z^h - t^h) / (h t^h) * (sum_i p(x_i) + z sum_i p(x_i)/(x_i - z))
+// over the coset t*H the sums ran over: t = s for columns < w_first, t = s * w_2h (t^h = -s^h) for the others (split proof).
+void vg_eval_columns_finish(const uint32_t* sums, uint64_t H, uint32_t w, uint32_t npoints, const E5* z, std::vector<E5>* ys /* [q][c] */, uint32_t w_first) {
     const uint64_t h = H / 2;
     uint32_t log_h = 0; while ((1ull << log_h) < h) log_h++;
     uint32_t s = bb::to_monty(bb::GEN_CANON), sh = s;
@@ -468,12 +479,13 @@ void vg_eval_columns_finish(const uint32_t* sums, uint64_t H, uint32_t w, uint32
     ys->assign((size_t)npoints * w, bb::e5_zero());
     for (uint32_t q = 0; q < npoints; q++) {
         E5 zh = bb::e5_exp_pow2(z[q], (int)log_h);
-        E5 norm = bb::e5_neg(bb::e5_mul_base(bb::e5_sub_base(zh, sh), denom_inv));
+        const E5 norm_a = bb::e5_neg(bb::e5_mul_base(bb::e5_sub_base(zh, sh), denom_inv));       // -(z^h - s^h) / (h s^h)
+        const E5 norm_b = bb::e5_mul_base(bb::e5_add_base(zh, sh), denom_inv);                     // -(z^h + s^h) / (h (-s^h))
         for (uint32_t c = 0; c < w; c++) {
             E5 D;   // sum_i p_c(x_i) / (x_i - z_q)
             for (int l = 0; l < 5; l++) D.c[l] = sums[(size_t)c * BARY_OUT + q * 5 + l];
             const E5 S = bb::e5_add_base(bb::e5_mul(z[q], D), sums[(size_t)c * BARY_OUT + 10]);
-            (*ys)[(size_t)q * w + c] = bb::e5_mul(S, norm);
+            (*ys)[(size_t)q * w + c] = bb::e5_mul(S, c < w_first ? norm_a : norm_b);
         }
     }
 }
@@ -524,7 +536,7 @@ int32_t vg_fri_fold(vgpu_ctx* ctx, const uint32_t* cur, uint64_t ccs, uint64_t n
 // The words behind `ptrs` (null = reported by another rank of a split proof), summed over the ranks.
 int32_t vg_gather_words(vgpu_ctx* ctx, const std::vector<const uint32_t*>& ptrs, std::vector<uint32_t>* out) {
     size_t n = ptrs.size();
-    out->assign(n, 0);
+    out->resize(n);
     if (!n) return 0;
     const bool all = vg_sharded(ctx);
     const size_t G = all ? (size_t)ctx->comm_size : 1;
