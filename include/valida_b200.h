@@ -193,7 +193,10 @@ int32_t vgpu_comm_init_local(vgpu_ctx* const* ctxs, int32_t nranks);          /*
 int32_t vgpu_comm_set_sharding(vgpu_ctx* ctx, int32_t on);                    /* 0: behave as a lone GPU (independent replicas) */
 /* Collectives since the last reset: [0] barriers, [1] all-gathers, [2] peer-store exchanges (calls; bytes sent to peers). */
 void vgpu_comm_stats(vgpu_ctx* ctx, uint32_t calls[3], double bytes[3], int32_t reset);
-void vgpu_shard_range(uint64_t total, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* end);   /* the split used for columns */
+void vgpu_shard_range(uint64_t total, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* end);   /* contiguous balanced split (rows of a shard) */
+/* Which rank extends which columns in one commit of n tall matrices (heights[i] x widths[i]): contiguous ranges per rank, sized by
+ * water-filling over the whole commit (tallest first, a column of height h weighs h).  begin_out: n rows of nranks + 1 first-column indices. */
+void vgpu_split_column_plan(int32_t nranks, uint32_t n, const uint64_t* heights, const uint64_t* widths, uint32_t* begin_out);
 void vgpu_tree_share(uint64_t len, int32_t nranks, int32_t rank, uint64_t* begin, uint64_t* count, int32_t* split); /* ... for tree layers */
 
 /* ---- Machine::verify (machine/src/machine.rs:26-31; body derive/src/lib.rs:492-650) ------------------

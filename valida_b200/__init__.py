@@ -30,5 +30,6 @@ from .api import (  # noqa: F401
     comm_init_local,
     run_ranks,
     shard_range,
+    split_column_plan,
     tree_share,
 )

@@ -73,6 +73,7 @@ def _load():
         "vgpu_comm_stats": (None, [vp, u32p, C.POINTER(C.c_double), C.c_int32]),
         "vgpu_comm_set_sharding": (C.c_int32, [vp, C.c_int32]),
         "vgpu_shard_range": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
+        "vgpu_split_column_plan": (None, [C.c_int32, C.c_uint32, C.POINTER(u64), C.POINTER(u64), u32p]),
         "vgpu_tree_share": (None, [u64, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_int32)]),
         "vgpu_open": (C.c_int32, [vp, C.POINTER(vp), C.c_uint32, u32p, u32p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(u64)]),
         "vgpu_verify": (C.c_int32, [vp, C.c_char_p, u64, C.POINTER(_Matrix), C.c_int32, C.POINTER(C.c_int32)]),
@@ -468,6 +469,16 @@ def shard_range(total, world_size, rank):
     b, e = C.c_uint64(), C.c_uint64()
     lib().vgpu_shard_range(total, world_size, rank, C.byref(b), C.byref(e))
     return int(b.value), int(e.value)
+
+
+def split_column_plan(world_size, shapes):
+    """Column ownership of one split commit: shapes = [(height, width), ...] -> per matrix the list of world_size + 1 first-column indices."""
+    n = len(shapes)
+    hs = (C.c_uint64 * n)(*[int(h) for h, _ in shapes])
+    ws = (C.c_uint64 * n)(*[int(w) for _, w in shapes])
+    out = (C.c_uint32 * (n * (world_size + 1)))()
+    lib().vgpu_split_column_plan(world_size, n, hs, ws, out)
+    return [[int(out[i * (world_size + 1) + r]) for r in range(world_size + 1)] for i in range(n)]
 
 
 def tree_share(length, world_size, rank):

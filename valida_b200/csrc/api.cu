@@ -318,8 +318,7 @@ static uint32_t lde_shift_of(const uint32_t* coset_shifts_or_null, uint32_t i) {
 // weighs h) — so that a rank that had to take two of the ten columns of a 2^24-row matrix takes fewer columns of the others.
 // (An even split of every matrix on its own leaves the first ranks with up to 60 % more LDE work than the mean at 8 ranks.)
 struct ColPlan { uint32_t begin[17]; uint32_t widest; };
-static std::vector<ColPlan> plan_columns(const vgpu_ctx* ctx, const std::vector<std::pair<uint64_t, uint64_t>>& dims /* (height, width) of the tall matrices */) {
-    const int G = ctx->comm_size;
+static std::vector<ColPlan> plan_columns(const int G, const std::vector<std::pair<uint64_t, uint64_t>>& dims /* (height, width) of the tall matrices */) {
     std::vector<size_t> order(dims.size());
     for (size_t k = 0; k < dims.size(); k++) order[k] = k;
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dims[a].first > dims[b].first; });
@@ -344,11 +343,20 @@ static std::vector<ColPlan> plan_columns(const vgpu_ctx* ctx, const std::vector<
 extern "C++" size_t vg_commit_symm_need(const vgpu_ctx* ctx, const std::vector<std::pair<uint64_t, uint64_t>>& dims_all) {
     std::vector<std::pair<uint64_t, uint64_t>> dims;
     for (auto& d : dims_all) if (vg_split_rows(ctx, 2 * d.first)) dims.push_back(d);
-    const std::vector<ColPlan> plan = plan_columns(ctx, dims);
+    const std::vector<ColPlan> plan = plan_columns(ctx->comm_size, dims);
     size_t need = 0;
     for (size_t k = 0; k < dims.size(); k++)
         need += vg_symm_round((2 * dims[k].first / (uint64_t)ctx->comm_size) * dims[k].second * 4) + vg_symm_round(dims[k].first * plan[k].widest * 4);
     return need;
+}
+
+// The column plan of a commit as data (tests; a host program that wants to know which rank extends what): matrices i = 0..n-1 of
+// heights[i] x widths[i], all tall enough to be split; begin_out[i * (nranks + 1) + r] = first column of rank r, ... + nranks] = width.
+void vgpu_split_column_plan(int32_t nranks, uint32_t n, const uint64_t* heights, const uint64_t* widths, uint32_t* begin_out) {
+    std::vector<std::pair<uint64_t, uint64_t>> dims;
+    for (uint32_t i = 0; i < n; i++) dims.push_back({heights[i], widths[i]});
+    const std::vector<ColPlan> plan = plan_columns(nranks, dims);
+    for (uint32_t i = 0; i < n; i++) for (int r = 0; r <= nranks; r++) begin_out[(size_t)i * (nranks + 1) + r] = plan[i].begin[r];
 }
 
 // Split proof: the tall matrices of a commit.  (1) a matrix that arrives as row shards is handed to the ranks that extend
@@ -358,7 +366,7 @@ static int32_t extend_split(vgpu_ctx* ctx, vgpu_prover_data* pd, const vgpu_dmat
     const uint64_t G = (uint64_t)ctx->comm_size;
     std::vector<std::pair<uint64_t, uint64_t>> dims;
     for (size_t i : tall) dims.push_back({mats[i]->gh, mats[i]->gw});
-    const std::vector<ColPlan> plan = plan_columns(ctx, dims);
+    const std::vector<ColPlan> plan = plan_columns(ctx->comm_size, dims);
     size_t need = 0;
     for (size_t k = 0; k < tall.size(); k++) {
         const vgpu_dmat* m = mats[tall[k]];
