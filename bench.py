@@ -341,6 +341,13 @@ def main():
         # N > 1: ONE proof per step, split across the ranks (row shards after one peer-store exchange; include/valida_b200.h)
         ctx.comm_init_from_torch()
 
+        def watchdog():      # a rank that died leaves the others inside a collective: end the run instead of hanging the box
+            time.sleep(1500)
+            sys.stderr.write("bench.py: watchdog — the run did not finish within 1500 s\n")
+            os._exit(3)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+
     workload, log_rows = resolve_workload(args)
     t0 = time.perf_counter()
     traces, rows, what = build_traces(workload, log_rows)

@@ -315,7 +315,12 @@ extern "C" int32_t vgpu_verify(vgpu_ctx* ctx, const uint8_t* proof, uint64_t pro
     {   // preprocessed commitment, recomputed (derive/src/lib.rs:505-517)
         uint32_t digest[8];
         vgpu_prover_data* pd = nullptr;
-        VG_TRY(vgpu_commit_batches_host(ctx, prep, 2, repr, nullptr, digest, &pd));
+        // a verifier checks alone: no collective here even when the context is a rank of a split prover
+        const bool was_sharding = ctx->sharding;
+        ctx->sharding = false;
+        const int32_t rc = vgpu_commit_batches_host(ctx, prep, 2, repr, nullptr, digest, &pd);
+        ctx->sharding = was_sharding;
+        if (rc) return rc;
         vgpu_prover_data_free(pd);
         ch.observe_digest_canonical(digest);
     }
