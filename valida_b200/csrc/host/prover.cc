@@ -248,14 +248,22 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
 
     // ---- query phase: one gather for every word the proof needs (split proof: every rank reports the words it holds) ------
     HostPhase hq(ctx, "host+device: query phase (pointer list, gather, answers)");
-    std::vector<const uint32_t*> ptrs;
-    ptrs.reserve(1u << 18);
-    auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) ptrs.push_back(d ? d + k : nullptr); };
-    for (uint64_t index : indices) {
+    // every query asks for the same NUMBER of words (its index only selects which): the 40 pointer lists, and later the 40 answers,
+    // are filled by the host threads in parallel
+    size_t per_query = 0;
+    for (auto& L : S.layers) per_query += 5 + 8 * (L.tree.layer_ptr.size() - 1);
+    for (const OpenRound& rd : rounds) { for (auto* m : rd.pd->ldes) per_query += m->w; per_query += 8 * (size_t)log2u(rd.pd->max_height); }
+    const long nq = (long)indices.size();
+    std::vector<const uint32_t*> ptrs(per_query * (size_t)nq);
+#pragma omp parallel for schedule(static) num_threads(8)
+    for (long qi = 0; qi < nq; qi++) {
+        const uint64_t index = indices[qi];
+        const uint32_t** o = ptrs.data() + per_query * (size_t)qi;
+        auto push_digest = [&](const uint32_t* d) { for (int k = 0; k < 8; k++) *o++ = d ? d + k : nullptr; };
         for (size_t i = 0; i < S.layers.size(); i++) {
             const FriLayer& L = S.layers[i];
             uint64_t index_i = index >> i, sib = index_i ^ 1, pair = index_i >> 1;
-            for (int l = 0; l < 5; l++) ptrs.push_back(L.values.at(ctx, l, sib));
+            for (int l = 0; l < 5; l++) *o++ = L.values.at(ctx, l, sib);
             for (size_t lvl = 0; lvl + 1 < L.tree.layer_ptr.size(); lvl++) push_digest(L.tree.node(ctx, lvl, (pair >> lvl) ^ 1));
         }
         for (const OpenRound& rd : rounds) {
@@ -264,25 +272,29 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
             for (auto* m : rd.pd->ldes) {
                 const uint64_t row = bidx >> (lg - log2u(m->gh));
                 const bool mine = m->dist == VG_ROWS ? (row >= m->row0 && row < m->row0 + m->h) : (ctx->comm_rank == 0 || !vg_sharded(ctx));
-                for (uint64_t c = 0; c < m->w; c++) ptrs.push_back(mine ? m->d + c * m->col_stride + (row - m->row0) : nullptr);
+                for (uint64_t c = 0; c < m->w; c++) *o++ = mine ? m->d + c * m->col_stride + (row - m->row0) : nullptr;
             }
             for (int lvl = 0; lvl < lg; lvl++) push_digest(rd.pd->tree.node(ctx, lvl, (bidx >> lvl) ^ 1));
         }
     }
     std::vector<uint32_t> words;
     VG_TRY(vg_gather_words(ctx, ptrs, &words));
-    size_t pos = 0;
-    auto take_digest = [&]() { Digest d; for (int k = 0; k < 8; k++) d[k] = words[pos++]; return d; };
-    for (size_t qi = 0; qi < indices.size(); qi++) {
-        QueryProofH qp;
+    out->fri.query_proofs.assign((size_t)nq, QueryProofH());
+    out->query_openings.assign((size_t)nq, std::vector<BatchOpeningH>());
+#pragma omp parallel for schedule(static) num_threads(8)
+    for (long qi = 0; qi < nq; qi++) {
+        size_t pos = per_query * (size_t)qi;
+        auto take_digest = [&]() { Digest d; for (int k = 0; k < 8; k++) d[k] = words[pos++]; return d; };
+        QueryProofH& qp = out->fri.query_proofs[qi];
+        qp.steps.reserve(S.layers.size());
         for (size_t i = 0; i < S.layers.size(); i++) {
             CommitPhaseStepH st;
             for (int l = 0; l < 5; l++) st.sibling_value.c[l] = bb::from_monty(words[pos++]);
-            for (size_t lvl = 0; lvl + 1 < S.layers[i].tree.layer_ptr.size(); lvl++) st.opening_proof.push_back(take_digest());
+            const size_t depth = S.layers[i].tree.layer_ptr.size() - 1;
+            st.opening_proof.reserve(depth);
+            for (size_t lvl = 0; lvl < depth; lvl++) st.opening_proof.push_back(take_digest());
             qp.steps.push_back(std::move(st));
         }
-        out->fri.query_proofs.push_back(std::move(qp));
-        out->query_openings.emplace_back();
         for (const OpenRound& rd : rounds) {
             BatchOpeningH bo;
             int lg = log2u(rd.pd->max_height);
@@ -292,7 +304,7 @@ int32_t open_multi_batches(vgpu_ctx* ctx, const std::vector<OpenRound>& rounds, 
                 bo.opened_values.push_back(std::move(row));
             }
             for (int lvl = 0; lvl < lg; lvl++) bo.opening_proof.push_back(take_digest());
-            out->query_openings.back().push_back(std::move(bo));
+            out->query_openings[qi].push_back(std::move(bo));
         }
     }
     return 0;
@@ -335,26 +347,40 @@ struct Cbor {
 
 // TwoAdicFriPcsProof { fri_proof, query_openings } as serde/ciborium writes it
 void write_opening_proof(Cbor& w, const OpeningH& op) {
+    // the per-query parts (nine tenths of the bytes) are encoded by the host threads into their own buffers and appended in order
+    const long nq = (long)op.fri.query_proofs.size();
+    std::vector<Cbor> qa((size_t)nq), qb(op.query_openings.size());
+#pragma omp parallel for schedule(static) num_threads(8)
+    for (long i = 0; i < nq; i++) {
+        Cbor& c = qa[i];
+        c.b.resize(1u << 16);
+        const QueryProofH& q = op.fri.query_proofs[i];
+        c.map(1); c.key("commit_phase_openings"); c.arr(q.steps.size());
+        for (auto& s : q.steps) { c.map(2); c.key("sibling_value"); c.ext(s.sibling_value); c.key("opening_proof"); c.digests(s.opening_proof); }
+    }
+#pragma omp parallel for schedule(static) num_threads(8)
+    for (long i = 0; i < (long)op.query_openings.size(); i++) {
+        Cbor& c = qb[i];
+        c.b.resize(1u << 16);
+        const std::vector<BatchOpeningH>& q = op.query_openings[i];
+        c.arr(q.size());
+        for (auto& bo : q) {
+            c.map(2);
+            c.key("opened_values"); c.arr(bo.opened_values.size());
+            for (auto& row : bo.opened_values) { c.arr(row.size()); for (uint32_t x : row) c.felt(x); }
+            c.key("opening_proof"); c.digests(bo.opening_proof);
+        }
+    }
+    auto append = [&](const Cbor& c) { std::memcpy(w.room(c.n), c.b.data(), c.n); w.n += c.n; };
     w.map(2);
     w.key("fri_proof"); w.map(4);
     w.key("commit_phase_commits"); w.digests(op.fri.commit_phase_commits);
     w.key("query_proofs"); w.arr(op.fri.query_proofs.size());
-    for (auto& q : op.fri.query_proofs) {
-        w.map(1); w.key("commit_phase_openings"); w.arr(q.steps.size());
-        for (auto& s : q.steps) { w.map(2); w.key("sibling_value"); w.ext(s.sibling_value); w.key("opening_proof"); w.digests(s.opening_proof); }
-    }
+    for (auto& c : qa) append(c);
     w.key("final_poly"); w.ext(op.fri.final_poly);
     w.key("pow_witness"); w.felt(op.fri.pow_witness);
     w.key("query_openings"); w.arr(op.query_openings.size());
-    for (auto& q : op.query_openings) {
-        w.arr(q.size());
-        for (auto& bo : q) {
-            w.map(2);
-            w.key("opened_values"); w.arr(bo.opened_values.size());
-            for (auto& row : bo.opened_values) { w.arr(row.size()); for (uint32_t x : row) w.felt(x); }
-            w.key("opening_proof"); w.digests(bo.opening_proof);
-        }
-    }
+    for (auto& c : qb) append(c);
 }
 
 vgh::Poseidon16* poseidon_of(vgpu_ctx* ctx) {
