@@ -347,40 +347,27 @@ struct Cbor {
 
 // TwoAdicFriPcsProof { fri_proof, query_openings } as serde/ciborium writes it
 void write_opening_proof(Cbor& w, const OpeningH& op) {
-    // the per-query parts (nine tenths of the bytes) are encoded by the host threads into their own buffers and appended in order
-    const long nq = (long)op.fri.query_proofs.size();
-    std::vector<Cbor> qa((size_t)nq), qb(op.query_openings.size());
-#pragma omp parallel for schedule(static) num_threads(8)
-    for (long i = 0; i < nq; i++) {
-        Cbor& c = qa[i];
-        c.b.resize(1u << 16);
-        const QueryProofH& q = op.fri.query_proofs[i];
-        c.map(1); c.key("commit_phase_openings"); c.arr(q.steps.size());
-        for (auto& s : q.steps) { c.map(2); c.key("sibling_value"); c.ext(s.sibling_value); c.key("opening_proof"); c.digests(s.opening_proof); }
-    }
-#pragma omp parallel for schedule(static) num_threads(8)
-    for (long i = 0; i < (long)op.query_openings.size(); i++) {
-        Cbor& c = qb[i];
-        c.b.resize(1u << 16);
-        const std::vector<BatchOpeningH>& q = op.query_openings[i];
-        c.arr(q.size());
-        for (auto& bo : q) {
-            c.map(2);
-            c.key("opened_values"); c.arr(bo.opened_values.size());
-            for (auto& row : bo.opened_values) { c.arr(row.size()); for (uint32_t x : row) c.felt(x); }
-            c.key("opening_proof"); c.digests(bo.opening_proof);
-        }
-    }
-    auto append = [&](const Cbor& c) { std::memcpy(w.room(c.n), c.b.data(), c.n); w.n += c.n; };
+    // (encoding the per-query parts on several host threads into buffers of their own was measured: 0.88 ms against 0.64 ms serial)
     w.map(2);
     w.key("fri_proof"); w.map(4);
     w.key("commit_phase_commits"); w.digests(op.fri.commit_phase_commits);
     w.key("query_proofs"); w.arr(op.fri.query_proofs.size());
-    for (auto& c : qa) append(c);
+    for (auto& q : op.fri.query_proofs) {
+        w.map(1); w.key("commit_phase_openings"); w.arr(q.steps.size());
+        for (auto& s : q.steps) { w.map(2); w.key("sibling_value"); w.ext(s.sibling_value); w.key("opening_proof"); w.digests(s.opening_proof); }
+    }
     w.key("final_poly"); w.ext(op.fri.final_poly);
     w.key("pow_witness"); w.felt(op.fri.pow_witness);
     w.key("query_openings"); w.arr(op.query_openings.size());
-    for (auto& c : qb) append(c);
+    for (auto& q : op.query_openings) {
+        w.arr(q.size());
+        for (auto& bo : q) {
+            w.map(2);
+            w.key("opened_values"); w.arr(bo.opened_values.size());
+            for (auto& row : bo.opened_values) { w.arr(row.size()); for (uint32_t x : row) w.felt(x); }
+            w.key("opening_proof"); w.digests(bo.opening_proof);
+        }
+    }
 }
 
 vgh::Poseidon16* poseidon_of(vgpu_ctx* ctx) {
