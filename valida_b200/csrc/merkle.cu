@@ -107,11 +107,58 @@ __global__ void __launch_bounds__(128) compress_layer_kernel(const uint32_t* __r
     w[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// ---- Keccak-f[1600] spread over the lanes of a warp ------------------------------------------------------------------------------
+// For the last few layers of a tree there is nothing to run in parallel: a layer of n <= 32 nodes is n chains of 24 dependent rounds,
+// and a lone thread needs ~5.5 us for one (4166 instructions, one warp per scheduler).  Here lane t = x + 5y of a warp holds lane
+// A[x, y] of ONE state: a round is 18 shuffles and ~25 ALU instructions per lane (theta: column parity by four shuffles, D by two;
+// rho: a per-lane rotation amount; pi: one shuffle; chi: two), ~140 cycles of latency — about a third of the lone thread's chain.
+__constant__ uint8_t WK_ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};   // r[x + 5y]
+struct WarpKeccak {
+    uint32_t rot, col[4], dm, dp, pi, c1, c2, lane;
+    __device__ __forceinline__ void init(uint32_t lane_) {
+        lane = lane_;
+        const uint32_t t = lane < 25 ? lane : 0, x = t % 5, y = t / 5;
+        rot = WK_ROT[t];
+#pragma unroll
+        for (int k = 0; k < 4; k++) col[k] = (t + 5 * (k + 1)) % 25;
+        dm = (x + 4) % 5 + 5 * y; dp = (x + 1) % 5 + 5 * y;
+        pi = (x + 3 * y) % 5 + 5 * x;                 // B[x, y] comes from A[(x + 3y) mod 5, x]
+        c1 = (x + 1) % 5 + 5 * y; c2 = (x + 2) % 5 + 5 * y;
+    }
+    static __device__ __forceinline__ uint2 sh(uint2 v, uint32_t src) { return make_uint2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+    __device__ __forceinline__ void permute(uint2& a) const {
+#pragma unroll 1
+        for (int round = 0; round < 24; round++) {
+            uint2 p = a;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint2 o = sh(a, col[k]); p.x ^= o.x; p.y ^= o.y; }
+            const uint2 pm = sh(p, dm), pp = sh(p, dp);
+            a.x ^= pm.x ^ __funnelshift_l(pp.y, pp.x, 1); a.y ^= pm.y ^ __funnelshift_l(pp.x, pp.y, 1);
+            uint32_t lo = a.x, hi = a.y;
+            if (rot & 32) { const uint32_t tmp = lo; lo = hi; hi = tmp; }
+            uint2 b = make_uint2(__funnelshift_l(hi, lo, rot & 31), __funnelshift_l(lo, hi, rot & 31));
+            b = sh(b, pi);
+            const uint2 b1 = sh(b, c1), b2 = sh(b, c2);
+            a.x = b.x ^ (~b1.x & b2.x); a.y = b.y ^ (~b1.y & b2.y);
+            if (lane == 0) { const uint2 rc = kk::RC[round]; a.x ^= rc.x; a.y ^= rc.y; }
+            if (lane >= 25) a = make_uint2(0, 0);
+        }
+    }
+    // 64-byte compression: lanes 0..7 hold the sixteen input words (2 each); on return lanes 0..3 hold the digest words, reduced mod p
+    __device__ __forceinline__ uint2 compress(uint2 words) const {
+        uint2 a = lane < 8 ? words : lane == 8 ? make_uint2(1u, 0u) : lane == 16 ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
+        permute(a);
+        return make_uint2(wrap_mod_p(a.x), wrap_mod_p(a.y));
+    }
+};
+
 // The short layers of a tree in ONE launch: a CTA owns `sub` consecutive nodes of the first fused layer and reduces that sub-tree
 // level by level in shared memory (each level is written to its place in global memory as well), so the 10 - 16 launches of a tree's
-// tail — each a handful of warps waiting on a single Keccak-f — become one or two.  Bases are virtual (+ global node index), as in
-// compress_layer_kernel; inj_v[k] = digests of the rows a shorter matrix group contributes at fused level k, or null.
-constexpr int TAIL_SUB = 256, TAIL_THREADS = 256, TAIL_MAX_LEVELS = 9;      // one node per thread at the first fused level
+// tail — each a handful of warps waiting on a single Keccak-f — become one or two.  Levels of more than 32 nodes take a thread per
+// node; the narrower ones a WARP per node (WarpKeccak), which shortens the dependent chain that is all that is left there.
+// Bases are virtual (+ global node index), as in compress_layer_kernel; inj_v[k] = digests of the rows a shorter matrix group
+// contributes at fused level k, or null.
+constexpr int TAIL_SUB = 256, TAIL_THREADS = 512, TAIL_MAX_LEVELS = 9, TAIL_WARP_NODES = 32;
 struct TailParams {
     const uint32_t* prev_v;
     uint32_t* next_v[TAIL_MAX_LEVELS];
@@ -129,26 +176,45 @@ __global__ void __launch_bounds__(TAIL_THREADS) tree_tail_kernel(const __grid_co
         for (uint32_t i = threadIdx.x; i < 4 * p.sub; i += TAIL_THREADS) buf_a[i] = __ldg(src + i);
     }
     __syncthreads();
+    WarpKeccak wk;
+    wk.init(threadIdx.x & 31);
     uint4* cur = buf_a; uint4* nxt = buf_b;
     for (uint32_t k = 0; k < p.levels; k++) {
         const uint32_t n = p.sub >> k;
         const uint64_t base = node0 >> k;
-        for (uint32_t t = threadIdx.x; t < n; t += TAIL_THREADS) {
-            const uint4 a = cur[4 * t], b = cur[4 * t + 1], c = cur[4 * t + 2], d = cur[4 * t + 3];
-            uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, r[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w}, o[8];
-            compress_pair(l, r, o);
-            if (p.inj_v[k]) {
-                const uint4* q = reinterpret_cast<const uint4*>(p.inj_v[k] + (base + t) * 8);
-                const uint4 e = __ldg(q), f = __ldg(q + 1);
-                uint32_t tt[8] = {e.x, e.y, e.z, e.w, f.x, f.y, f.z, f.w}, o2[8];
-                compress_pair(o, tt, o2);
+        if (n > TAIL_WARP_NODES) {
+            for (uint32_t t = threadIdx.x; t < n; t += TAIL_THREADS) {
+                const uint4 a = cur[4 * t], b = cur[4 * t + 1], c = cur[4 * t + 2], d = cur[4 * t + 3];
+                uint32_t l[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, r[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w}, o[8];
+                compress_pair(l, r, o);
+                if (p.inj_v[k]) {
+                    const uint4* q = reinterpret_cast<const uint4*>(p.inj_v[k] + (base + t) * 8);
+                    const uint4 e = __ldg(q), f = __ldg(q + 1);
+                    uint32_t tt[8] = {e.x, e.y, e.z, e.w, f.x, f.y, f.z, f.w}, o2[8];
+                    compress_pair(o, tt, o2);
 #pragma unroll
-                for (int i = 0; i < 8; i++) o[i] = o2[i];
+                    for (int i = 0; i < 8; i++) o[i] = o2[i];
+                }
+                const uint4 w0 = make_uint4(o[0], o[1], o[2], o[3]), w1 = make_uint4(o[4], o[5], o[6], o[7]);
+                nxt[2 * t] = w0; nxt[2 * t + 1] = w1;
+                uint4* g = reinterpret_cast<uint4*>(p.next_v[k] + (base + t) * 8);
+                g[0] = w0; g[1] = w1;
             }
-            const uint4 w0 = make_uint4(o[0], o[1], o[2], o[3]), w1 = make_uint4(o[4], o[5], o[6], o[7]);
-            nxt[2 * t] = w0; nxt[2 * t + 1] = w1;
-            uint4* g = reinterpret_cast<uint4*>(p.next_v[k] + (base + t) * 8);
-            g[0] = w0; g[1] = w1;
+        } else {
+            const uint32_t lane = threadIdx.x & 31;
+            for (uint32_t t = threadIdx.x >> 5; t < n; t += TAIL_THREADS / 32) {      // a warp per node
+                const uint2* in = reinterpret_cast<const uint2*>(cur + 4 * t);         // 16 words = 8 uint2
+                uint2 dg = wk.compress(lane < 8 ? in[lane] : make_uint2(0, 0));        // lanes 0..3: the digest
+                if (p.inj_v[k]) {
+                    const uint2* q = reinterpret_cast<const uint2*>(p.inj_v[k] + (base + t) * 8);
+                    const uint2 w = lane < 4 ? dg : (lane < 8 ? __ldg(q + (lane - 4)) : make_uint2(0, 0));
+                    dg = wk.compress(w);
+                }
+                if (lane < 4) {
+                    reinterpret_cast<uint2*>(nxt + 2 * t)[lane] = dg;
+                    reinterpret_cast<uint2*>(p.next_v[k] + (base + t) * 8)[lane] = dg;
+                }
+            }
         }
         __syncthreads();
         uint4* tmp = cur; cur = nxt; nxt = tmp;
