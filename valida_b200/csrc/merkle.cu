@@ -7,7 +7,10 @@
 //    little-endian into a register-resident 1600-bit state; digest words are reduced mod p;
 //  * node kernel: one thread per parent, 64-byte compression (one permutation), with the
 //    "inject shorter matrices" rule: node = compress(compress(l, r), hash(rows at that height)).
-// Digests are stored canonical, 8 words (32 B) per node, all layers kept for the opening phase.
+//  * short layers (<= 2^15 nodes): tree_tail_kernel reduces a sub-tree per CTA in shared memory, a thread per node while a level is
+//    wide, a warp per node (the Keccak state spread over 25 lanes) on the last levels, where only the dependent chain is left.
+// Digests are stored canonical, 8 words (32 B) per node, all layers kept for the opening phase.  Split proof (merkle.h): a rank
+// computes and keeps its run of every layer — the sub-tree over its rows — and only the layer of comm_size sub-roots is all-gathered.
 #include "ctx.h"
 #include "keccak.cuh"
 #include "merkle.h"
@@ -293,7 +296,7 @@ static int32_t hash_rows(vgpu_ctx* ctx, const std::vector<const vgpu_dmat*>& mat
 
 // layers 1.. of a planned tree whose leaf layer is already hashed; inject(lvl, plan, inj_v, &have) fills the digests of the rows a
 // shorter matrix group contributes at layer lvl.  Long layers take one launch each; from the first layer of at most TAIL_FUSE nodes
-// (computed here) on, runs of up to 10 layers go into ONE launch of tree_tail_kernel; a run ends at the sub-root layer of a split tree
+// (computed here) on, runs of up to 9 layers go into ONE launch of tree_tail_kernel; a run ends at the sub-root layer of a split tree
 // (its all-gather comes next) and at the root.
 constexpr uint64_t TAIL_FUSE = 1u << 15;
 template <class Inject>
