@@ -7,6 +7,9 @@
 // coset_shift, log_blowup, open_multi_batches, verify_multi_batches; plus p3-fri's prover/verifier
 // and fold_even_odd.   [P3-UNVERIFIED; SURVEY App. A items 5, 9, 14, 15, 17]
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "field.h"
 #include "ntt.h"
 #include "merkle.h"
@@ -123,6 +126,8 @@ struct Pcs {
 
     std::pair<OpenedValues, PcsProof> open_multi_batches(const std::vector<Round>& rounds, Challenger& ch) const {
         Ext5 alpha = ch.sample_ext();
+        double T_eval = 0, T_inv = 0, T_red = 0, T_xs = 0; auto NOW = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double T_start = NOW();
         OpenedValues all;
         std::vector<std::vector<Ext5>> ro(32);
         size_t num_reduced[32] = {0};
@@ -136,14 +141,18 @@ struct Pcs {
                 if (ro[lh].empty()) ro[lh].assign(H, Ext5::zero());
                 all.back().emplace_back();
                 // x for storage row i: g * omega^{bitrev(i)}
+                double tq0 = NOW();
                 std::vector<uint32_t> xs(H);
                 { std::vector<uint32_t> nat = geometric(GEN, two_adic_generator(lh), H);
 #pragma omp parallel for schedule(static) if (H > 8192)
                   for (long i = 0; i < (long)H; i++) xs[i] = nat[reverse_bits_len((uint32_t)i, lh)]; }
                 std::vector<Ext5> apow(w);
                 { Ext5 a = Ext5::one(); for (size_t c = 0; c < w; c++) { apow[c] = a; a = a * alpha; } }
+                T_xs += NOW() - tq0;
                 for (const Ext5& z : rd.points[mi]) {
+                    double t0 = NOW();
                     std::vector<Ext5> ys = eval_at(mat, z);
+                    double t1 = NOW(); T_eval += t1 - t0;
                     Ext5 alpha_pow_offset = ext_pow(alpha, num_reduced[lh]);
                     Ext5 sum_y = Ext5::zero();
                     for (size_t c = 0; c < w; c++) sum_y += apow[c] * ys[c];
@@ -151,6 +160,7 @@ struct Pcs {
 #pragma omp parallel for schedule(static) if (H > 4096)
                     for (long i = 0; i < (long)H; i++) den[i] = -z + xs[i];
                     std::vector<Ext5> dinv = batch_inverse(den);
+                    double t2 = NOW(); T_inv += t2 - t1;
                     std::vector<Ext5>& r = ro[lh];
 #pragma omp parallel for schedule(static) if (H * w > (1u << 14))
                     for (long i = 0; i < (long)H; i++) {
@@ -159,11 +169,13 @@ struct Pcs {
                         for (size_t c = 0; c < w; c++) red += apow[c] * row[c];
                         r[i] += alpha_pow_offset * (red - sum_y) * dinv[i];
                     }
+                    T_red += NOW() - t2;
                     num_reduced[lh] += w;
                     all.back().back().push_back(std::move(ys));
                 }
             }
         }
+        if (getenv("ORACLE_TIMING")) fprintf(stderr, "  open: xs %.3f eval %.3f inv %.3f reduce %.3f (total so far %.3f)\n", T_xs, T_eval, T_inv, T_red, NOW() - T_start);
         // ---- p3-fri prove ----
         int log_max_height = 31;
         while (log_max_height >= 0 && ro[log_max_height].empty()) log_max_height--;
@@ -188,6 +200,7 @@ struct Pcs {
         assert(current.size() == (1u << fri.log_blowup));
         for (auto& x : current) { assert(x == current[0]); (void)x; }
         proof.fri.final_poly = current[0];
+        if (getenv("ORACLE_TIMING")) fprintf(stderr, "  open: fri commit phase done at %.3f\n", NOW() - T_start);
         proof.fri.pow_witness = ch.grind(fri.pow_bits);
         std::vector<size_t> query_indices;
         for (int q = 0; q < fri.num_queries; q++) query_indices.push_back(ch.sample_bits(log_max_height));
