@@ -170,6 +170,7 @@ def run_reference(args, rank):
 
     vbuild.build_oracle()
     orc = oracle_binding.Oracle()
+    orc.tune_allocator()                             # freed vectors stay in the heap: no page faults on every re-allocation
     workload, full_log_rows = resolve_workload(args)
     log_rows = min(args.ref_log_rows, full_log_rows)
     main, prep = _load_trace_files(workload, log_rows)

@@ -10,10 +10,19 @@
 using namespace orc;
 
 #include <omp.h>
+#include <malloc.h>
 
 extern "C" {
 
 void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+// For the process that TIMES the oracle as the CPU baseline (bench.py --impl reference): keep freed blocks in the heap instead
+// of returning every multi-megabyte vector to the kernel and faulting its pages in again on the next allocation (what a
+// Rust prover gets from its allocator); process-wide, so the test suite does not call it.  Returns 1 when all three took.
+int orc_tune_allocator() {
+    int ok = mallopt(M_MMAP_MAX, 0);
+    ok &= mallopt(M_TRIM_THRESHOLD, 1 << 30) & mallopt(M_TOP_PAD, 256 << 20);
+    return ok;
+}
 int orc_max_threads() { return omp_get_max_threads(); }
 
 void orc_keccak256(const uint8_t* in, uint64_t len, uint8_t* out, uint32_t pad) { keccak256_pad(in, len, out, (uint8_t)pad); }

@@ -39,6 +39,10 @@ class Oracle:
     def max_threads(self):
         return int(self.L.orc_max_threads())
 
+    def tune_allocator(self):
+        """Process-wide malloc settings for a process that only times the oracle (bench.py --impl reference)."""
+        return int(self.L.orc_tune_allocator())
+
     # ---- primitives ----
     def keccak256(self, data, pad=0x01):
         out = (C.c_uint8 * 32)()
