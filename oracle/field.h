@@ -109,6 +109,15 @@ static inline Ext5& operator*=(Ext5& a, const Ext5& b) { a = a * b; return a; }
 static inline Ext5 operator+(const Ext5& a, uint32_t b) { Ext5 r = a; r.c[0] = add(r.c[0], b); return r; }
 static inline Ext5 operator-(const Ext5& a, uint32_t b) { Ext5 r = a; r.c[0] = sub(r.c[0], b); return r; }
 
+// Sum of ext5 x base products with the reductions postponed: four raw products (each < p^2 < 2^61.9) plus a canonical
+// remainder fit in a u64, so fold() is due after every fourth mad().  Same values as the reduced sum (reduction is exact).
+struct Lazy5 {
+    uint64_t s[5] = {0, 0, 0, 0, 0};
+    void mad(const Ext5& a, uint32_t b) { for (int i = 0; i < 5; i++) s[i] += (uint64_t)a.c[i] * b; }
+    void fold() { for (int i = 0; i < 5; i++) s[i] %= P; }
+    Ext5 value() const { Ext5 r; for (int i = 0; i < 5; i++) r.c[i] = (uint32_t)(s[i] % P); return r; }
+};
+
 static inline Ext5 ext_pow(Ext5 a, uint64_t e) {
     Ext5 r = Ext5::one();
     while (e) { if (e & 1) r = r * a; a = a * a; e >>= 1; }

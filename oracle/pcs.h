@@ -106,15 +106,17 @@ struct Pcs {
         std::vector<Ext5> acc(w, Ext5::zero());
 #pragma omp parallel if (h > 4096)
         {
-            std::vector<Ext5> loc(w, Ext5::zero());
+            std::vector<Lazy5> loc(w);
+            int pending = 0;
 #pragma omp for schedule(static) nowait
             for (long i = 0; i < (long)h; i++) {
                 Ext5 wgt = dinv[i] * xs[i];
                 const uint32_t* row = lde.row(reverse_bits_len((uint32_t)i, lg));
-                for (size_t c = 0; c < w; c++) loc[c] += wgt * row[c];
+                for (size_t c = 0; c < w; c++) loc[c].mad(wgt, row[c]);
+                if (++pending == 4) { for (size_t c = 0; c < w; c++) loc[c].fold(); pending = 0; }
             }
 #pragma omp critical
-            for (size_t c = 0; c < w; c++) acc[c] += loc[c];
+            for (size_t c = 0; c < w; c++) acc[c] += loc[c].value();
         }
         uint32_t sn = exp_pow2(s, lg);
         Ext5 scale = (ext_exp_pow2(z, lg) - sn) * inv(mul((uint32_t)(h % P), sn));
@@ -165,8 +167,9 @@ struct Pcs {
 #pragma omp parallel for schedule(static) if (H * w > (1u << 14))
                     for (long i = 0; i < (long)H; i++) {
                         const uint32_t* row = mat.row(i);
-                        Ext5 red = Ext5::zero();
-                        for (size_t c = 0; c < w; c++) red += apow[c] * row[c];
+                        Lazy5 lz;
+                        for (size_t c = 0; c < w; c++) { lz.mad(apow[c], row[c]); if ((c & 3) == 3) lz.fold(); }
+                        Ext5 red = lz.value();
                         r[i] += alpha_pow_offset * (red - sum_y) * dinv[i];
                     }
                     T_red += NOW() - t2;
