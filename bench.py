@@ -30,6 +30,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
 
+# CPU arm: keep the oracle's threads on neighbouring cores of one socket (measured on the 2 x 32-core host: 1.65 -> 1.53 s per 2^18-row proof).
+if "reference" in sys.argv:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
 FIB_N = {22: 599183, 20: 149794, 18: 37447, 17: 9360 * 2, 16: 9360, 15: 2339, 12: 582, 8: 25}   # log2(CPU rows) -> n (cycles = 17 + 7n)
 
 
