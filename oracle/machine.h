@@ -10,6 +10,7 @@
 // Inputs are the 14 main traces (row-major, canonical u32) and the two preprocessed traces
 // (program: 7 columns, range: 1 column) — trace generation is outside this file.
 #pragma once
+#include <ctime>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -234,8 +235,11 @@ static inline MachineProof machine_prove(const MachineInput& in, const Poseidon1
     Pcs pcs;
     Challenger ch(&perm16);
     // ORACLE_TIMING=1: wall time of each phase on stderr (where the CPU baseline spends its time)
+    // (with OMP_WAIT_POLICY=passive the process CPU time beside it shows how much of a phase ran on one thread only)
     auto T0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) { if (getenv("ORACLE_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "oracle %-18s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
+    auto cpu_now = [] { timespec ts; clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    double C0 = cpu_now();
+    auto lap = [&](const char* what) { if (getenv("ORACLE_TIMING")) { auto t = std::chrono::steady_clock::now(); double c = cpu_now(); fprintf(stderr, "oracle %-18s %.3f s (cpu %.3f s)\n", what, std::chrono::duration<double>(t - T0).count(), c - C0); T0 = t; C0 = c; } };
     // preprocessed commit (derive:299-311)
     PcsData prep_data = pcs.commit_batches({in.program_prep, in.range_prep});
     Digest prep_commit = prep_data.tree.root();
