@@ -139,6 +139,53 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
 
 
+_HOST = None
+
+
+def host_cpus():
+    """What the host really grants this process: logical CPUs, the scheduler affinity mask, and the container's CPU quota (cgroup
+    v2 cpu.max / v1 cfs_quota) — os.cpu_count() alone over-reports inside a limited container, and OpenMP threads beyond the
+    quota only get throttled."""
+    global _HOST
+    if _HOST is not None:
+        return _HOST
+    info = {"logical": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["logical"]
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    info["cgroup_quota_cpus"] = quota
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    usable = min(info["logical"], info["affinity"])
+    if quota:
+        usable = max(1, min(usable, int(quota + 0.5)))
+    info["usable"] = usable
+    _HOST = info
+    return info
+
+
+def thread_candidates(usable):
+    """Thread counts the CPU arm tries on the sample itself: beyond 64 the oracle's short parallel regions oversubscribe
+    (measured on the 128-CPU box: 3.4 s at 16 / 32, 4.8 s at 64, 51 s at 128 threads for the same 2^18-row proof)."""
+    return sorted({max(1, min(usable, c)) for c in (16, 32, 64)})
+
+
 def _tracegen_to_files(workload, log_rows, out_prefix):
     """Child-process entry (python bench.py --tracegen ...): the witness generator lives in the product library, the
     reference arm must not load it — so the traces reach the reference process as .npy files."""
@@ -180,10 +227,9 @@ def run_reference(args, rank):
     log_rows = min(args.ref_log_rows, full_log_rows)
     main, prep = _load_trace_files(workload, log_rows)
     rows = main[0].shape[0]
-    cores = os.cpu_count() or 1
-    # the oracle's many short parallel regions oversubscribe badly beyond 64 threads (measured on the 128-core box: 3.4 s at 16 / 32, 4.8 s
-    # at 64, 51 s at 128 threads for the same 2^18-row proof), so the sweep stops there
-    cand = sorted({min(cores, c) for c in (16, 32, 64)})
+    host = host_cpus()
+    cores = host["logical"]
+    cand = thread_candidates(host["usable"])
     sweep, times = {}, []
     threads = cand[-1]
     for i in range(args.warmup + args.steps):
@@ -222,7 +268,7 @@ def run_reference(args, rank):
         "config": {"workload": workload_name(workload, full_log_rows), "sample": sample, "same_config": log_rows == full_log_rows},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()},
+        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()}, "host": host,
         "note": "the real reference (Rust + un-vendored Plonky3) cannot be built here; this is oracle/, the C++ restatement, OpenMP; rows/s at the measured sizes are in `sizes`",
     }
     emit(line)
@@ -293,6 +339,7 @@ def main():
         _tracegen_to_files(w, lr, args.tracegen)
         return
 
+    host_cpus()      # read the affinity mask before an OpenMP runtime loads: with OMP_PROC_BIND set libgomp pins the initial thread to one place
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -645,9 +692,10 @@ def main():
             orc = oracle_binding.Oracle()
             cbl = min(args.cpu_baseline_log_rows, log_rows)
             tb, _, _ = build_traces(workload, cbl)
-            cores = os.cpu_count() or 1
+            host = host_cpus()
+            cores = host["logical"]
             best = None
-            for th in sorted({min(cores, c) for c in (16, 32, 64)}):     # thread sweep on the sample itself (beyond 64 the oracle oversubscribes)
+            for th in thread_candidates(host["usable"]):     # thread sweep on the sample itself (beyond 64 the oracle oversubscribes)
                 orc.set_threads(th)
                 t0 = time.perf_counter()
                 ref = orc.prove(tb.main, tb.preprocessed, debug_checks=False)
@@ -657,7 +705,7 @@ def main():
                     best = (dt, th)
             cpu_baseline = {"value": tb.main[0].shape[0] / best[0], "unit": "rows/s", "cores": best[1], "kind": "port",
                             "sample": "%s at 2^%d CPU rows, one full oracle prove, %.1f s, %d OpenMP threads (fastest of a sweep on this size) on %d host cores"
-                                      % (workload, cbl, best[0], best[1], cores)}
+                                      % (workload, cbl, best[0], best[1], cores), "host": host}
 
         G = world
         line = {
