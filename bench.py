@@ -198,15 +198,25 @@ def _tracegen_to_files(workload, log_rows, out_prefix):
 
 def _load_trace_files(workload, log_rows):
     import numpy as np
+    import shutil
     import tempfile
 
-    d = tempfile.mkdtemp(prefix="vgpu_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    prefix = os.path.join(d, "t")
-    subprocess.run([sys.executable, os.path.abspath(__file__), "--tracegen", prefix, "--workload", workload, "--log-rows", str(log_rows)], check=True)
-    mats = [np.load("%s.%d.npy" % (prefix, i)) for i in range(16)]
-    for i in range(16):
-        os.remove("%s.%d.npy" % (prefix, i))
-    os.rmdir(d)
+    # ~2.1 GB of traces at 2^22 CPU rows (Fibonacci); /dev/shm when it has the room (a container's default is 64 MB), else the temp dir
+    need = int(2.6e9 * (1 << log_rows) / (1 << 22)) + (64 << 20)
+    base = None
+    try:
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize > need:
+            base = "/dev/shm"
+    except OSError:
+        pass
+    d = tempfile.mkdtemp(prefix="vgpu_ref_", dir=base)
+    try:
+        prefix = os.path.join(d, "t")
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--tracegen", prefix, "--workload", workload, "--log-rows", str(log_rows)], check=True)
+        mats = [np.load("%s.%d.npy" % (prefix, i)) for i in range(16)]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
     return mats[:14], mats[14:]
 
 
@@ -250,22 +260,34 @@ def run_reference(args, rank):
             times.append(dt)
     total = sum(times)
     value = rows * len(times) / total
-    sizes = {"2^%d" % log_rows: {"rows_per_s": value, "s_per_proof": total / len(times), "threads": threads}}
-    if args.ref_extra_log_rows and args.ref_extra_log_rows <= full_log_rows and args.ref_extra_log_rows != log_rows:
-        m2, p2 = _load_trace_files(workload, args.ref_extra_log_rows)
-        orc.set_threads(threads)
-        t0 = time.perf_counter()
-        pr = orc.prove(m2, p2, debug_checks=False)
-        dt = time.perf_counter() - t0
-        del pr
-        sizes["2^%d" % args.ref_extra_log_rows] = {"rows_per_s": m2[0].shape[0] / dt, "s_per_proof": dt, "threads": threads, "proofs": 1}
+    sizes = {"2^%d" % log_rows: {"rows_per_s": value, "s_per_proof": total / len(times), "threads": threads, "proofs": len(times)}}
+    del main, prep
+    # one proof at each further size (by default 2^18 and the arm's full workload, 2^22): how the per-row cost moves with the size is then
+    # measured, not extrapolated; a size that fails (memory, temp space) is recorded and changes nothing above
+    for extra in [int(x) for x in str(args.ref_extra_log_rows).split(",") if x.strip() and int(x) > 0]:
+        if extra > full_log_rows or extra == log_rows:
+            continue
+        try:
+            m2, p2 = _load_trace_files(workload, extra)
+            orc.set_threads(threads)
+            t0 = time.perf_counter()
+            pr = orc.prove(m2, p2, debug_checks=False)
+            dt = time.perf_counter() - t0
+            del pr
+            sizes["2^%d" % extra] = {"rows_per_s": m2[0].shape[0] / dt, "s_per_proof": dt, "threads": threads, "proofs": 1}
+            del m2, p2
+        except Exception as exc:   # noqa: BLE001
+            sizes["2^%d" % extra] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    full_key = "2^%d" % full_log_rows
+    full_measured = full_key in sizes and "rows_per_s" in sizes[full_key]
     sample = "%s at 2^%d CPU rows (one full prove per step; the arm's workload is 2^%d rows); %d OpenMP threads (fastest of %s in the warm-up steps, on this size) of %d host cores" % (
         workload, log_rows, full_log_rows, threads, cand, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-        "config": {"workload": workload_name(workload, full_log_rows), "sample": sample, "same_config": log_rows == full_log_rows},
+        "config": {"workload": workload_name(workload, full_log_rows), "sample": sample, "same_config": log_rows == full_log_rows,
+                   "full_workload_measured_once": full_measured, "full_workload_rows_per_s": sizes[full_key]["rows_per_s"] if full_measured else None},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()}, "host": host,
@@ -327,8 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fib22", help="fib22 (BASELINE config 3, default) | fib24 (config 4) | config5 | fib / config5 with --log-rows")
     ap.add_argument("--log-rows", type=int, default=22, help="log2 of the CPU-chip trace height for --workload fib / config5")
-    ap.add_argument("--ref-log-rows", type=int, default=18, help="bounded sample size of the CPU reference arm (one proof per step)")
-    ap.add_argument("--ref-extra-log-rows", type=int, default=20, help="reference arm: one extra proof at this size (0 = none)")
+    ap.add_argument("--ref-log-rows", type=int, default=20, help="bounded sample size of the CPU reference arm (one proof per step)")
+    ap.add_argument("--ref-extra-log-rows", default="18,22", help="reference arm: one extra proof at each of these sizes (comma separated; 0 = none)")
     ap.add_argument("--cpu-baseline-log-rows", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the independent-proofs-per-GPU figure")
