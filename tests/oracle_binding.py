@@ -43,6 +43,11 @@ class Oracle:
         """Process-wide malloc settings for a process that only times the oracle (bench.py --impl reference)."""
         return int(self.L.orc_tune_allocator())
 
+    def prefault_heap(self, nbytes):
+        """Maps and touches `nbytes` of heap on all threads and frees them again (after tune_allocator the pages stay mapped)."""
+        self.L.orc_prefault_heap.restype = C.c_uint64
+        return int(self.L.orc_prefault_heap(C.c_uint64(int(nbytes))))
+
     # ---- primitives ----
     def keccak256(self, data, pad=0x01):
         out = (C.c_uint8 * 32)()
