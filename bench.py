@@ -243,6 +243,7 @@ def run_reference(args, rank):
     the per-row cost moves with the size (the extrapolation to the full workload is then visible, not assumed)."""
     if rank != 0:
         return
+    t_arm0 = time.perf_counter()
     from valida_b200 import build as vbuild          # build helper only: the product library is NOT loaded in this process
     import oracle_binding
 
@@ -282,6 +283,12 @@ def run_reference(args, rank):
     # measured, not extrapolated; a size that fails (memory, temp space) is recorded and changes nothing above
     for extra in [int(x) for x in str(args.ref_extra_log_rows).split(",") if x.strip() and int(x) > 0]:
         if extra > full_log_rows or extra == log_rows:
+            continue
+        # the whole arm is meant to end within a few minutes: a further size is skipped when its projected time (per-row cost of the
+        # sample, with 50 % on top) would take the run past the budget
+        projected = 1.5 * (total / len(times)) * (1 << extra) / (1 << log_rows)
+        if time.perf_counter() - t_arm0 + projected > args.ref_budget_s:
+            sizes["2^%d" % extra] = {"skipped": "projected %.0f s would pass the arm's time budget of %d s" % (projected, args.ref_budget_s)}
             continue
         try:
             m2, p2 = _load_trace_files(workload, extra)
@@ -368,6 +375,7 @@ def main():
     ap.add_argument("--log-rows", type=int, default=22, help="log2 of the CPU-chip trace height for --workload fib / config5")
     ap.add_argument("--ref-log-rows", type=int, default=20, help="bounded sample size of the CPU reference arm (one proof per step)")
     ap.add_argument("--ref-extra-log-rows", default="18,22", help="reference arm: one extra proof at each of these sizes (comma separated; 0 = none)")
+    ap.add_argument("--ref-budget-s", type=int, default=480, help="reference arm: further sizes are skipped when they would take the run past this many seconds")
     ap.add_argument("--cpu-baseline-log-rows", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the independent-proofs-per-GPU figure")
