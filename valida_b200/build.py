@@ -72,7 +72,8 @@ def build(verbose=False, ptxas_info=False):
             list(ex.map(run, jobs))
     stale = not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
     if jobs or stale:
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", HOST_CXX, "-Xcompiler", "-fopenmp", "-lgomp", "-lcudart"]
+        # the arch is named at the link too: nvcc's device-link stub is otherwise an (empty) cubin for its default sm_52
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ccbin", HOST_CXX, "-Xcompiler", "-fopenmp", "-lgomp", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
