@@ -469,16 +469,15 @@ def main():
             rc[k] = c
             k += 1
     cfg = vb.StarkConfig(ctx, rc)
+    def watchdog():      # a rank that died leaves the others inside a collective, a kernel may never end: end the run instead of hanging the box
+        time.sleep(1500)
+        sys.stderr.write("bench.py: watchdog — the run did not finish within 1500 s\n")
+        os._exit(3)
+
+    threading.Thread(target=watchdog, daemon=True).start()
     if dist is not None:
         # N > 1: ONE proof per step, split across the ranks (row shards after one peer-store exchange; include/valida_b200.h)
         ctx.comm_init_from_torch()
-
-        def watchdog():      # a rank that died leaves the others inside a collective: end the run instead of hanging the box
-            time.sleep(1500)
-            sys.stderr.write("bench.py: watchdog — the run did not finish within 1500 s\n")
-            os._exit(3)
-
-        threading.Thread(target=watchdog, daemon=True).start()
 
     workload, log_rows = resolve_workload(args)
     t0 = time.perf_counter()
