@@ -336,6 +336,22 @@ def run_reference(args, rank):
             sizes["2^%d" % extra] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     full_key = "2^%d" % full_log_rows
     full_measured = full_key in sizes and "rows_per_s" in sizes[full_key]
+    # BASELINE.json configs[0], the reference's own test: prove_fibonacci n = 25 (192 cycles; CPU chip 2^8 rows, mul chip floor 2^10)
+    config1 = None
+    try:
+        m1, p1 = _load_trace_files("fibn25", 8)
+        config1 = {"program": "fib n=25 (basic/tests/test_prover.rs:474-487): 192 cycles, CPU trace 2^8 rows"}
+        for th in sorted({1, threads}):
+            orc.set_threads(th)
+            ts = []
+            for _ in range(7):
+                t0 = time.perf_counter()
+                pr = orc.prove(m1, p1, debug_checks=False)
+                ts.append(time.perf_counter() - t0)
+                del pr
+            config1["ms_per_proof_%d_threads" % th] = 1e3 * sorted(ts)[len(ts) // 2]
+    except Exception as exc:   # noqa: BLE001
+        config1 = {"error": "%s: %s" % (type(exc).__name__, exc)}
     sample = "%s at 2^%d CPU rows (one full prove per step; the arm's workload is 2^%d rows); %d OpenMP threads (fastest of %s in the warm-up steps, on this size) of %d host cores" % (
         workload, log_rows, full_log_rows, threads, cand, cores)
     line = {
@@ -346,7 +362,7 @@ def run_reference(args, rank):
                    "full_workload_measured_once": full_measured, "full_workload_rows_per_s": sizes[full_key]["rows_per_s"] if full_measured else None},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()}, "host": host,
+        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()}, "host": host, "config1_prove_fibonacci_n25": config1,
         "note": "the real reference (Rust + un-vendored Plonky3) cannot be built here; this is oracle/, the C++ restatement, OpenMP; rows/s at the measured sizes are in `sizes`",
     }
     emit(line)
@@ -383,6 +399,8 @@ def workload_program(workload, log_rows):
     if workload == "fib":
         n = fib_n_for_log_rows(log_rows)
         return vb.fib_program(n), "fib n=%d" % n
+    if workload == "fibn25":       # BASELINE.json configs[0]: prove_fibonacci of basic/tests/test_prover.rs (n = 25: 192 cycles, 2^8 CPU rows)
+        return vb.fib_program(25), "fib n=25"
     if workload == "config5":
         from programs import config5_program
 

@@ -22,6 +22,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert set(d["sizes"]) == {"2^10", "2^8", "2^12"} and all("rows_per_s" in v for v in d["sizes"].values())
     assert d["config"]["full_workload_measured_once"] is True and d["config"]["same_config"] is False
     assert d["host"]["usable"] >= 1 and d["host"]["affinity"] >= 1
+    assert d["config1_prove_fibonacci_n25"]["ms_per_proof_1_threads"] > 0           # BASELINE.json configs[0]
     # the product library is not loaded in the arm's own process (its traces arrive as files from a child process)
     assert "libvalida_b200" not in r.stderr
 
