@@ -352,6 +352,32 @@ def run_reference(args, rank):
             config1["ms_per_proof_%d_threads" % th] = 1e3 * sorted(ts)[len(ts) // 2]
     except Exception as exc:   # noqa: BLE001
         config1 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    # BASELINE.json configs[1] on the CPU: 2^20 x 64 NTT + inverse through the oracle's transform (natural order in and out; the
+    # call copies the matrix in and out, which is inside the figure: ~0.5 GB of memcpy against 44 butterfly sweeps)
+    config2 = None
+    try:
+        import ctypes
+        import numpy as np
+
+        hh, ww = 1 << 20, 64
+        rr = np.arange(hh, dtype=np.uint64)[:, None]
+        cc = np.arange(ww, dtype=np.uint64)[None, :]
+        x = ((rr * 64 + cc) * 0x9E3779B1 % 2013265921).astype(np.uint32)          # SURVEY 8(d) config 2 input
+        y = x.copy()
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        orc.set_threads(threads)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            orc.L.orc_dft(y.ctypes.data_as(u32p), ctypes.c_uint64(hh), ctypes.c_uint64(ww), 0)
+            orc.L.orc_dft(y.ctypes.data_as(u32p), ctypes.c_uint64(hh), ctypes.c_uint64(ww), 1)
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+        config2 = {"workload": "2^20 x 64 NTT + iNTT (oracle, natural order in/out)", "ms_forward_plus_inverse": 1e3 * best, "threads": threads,
+                   "achieved": 2 * 8.0 * hh * ww / best / 1e9, "unit": "GB/s", "bytes": "8*h*w per transform", "roundtrip_bit_exact": bool(np.array_equal(x, y))}
+        del x, y
+    except Exception as exc:   # noqa: BLE001
+        config2 = {"error": "%s: %s" % (type(exc).__name__, exc)}
     sample = "%s at 2^%d CPU rows (one full prove per step; the arm's workload is 2^%d rows); %d OpenMP threads (fastest of %s in the warm-up steps, on this size) of %d host cores" % (
         workload, log_rows, full_log_rows, threads, cand, cores)
     line = {
@@ -362,7 +388,7 @@ def run_reference(args, rank):
                    "full_workload_measured_once": full_measured, "full_workload_rows_per_s": sizes[full_key]["rows_per_s"] if full_measured else None},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()}, "host": host, "config1_prove_fibonacci_n25": config1,
+        "sizes": sizes, "thread_sweep_s": {str(k): min(v) for k, v in sweep.items()}, "host": host, "config1_prove_fibonacci_n25": config1, "config2_ntt": config2,
         "note": "the real reference (Rust + un-vendored Plonky3) cannot be built here; this is oracle/, the C++ restatement, OpenMP; rows/s at the measured sizes are in `sizes`",
     }
     emit(line)

@@ -23,6 +23,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["config"]["full_workload_measured_once"] is True and d["config"]["same_config"] is False
     assert d["host"]["usable"] >= 1 and d["host"]["affinity"] >= 1
     assert d["config1_prove_fibonacci_n25"]["ms_per_proof_1_threads"] > 0           # BASELINE.json configs[0]
+    assert d["config2_ntt"]["roundtrip_bit_exact"] is True and d["config2_ntt"]["achieved"] > 0      # configs[1] on the CPU
     # the product library is not loaded in the arm's own process (its traces arrive as files from a child process)
     assert "libvalida_b200" not in r.stderr
 
