@@ -371,7 +371,7 @@ def check(program, fp=0x1000, static_data=None):
     return vm, got
 
 
-@pytest.mark.parametrize("n", [0, 1, 3, 25, 582, 2339])
+@pytest.mark.parametrize("n", [0, 1, 3, 25, 582, 2339, 9359])       # 9359: 2^16 CPU rows, 2^18 memory rows — the sizes at which the generator uses all threads
 def test_fibonacci_traces_word_for_word(built, n):
     import valida_b200 as vb
 
