@@ -429,6 +429,9 @@ def test_the_references_other_test_programs_and_the_multi_chip_mixes(built):
     assert len(vm.lts) == 4 * 37 and len(vm.adds) == 3 * 37
     vm, _ = check(config5_program(40))
     assert len(vm.bits) == 6 * 40 and len(vm.subs) == 2 * 40 and len(vm.lts) == 4 * 40
+    big = ((1 << 16) - 8) // 15                                                # 2^16 CPU rows: every chip's multi-threaded row fill
+    vm, _ = check(config5_program(big))
+    assert vm.clock == 3 + 15 * big + 1 and len(vm.bits) == 6 * big
 
 
 def test_lt_family_edge_operands(built):
