@@ -5,6 +5,7 @@ import sys
 
 import torch
 import torch.distributed as dist
+import pytest
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -139,14 +140,16 @@ def _split_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_split_commit_plan_gloo(built):
+@pytest.mark.parametrize("world", [2, 4])
+def test_split_commit_plan_gloo(built, world):
+    # 4 ranks over matrices of 5 / 3 / 7 columns: some ranks extend no column of some matrix (empty shares in the exchange)
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 31500 + (os.getpid() % 2000)
-    mp.spawn(_split_worker, args=(2, port, out), nprocs=2, join=True)
-    for rank in range(2):
+    port = 31500 + (os.getpid() % 2000) + 7 * world
+    mp.spawn(_split_worker, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
         plans, ok_shards, same_root = out[rank]
-        assert plans[0] == plans[1]                                # the ranks agree on who extends what
+        assert all(pl == plans[0] for pl in plans)                 # the ranks agree on who extends what
         assert ok_shards and same_root
 
 
