@@ -272,3 +272,20 @@ def test_a_proof_that_shrinks_a_preprocessed_chip_is_a_shape_error(fib3, oracle)
     assert oracle.verify(bad, t.preprocessed) == -1
     with pytest.raises(Reject, match="shape"):
         machine_verify_py(bad, t.preprocessed, [int(x) for x in oracle.rc480], n_inter)
+
+
+@pytest.mark.parametrize("workload", ["static_data", "config5"])
+def test_the_python_verifier_accepts_proofs_of_the_other_workloads(built, oracle, workload):
+    # static data (prove_static_data: the static rows open the memory trace) and the multi-chip program (sub, lt family, and / or / xor
+    # active: other trace heights, so other groups of matrices per tree layer and other reduced-opening heights)
+    import programs
+    import valida_b200 as vb
+    from test_quotient_restatement import CHIPS
+
+    if workload == "static_data":
+        prog, cells = programs.static_data_program()
+        t = vb.run_program(prog, initial_fp=0x1000, static_data=cells)
+    else:
+        t = vb.run_program(programs.config5_program(6), initial_fp=0x1000)
+    proof = oracle.prove(t.main, t.preprocessed, debug_checks=False).cbor()
+    assert machine_verify_py(proof, t.preprocessed, [int(x) for x in oracle.rc480], [len(CHIPS[i]) for i in range(14)])
