@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--log-rows", type=int, default=22, help="log2 of the CPU-chip trace height for --workload fib / config5")
     ap.add_argument("--ref-log-rows", type=int, default=20, help="bounded sample size of the CPU reference arm (one proof per step)")
     ap.add_argument("--ref-extra-log-rows", default="18,22", help="reference arm: one extra proof at each of these sizes (comma separated; 0 = none)")
-    ap.add_argument("--ref-budget-s", type=int, default=480, help="reference arm: further sizes are skipped when they would take the run past this many seconds")
+    ap.add_argument("--ref-budget-s", type=int, default=300, help="reference arm: further sizes are skipped when they would take the run past this many seconds")
     ap.add_argument("--cpu-baseline-log-rows", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the independent-proofs-per-GPU figure")
